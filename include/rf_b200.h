@@ -1,0 +1,143 @@
+/*
+ * rf_b200.h — C-ABI of the B200-native Riffusion hot paths (librf_b200.so).
+ *
+ * The reference (riffusion/riffusion-hobby, pure Python) has no FFI; its seams are
+ * duck-typed Python callables.  Each entry point below replaces the arithmetic behind
+ * one of those seams and is what a ctypes binding in the reference would call
+ * (INTEGRATION.md shows the stub).  Citations are into /root/reference unless
+ * prefixed TA/ (= site-packages/torchaudio, the third-party package that holds the
+ * arithmetic of path (a)).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer (e.g. torch.Tensor.data_ptr()); the
+ *     caller allocates inputs, outputs and the workspace (size from *_workspace_bytes);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all functions return 0 on success, non-zero on error; rf_last_error() returns a
+ *     thread-local message.  There is NO CPU fallback: device entry points fail with
+ *     RF_ERR_CUDA when no sm_100 device is usable;
+ *   - no global mutable state: a plan is immutable after its first upload, so
+ *     concurrent calls on different streams with different workspaces are safe
+ *     (the reference shares one converter across a ThreadPool, riffusion/cli.py:172-204).
+ */
+#ifndef RF_B200_H
+#define RF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_OK 0
+#define RF_ERR_INVALID 1     /* bad argument / unsupported geometry */
+#define RF_ERR_CUDA 2        /* CUDA runtime error or no usable device */
+#define RF_ERR_UNSUPPORTED 3 /* valid reference parameters this build has no kernel for */
+
+typedef struct rf_plan rf_plan;
+
+/* Mirrors riffusion/spectrogram_params.py:8-81 (SpectrogramParams + derived n_fft /
+ * win_length / hop_length) and the MelScale arguments of
+ * riffusion/spectrogram_converter.py:75-99. */
+typedef struct rf_plan_desc {
+    int32_t sample_rate;  /* 44100 */
+    int32_t n_fft;        /* 17640  (padded_duration_ms) */
+    int32_t win_length;   /* 4410   (window_duration_ms) */
+    int32_t hop_length;   /* 441    (step_size_ms) */
+    int32_t n_mels;       /* 512    (num_frequencies) */
+    float f_min;          /* 0      (min_frequency) */
+    float f_max;          /* 10000  (max_frequency) */
+    int32_t mel_norm_slaney; /* 0: norm=None, 1: "slaney" (mel_scale_norm) */
+    int32_t mel_scale_slaney; /* 0: "htk", 1: "slaney" (mel_scale_type) */
+    int32_t full_band;    /* 0: prune STFT bins to the mel filterbank's support
+                             (rows of fb that are not identically zero);
+                             1: keep all n_fft/2+1 bins (generic GriffinLim input) */
+} rf_plan_desc;
+
+typedef struct rf_plan_info {
+    int32_t n_freq;      /* n_fft/2 + 1 */
+    int32_t n_live;      /* STFT bins carried through Griffin-Lim */
+    int32_t k_lo, k_hi;  /* smallest / largest live bin */
+    int32_t n_even;      /* live bins with even k (first in the private bin order) */
+    int32_t fb_nnz;      /* non-zeros of the mel filterbank */
+    int32_t chunk_frames; /* frames per overlap-add chunk used by the iSTFT kernel */
+} rf_plan_info;
+
+const char* rf_last_error(void);
+const char* rf_version(void);
+
+/* Build the host side of a plan (all tables in fp64, rounded once to fp32).
+ *   window : optional host float[win_length] (e.g. torch.hann_window, periodic) — NULL =
+ *            computed here as 0.5-0.5cos(2 pi n/win) (TA/transforms/_transforms.py:94).
+ *   fb     : optional host float[n_freq][n_mels], row-major, the torchaudio
+ *            melscale_fbanks matrix (TA/functional/functional.py:518-587) — NULL =
+ *            computed here following the same formula.
+ * Device tables are uploaded lazily by the first device call. */
+int rf_plan_create(const rf_plan_desc* desc, const float* window, const float* fb, rf_plan** out);
+void rf_plan_destroy(rf_plan* plan);
+int rf_plan_get_info(const rf_plan* plan, rf_plan_info* info);
+/* Copy a named host table (for tests): "bins" int32[n_live], "pp" uint32[n_live],
+ * "wt_fwd"/"wt_inv" float[4][win][2], "window" float[win], "fb" float[n_freq][n_mels],
+ * "pinv" float[n_freq][n_mels] (= min-norm inverse-mel operator, dense),
+ * "tri" double[3][n_mels] (Gram tridiagonal: sub, diag, super). Returns RF_ERR_INVALID if
+ * `bytes` does not match the table size. */
+int rf_plan_table(const rf_plan* plan, const char* name, void* dst, size_t bytes);
+
+/* ---- path (a), inverse: mel amplitudes -> waveform ---------------------------------
+ * replaces SpectrogramConverter.waveform_from_mel_amplitudes
+ * (riffusion/spectrogram_converter.py:187-204). */
+
+/* InverseMelScale.forward (TA/transforms/_transforms.py:491-512): relu(min-norm lstsq).
+ * d_mel f32[B][n_mels][T] -> d_lin f32[B][n_freq][T] (torchaudio layout). */
+int rf_inverse_mel(rf_plan* plan, const float* d_mel, int B, int T, float* d_lin, void* stream);
+
+/* GriffinLim.forward -> F.griffinlim (TA/functional/functional.py:255-353), power=1.
+ *   d_lin         f32[B][n_freq][T]  magnitudes (bins outside the plan's live set must be 0;
+ *                                    use a full_band plan for arbitrary input)
+ *   d_init_angles c64[B][n_freq][T]  initial "angles" (torch.rand(cfloat), :310) or NULL for
+ *                                    rand_init=False (all ones, :312)
+ *   d_wave        f32[B][hop*(T-1)]
+ * Requires hop*(T-1) > n_fft/2 (torch.stft reflect padding limit, same error as torch). */
+size_t rf_griffinlim_workspace_bytes(const rf_plan* plan, int B, int T);
+int rf_griffinlim(rf_plan* plan, const float* d_lin, const void* d_init_angles, int B, int T,
+                  int n_iter, float momentum, float* d_wave, void* d_workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Fused inverse-mel + Griffin-Lim (no [B][n_freq][T] intermediate). Requires a pruned
+ * (full_band=0) plan. Same workspace size as rf_griffinlim. */
+int rf_mel_to_wave(rf_plan* plan, const float* d_mel, const void* d_init_angles, int B, int T,
+                   int n_iter, float momentum, float* d_wave, void* d_workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- path (a), forward: waveform -> mel amplitudes ---------------------------------
+ * replaces SpectrogramConverter.mel_amplitudes_from_waveform
+ * (riffusion/spectrogram_converter.py:165-185): Spectrogram(power=None) -> abs -> MelScale.
+ * d_wave f32[B][L] -> d_mel f32[B][n_mels][T], T = 1 + L/hop. Requires L > n_fft/2. */
+int rf_stft_mel(rf_plan* plan, const float* d_wave, int B, int L, float* d_mel, void* stream);
+/* Complex STFT only (Spectrogram(power=None), TA/functional/functional.py:54-145):
+ * d_spec c64[B][n_freq][T]; bins outside the live set are written as 0 unless full_band. */
+int rf_stft(rf_plan* plan, const float* d_wave, int B, int L, void* d_spec, void* stream);
+/* MelScale.forward (TA/transforms/_transforms.py:407-419) on its own:
+ * d_spec f32[B][n_freq][T] -> d_mel f32[B][n_mels][T]. */
+int rf_mel_scale(rf_plan* plan, const float* d_spec, int B, int T, float* d_mel, void* stream);
+
+/* ---- image <-> spectrogram quantisation, int16 waveform --------------------------- */
+/* image_util.spectrogram_from_image (riffusion/util/image_util.py:59-110) after the
+ * P/L->RGB conversion: d_img u8[Hh][Ww][3] -> d_mel f32[C][Hh][Ww] (C = stereo?2:1),
+ * flip-Y, mono = R plane, stereo = G,B planes, ((255-u8)/255)^(1/power) * max_value. */
+int rf_image_to_mel(const uint8_t* d_img, int height, int width, int stereo, float power,
+                    float max_value, float* d_mel, void* stream);
+/* image_util.image_from_spectrogram (riffusion/util/image_util.py:13-56):
+ * d_mel f32[C][Hh][Ww] -> d_img u8[Hh][Ww][3]; d_max receives max over all channels
+ * (written to EXIF MAX_VALUE by spectrogram_image_converter.py:59). d_scratch: >= 4 bytes. */
+int rf_mel_to_image(const float* d_mel, int channels, int height, int width, float power,
+                    uint8_t* d_img, float* d_max, void* stream);
+/* audio_util.audio_from_waveform(normalize=True) (riffusion/util/audio_util.py:13-28):
+ * d_wave f32[C][L] -> d_pcm i16[L][C]; x *= 32767/max|x| over all channels, truncate. */
+int rf_wave_to_int16(const float* d_wave, int channels, int L, int normalize, int16_t* d_pcm,
+                     float* d_scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_B200_H */

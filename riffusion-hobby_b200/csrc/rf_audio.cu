@@ -1,0 +1,789 @@
+// Path (a) kernels + C-ABI: STFT / iSTFT / Griffin-Lim / mel / inverse mel / quantisation.
+// sm_100a only.  See DESIGN.md §3 for the algorithm and data layout.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rf_common.h"
+#include "rf_gl_phases.cuh"
+#include "rf_plan.h"
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_rf_err;
+void rf_set_error(const std::string& msg) { g_rf_err = msg; }
+int rf_fail(int code, const std::string& msg) {
+    g_rf_err = msg;
+    return code;
+}
+extern "C" const char* rf_last_error(void) { return g_rf_err.c_str(); }
+extern "C" const char* rf_version(void) { return "rf_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------
+// plan object
+// ---------------------------------------------------------------------------------------
+struct rf_plan {
+    rf_plan_host h;
+    std::mutex mu;
+    bool uploaded = false;
+    int device = -1;
+    rf_c32* d_wt_fwd = nullptr;
+    rf_c32* d_wt_inv = nullptr;
+    uint32_t* d_pp = nullptr;
+    int32_t* d_bins = nullptr;
+    int32_t* d_jofk = nullptr;
+    float* d_win2 = nullptr;
+    int32_t* d_melcol_ptr = nullptr;
+    int32_t* d_melcol_j = nullptr;
+    float* d_melcol_w = nullptr;
+    int32_t* d_binrow_ptr = nullptr;
+    int32_t* d_binrow_m = nullptr;
+    float* d_binrow_w = nullptr;
+    double* d_thomas = nullptr;  // [3][n_mels]: sub, cprime, inv_den
+    std::vector<void*> owned;
+};
+
+template <typename T>
+static cudaError_t upload(rf_plan* p, T** dst, const void* src, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    p->owned.push_back(*dst);
+    if (count) e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int rf_plan_upload(rf_plan* p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->uploaded) return RF_OK;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return rf_fail(RF_ERR_CUDA,
+                       "rf_b200: no CUDA device available (this library has no CPU fallback)");
+    int dev = 0;
+    RF_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    RF_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return rf_fail(RF_ERR_CUDA, std::string("rf_b200: kernels are built for sm_100a only; device is ") +
+                                        prop.name);
+    const rf_plan_host& h = p->h;
+    RF_CUDA_TRY(upload(p, &p->d_wt_fwd, h.wt_fwd.data(), h.wt_fwd.size() / 2));
+    RF_CUDA_TRY(upload(p, &p->d_wt_inv, h.wt_inv.data(), h.wt_inv.size() / 2));
+    RF_CUDA_TRY(upload(p, &p->d_pp, h.pp.data(), h.pp.size()));
+    RF_CUDA_TRY(upload(p, &p->d_bins, h.bins.data(), h.bins.size()));
+    RF_CUDA_TRY(upload(p, &p->d_jofk, h.jofk.data(), h.jofk.size()));
+    std::vector<float> w2(h.W);
+    for (int i = 0; i < h.W; ++i) w2[i] = h.window[i] * h.window[i];
+    RF_CUDA_TRY(upload(p, &p->d_win2, w2.data(), w2.size()));
+    RF_CUDA_TRY(upload(p, &p->d_melcol_ptr, h.melcol_ptr.data(), h.melcol_ptr.size()));
+    RF_CUDA_TRY(upload(p, &p->d_melcol_j, h.melcol_j.data(), h.melcol_j.size()));
+    RF_CUDA_TRY(upload(p, &p->d_melcol_w, h.melcol_w.data(), h.melcol_w.size()));
+    RF_CUDA_TRY(upload(p, &p->d_binrow_ptr, h.binrow_ptr.data(), h.binrow_ptr.size()));
+    RF_CUDA_TRY(upload(p, &p->d_binrow_m, h.binrow_m.data(), h.binrow_m.size()));
+    RF_CUDA_TRY(upload(p, &p->d_binrow_w, h.binrow_w.data(), h.binrow_w.size()));
+    std::vector<double> th(3 * static_cast<size_t>(h.n_mels));
+    for (int i = 0; i < h.n_mels; ++i) {
+        th[i] = h.tri[i];                          // sub
+        th[h.n_mels + i] = h.thomas[i];            // cprime
+        th[2 * h.n_mels + i] = h.thomas[h.n_mels + i];  // inv_den
+    }
+    RF_CUDA_TRY(upload(p, &p->d_thomas, th.data(), th.size()));
+    p->device = dev;
+    p->uploaded = true;
+    return RF_OK;
+}
+
+extern "C" int rf_plan_create(const rf_plan_desc* desc, const float* window, const float* fb,
+                              rf_plan** out) {
+    if (!desc || !out) return rf_fail(RF_ERR_INVALID, "rf_plan_create: null argument");
+    rf_plan* p = new rf_plan();
+    int code = RF_OK;
+    std::string err = rf_plan_build_host(*desc, window, fb, p->h, code);
+    if (code != RF_OK) {
+        delete p;
+        return rf_fail(code, err);
+    }
+    *out = p;
+    return RF_OK;
+}
+
+extern "C" void rf_plan_destroy(rf_plan* p) {
+    if (!p) return;
+    for (void* q : p->owned) cudaFree(q);
+    delete p;
+}
+
+extern "C" int rf_plan_get_info(const rf_plan* p, rf_plan_info* info) {
+    if (!p || !info) return rf_fail(RF_ERR_INVALID, "rf_plan_get_info: null argument");
+    info->n_freq = p->h.F;
+    info->n_live = p->h.n_live;
+    info->k_lo = p->h.k_lo;
+    info->k_hi = p->h.k_hi;
+    info->n_even = p->h.n_even;
+    info->fb_nnz = p->h.fb_nnz;
+    info->chunk_frames = RF_CHUNK;
+    return RF_OK;
+}
+
+extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size_t bytes) {
+    if (!p || !name || !dst) return rf_fail(RF_ERR_INVALID, "rf_plan_table: null argument");
+    const rf_plan_host& h = p->h;
+    const void* src = nullptr;
+    size_t n = 0;
+    std::vector<float> tmp;
+    const std::string s(name);
+    if (s == "bins") { src = h.bins.data(); n = h.bins.size() * 4; }
+    else if (s == "pp") { src = h.pp.data(); n = h.pp.size() * 4; }
+    else if (s == "wt_fwd") { src = h.wt_fwd.data(); n = h.wt_fwd.size() * 4; }
+    else if (s == "wt_inv") { src = h.wt_inv.data(); n = h.wt_inv.size() * 4; }
+    else if (s == "window") { src = h.window.data(); n = h.window.size() * 4; }
+    else if (s == "fb") { src = h.fb.data(); n = h.fb.size() * 4; }
+    else if (s == "tri") { src = h.tri.data(); n = h.tri.size() * 8; }
+    else if (s == "pinv") {
+        // dense min-norm operator P = fb (fb^T fb)^{-1}, built column by column with the
+        // same Thomas factors the kernel uses (fp64), for tests
+        const int M = h.n_mels;
+        std::vector<double> ginv(static_cast<size_t>(M) * M);
+        std::vector<double> y(M);
+        for (int col = 0; col < M; ++col) {
+            for (int i = 0; i < M; ++i) {
+                const double rhs = (i == col) ? 1.0 : 0.0;
+                y[i] = (rhs - (i ? h.tri[i] * y[i - 1] : 0.0)) * h.thomas[M + i];
+            }
+            for (int i = M - 2; i >= 0; --i) y[i] -= h.thomas[i] * y[i + 1];
+            for (int i = 0; i < M; ++i) ginv[static_cast<size_t>(i) * M + col] = y[i];
+        }
+        tmp.assign(static_cast<size_t>(h.F) * M, 0.f);
+        for (int j = 0; j < h.n_live; ++j) {
+            const int k = h.bins[j];
+            for (int m = 0; m < M; ++m) {
+                double acc = 0;
+                for (int e = h.binrow_ptr[j]; e < h.binrow_ptr[j + 1]; ++e)
+                    acc += static_cast<double>(h.binrow_w[e]) * ginv[static_cast<size_t>(h.binrow_m[e]) * M + m];
+                tmp[static_cast<size_t>(k) * M + m] = static_cast<float>(acc);
+            }
+        }
+        src = tmp.data();
+        n = tmp.size() * 4;
+    } else
+        return rf_fail(RF_ERR_INVALID, "rf_plan_table: unknown table " + s);
+    if (n != bytes)
+        return rf_fail(RF_ERR_INVALID, "rf_plan_table: size mismatch for " + s + ": have " +
+                                           std::to_string(n) + " bytes, caller gave " + std::to_string(bytes));
+    std::memcpy(dst, src, n);
+    return RF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+constexpr int RF_NT = 224;  // threads per CTA of the FFT kernels (441 = 2*224 - 7 radix-10 items)
+
+// ---- iSTFT of one overlap-add chunk (G frames) of one clip, one r-group ------------------
+// grid (nchunks*2, B). Output: part[b][g][chunk][PL] partial overlap-add sums.
+__global__ void __launch_bounds__(RF_NT, 2)
+k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __restrict__ cur,
+              const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL,
+              int nchunks, float* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
+    float* ola = reinterpret_cast<float*>(smem_raw + 2 * RF_PW * sizeof(rf_c32));
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x & 1, chunk = blockIdx.x >> 1, b = blockIdx.y;
+    const int f0 = chunk * G;
+    const int nf = min(G, T - f0);
+    const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
+    for (int i = tid; i < PL; i += RF_NT) ola[i] = 0.f;
+    const size_t row = static_cast<size_t>(tb.n_live);
+    for (int pr = 0; 2 * pr < nf; ++pr) {
+        const int t0 = f0 + 2 * pr;
+        const bool has1 = (2 * pr + 1) < nf;
+        rf_istft_zero(tid, RF_NT, V);
+        __syncthreads();
+        rf_istft_in in;
+        const size_t o0 = (static_cast<size_t>(b) * T + t0) * row;
+        in.S0 = S + o0;
+        in.cur0 = cur + o0;
+        in.prev0 = prev ? prev + o0 : nullptr;
+        in.S1 = has1 ? S + o0 + row : nullptr;
+        in.cur1 = cur + o0 + row;
+        in.prev1 = prev ? prev + o0 + row : nullptr;
+        in.mode = mode;
+        in.momentum = momentum;
+        rf_istft_load(tid, RF_NT, V, tb, j0, j1, in);
+        __syncthreads();
+        rf_pass_c<true>(tid, RF_NT, V);
+        __syncthreads();
+        rf_pass_b<true>(tid, RF_NT, V);
+        __syncthreads();
+        rf_istft_pass_a(tid, RF_NT, V, ola + 2 * pr * tb.hop, tb, g, has1);
+        __syncthreads();
+    }
+    float* dst = part + ((static_cast<size_t>(b) * 2 + g) * nchunks + chunk) * PL;
+    for (int i = tid; i < PL; i += RF_NT) dst[i] = ola[i];
+}
+
+// ---- overlap-add assembly: x[b][i] = sum(parts) / envelope, kept region only --------------
+// (torch.istft: y / window_envelope, trimmed by n_fft/2 each side)
+__global__ void k_ola_assemble(const float* __restrict__ part, const float* __restrict__ win2,
+                               int T, int G, int PL, int nchunks, int H, int W, int L,
+                               float* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= L) return;
+    x[static_cast<size_t>(b) * L + i] =
+        rf_ola_sample(i, part + static_cast<size_t>(b) * 2 * nchunks * PL, win2, T, G, PL, nchunks, H, W);
+}
+
+// ---- STFT of one frame pair, one r-group ------------------------------------------------
+// grid (npairs*2, B). x: [B][L] un-padded signal (reflect padding applied on the fly).
+__global__ void __launch_bounds__(RF_NT, 2)
+k_stft_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, rf_c32* __restrict__ R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
+    float* xs = reinterpret_cast<float*>(smem_raw + 2 * RF_PW * sizeof(rf_c32));
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x & 1, pr = blockIdx.x >> 1, b = blockIdx.y;
+    const int t0 = 2 * pr;
+    const bool has1 = t0 + 1 < T;
+    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop, has1);
+    __syncthreads();
+    rf_stft_pass_a(tid, RF_NT, V, xs, tb, g);
+    __syncthreads();
+    rf_pass_b<false>(tid, RF_NT, V);
+    __syncthreads();
+    rf_pass_c<false>(tid, RF_NT, V);
+    __syncthreads();
+    const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
+    rf_c32* out0 = R + (static_cast<size_t>(b) * T + t0) * tb.n_live;
+    rf_stft_post(tid, RF_NT, V, tb, j0, j1, out0, has1 ? out0 + tb.n_live : nullptr);
+}
+
+// ---- STFT + |.| + mel of one frame pair (both groups in one CTA) -------------------------
+__global__ void __launch_bounds__(RF_NT, 1)
+k_stft_mel_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int n_mels,
+                const int32_t* __restrict__ melcol_ptr, const int32_t* __restrict__ melcol_j,
+                const float* __restrict__ melcol_w, float* __restrict__ mel) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
+    float* xs = reinterpret_cast<float*>(smem_raw + 2 * RF_PW * sizeof(rf_c32));
+    rf_c32* spec0 = reinterpret_cast<rf_c32*>(xs + RF_PW + tb.hop + ((RF_PW + tb.hop) & 1));
+    rf_c32* spec1 = spec0 + tb.n_live;
+    const int tid = threadIdx.x;
+    const int pr = blockIdx.x, b = blockIdx.y;
+    const int t0 = 2 * pr;
+    const bool has1 = t0 + 1 < T;
+    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop, has1);
+    __syncthreads();
+    for (int g = 0; g < 2; ++g) {
+        rf_stft_pass_a(tid, RF_NT, V, xs, tb, g);
+        __syncthreads();
+        rf_pass_b<false>(tid, RF_NT, V);
+        __syncthreads();
+        rf_pass_c<false>(tid, RF_NT, V);
+        __syncthreads();
+        const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
+        rf_stft_post(tid, RF_NT, V, tb, j0, j1, spec0, spec1);
+        __syncthreads();
+    }
+    // magnitude in place (spec.x = |X|), torch.abs on complex64
+    for (int j = tid; j < tb.n_live; j += RF_NT) {
+        spec0[j].x = hypotf(spec0[j].x, spec0[j].y);
+        spec1[j].x = hypotf(spec1[j].x, spec1[j].y);
+    }
+    __syncthreads();
+    // mel[m] = sum_k fb[k][m] |X[k]|   (MelScale.forward, TA/transforms/_transforms.py:417)
+    for (int it = tid; it < 2 * n_mels; it += RF_NT) {
+        const int f = it / n_mels, m = it - f * n_mels;
+        if (f == 1 && !has1) continue;
+        const rf_c32* sp = f ? spec1 : spec0;
+        float acc = 0.f;
+        for (int e = melcol_ptr[m]; e < melcol_ptr[m + 1]; ++e) acc += melcol_w[e] * sp[melcol_j[e]].x;
+        mel[(static_cast<size_t>(b) * n_mels + m) * T + t0 + f] = acc;
+    }
+}
+
+// ---- layout permutations between torchaudio's [B][F][T] and the private [B][T][n_live] ----
+template <typename TT>
+__global__ void k_gather_FT_to_TJ(const TT* __restrict__ src, const int32_t* __restrict__ bins,
+                                  int F, int T, int n_live, TT* __restrict__ dst) {
+    __shared__ TT tile[32][33];
+    const int b = blockIdx.z;
+    const int j0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    {
+        const int j = j0 + threadIdx.y, t = t0 + threadIdx.x;
+        if (j < n_live && t < T)
+            tile[threadIdx.y][threadIdx.x] = src[(static_cast<size_t>(b) * F + bins[j]) * T + t];
+    }
+    __syncthreads();
+    {
+        const int t = t0 + threadIdx.y, j = j0 + threadIdx.x;
+        if (j < n_live && t < T)
+            dst[(static_cast<size_t>(b) * T + t) * n_live + j] = tile[threadIdx.x][threadIdx.y];
+    }
+}
+
+template <typename TT>
+__global__ void k_scatter_TJ_to_FT(const TT* __restrict__ src, const int32_t* __restrict__ bins,
+                                   int F, int T, int n_live, TT* __restrict__ dst) {
+    __shared__ TT tile[32][33];
+    const int b = blockIdx.z;
+    const int j0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    {
+        const int t = t0 + threadIdx.y, j = j0 + threadIdx.x;
+        if (j < n_live && t < T)
+            tile[threadIdx.y][threadIdx.x] = src[(static_cast<size_t>(b) * T + t) * n_live + j];
+    }
+    __syncthreads();
+    {
+        const int j = j0 + threadIdx.y, t = t0 + threadIdx.x;
+        if (j < n_live && t < T)
+            dst[(static_cast<size_t>(b) * F + bins[j]) * T + t] = tile[threadIdx.x][threadIdx.y];
+    }
+}
+
+__global__ void k_fill_c32(rf_c32* p, size_t n, float re, float im) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = c_make(re, im);
+}
+
+// ---- inverse mel: relu(fb (fb^T fb)^-1 mel) per time column -------------------------------
+// CTA = 32 time columns of one clip.  Phase 1: stage mel[:, t0:t0+32] in smem.  Phase 2: warp 0
+// solves the tridiagonal system per column in fp64 (Thomas).  Phase 3: sparse fb apply + relu.
+// out_mode 0: S[b][t][j] (private), 1: lin[b][k][t] (torchaudio layout; dead rows pre-zeroed)
+__global__ void __launch_bounds__(256)
+k_inverse_mel(const float* __restrict__ mel, int T, int n_mels, int n_live, int F,
+              const double* __restrict__ thomas, const int32_t* __restrict__ binrow_ptr,
+              const int32_t* __restrict__ binrow_m, const float* __restrict__ binrow_w,
+              const int32_t* __restrict__ bins, int out_mode, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* ys = reinterpret_cast<float*>(smem_raw);  // [n_mels][33]
+    const int b = blockIdx.y, t0 = blockIdx.x * 32;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_mels * 32; i += blockDim.x) {
+        const int m = i >> 5, tl = i & 31;
+        ys[m * 33 + tl] = (t0 + tl < T) ? mel[(static_cast<size_t>(b) * n_mels + m) * T + t0 + tl] : 0.f;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const double* sub = thomas;
+        const double* cp = thomas + n_mels;
+        const double* idn = thomas + 2 * n_mels;
+        double prevv = 0.0;
+        for (int m = 0; m < n_mels; ++m) {
+            const double v = (static_cast<double>(ys[m * 33 + tid]) - sub[m] * prevv) * idn[m];
+            ys[m * 33 + tid] = static_cast<float>(v);  // forward sweep kept in fp32 storage
+            prevv = v;
+        }
+        // back substitution: re-run in fp64 from the stored forward values
+        double nxt = static_cast<double>(ys[(n_mels - 1) * 33 + tid]);
+        for (int m = n_mels - 2; m >= 0; --m) {
+            const double v = static_cast<double>(ys[m * 33 + tid]) - cp[m] * nxt;
+            ys[m * 33 + tid] = static_cast<float>(v);
+            nxt = v;
+        }
+    }
+    __syncthreads();
+    if (out_mode == 0) {
+        for (int tl = 0; tl < 32 && t0 + tl < T; ++tl) {
+            float* row = out + (static_cast<size_t>(b) * T + t0 + tl) * n_live;
+            for (int j = tid; j < n_live; j += blockDim.x) {
+                float acc = 0.f;
+                for (int e = binrow_ptr[j]; e < binrow_ptr[j + 1]; ++e)
+                    acc += binrow_w[e] * ys[binrow_m[e] * 33 + tl];
+                row[j] = fmaxf(acc, 0.f);
+            }
+        }
+    } else {
+        const int tl = tid & 31;
+        for (int j = tid >> 5; j < n_live; j += blockDim.x >> 5) {
+            float acc = 0.f;
+            for (int e = binrow_ptr[j]; e < binrow_ptr[j + 1]; ++e)
+                acc += binrow_w[e] * ys[binrow_m[e] * 33 + tl];
+            if (t0 + tl < T) out[(static_cast<size_t>(b) * F + bins[j]) * T + t0 + tl] = fmaxf(acc, 0.f);
+        }
+    }
+}
+
+// ---- MelScale on its own: mel[b][m][t] = sum_k fb[k][m] spec[b][k][t] ---------------------
+__global__ void k_mel_scale(const float* __restrict__ spec, int F, int T, int n_mels,
+                            const int32_t* __restrict__ melcol_ptr, const int32_t* __restrict__ melcol_j,
+                            const float* __restrict__ melcol_w, const int32_t* __restrict__ bins,
+                            float* __restrict__ mel) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    float acc = 0.f;
+    for (int e = melcol_ptr[m]; e < melcol_ptr[m + 1]; ++e)
+        acc += melcol_w[e] * spec[(static_cast<size_t>(b) * F + bins[melcol_j[e]]) * T + t];
+    mel[(static_cast<size_t>(b) * n_mels + m) * T + t] = acc;
+}
+
+// ---- image <-> mel quantisation, int16 -------------------------------------------------------
+__global__ void k_image_to_mel(const uint8_t* __restrict__ img, int Hh, int Ww, int stereo, float inv_power,
+                               float max_value, float* __restrict__ mel) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;  // output row (mel bin, 0 = lowest) = image row Hh-1-y
+    const int c = blockIdx.z;
+    if (x >= Ww) return;
+    const int plane = stereo ? (1 + c) : 0;
+    const uint8_t u = img[(static_cast<size_t>(Hh - 1 - y) * Ww + x) * 3 + plane];
+    float d = 255.0f - static_cast<float>(u);
+    d = d / 255.0f;
+    d = powf(d, inv_power);
+    mel[(static_cast<size_t>(c) * Hh + y) * Ww + x] = d * max_value;
+}
+
+__global__ void k_absmax(const float* __restrict__ v, size_t n, int use_abs, float* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float a = use_abs ? fabsf(v[i]) : v[i];
+        m = fmaxf(m, a);
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // values are >= 0 so the int ordering of the bit patterns equals the float ordering
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+__global__ void k_mel_to_image(const float* __restrict__ mel, int C, int Hh, int Ww, float power,
+                               const float* __restrict__ maxv, uint8_t* __restrict__ img) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;  // image row
+    if (x >= Ww) return;
+    const float mx = *maxv;
+    uint8_t px[3];
+    for (int c = 0; c < C; ++c) {
+        float d = mel[(static_cast<size_t>(c) * Hh + (Hh - 1 - y)) * Ww + x] / mx;
+        d = powf(d, power);
+        d = d * 255.0f;
+        d = 255.0f - d;
+        px[c] = static_cast<uint8_t>(d);  // truncation (numpy astype(uint8) on [0,255])
+    }
+    uint8_t* o = img + (static_cast<size_t>(y) * Ww + x) * 3;
+    if (C == 1) {
+        o[0] = o[1] = o[2] = px[0];
+    } else {
+        o[0] = 0;
+        o[1] = px[0];
+        o[2] = px[1];
+    }
+}
+
+__global__ void k_wave_to_int16(const float* __restrict__ w, int C, int L, const float* __restrict__ maxv,
+                                int normalize, int16_t* __restrict__ pcm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    // samples *= iinfo(int16).max / max|samples|  (audio_util.py:24): the scale is computed in
+    // fp32 (numpy float32 scalar arithmetic), then multiplied.
+    const float scale = normalize ? (32767.0f / *maxv) : 1.0f;
+    for (int c = 0; c < C; ++c) {
+        const float v = w[static_cast<size_t>(c) * L + i] * scale;
+        pcm[static_cast<size_t>(i) * C + c] = static_cast<int16_t>(v);  // truncation toward zero
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------
+static rf_gl_tables make_tables(const rf_plan* p) {
+    rf_gl_tables tb;
+    tb.wt_fwd = p->d_wt_fwd;
+    tb.wt_inv = p->d_wt_inv;
+    tb.pp = p->d_pp;
+    tb.n_live = p->h.n_live;
+    tb.n_even = p->h.n_even;
+    tb.hop = p->h.H;
+    return tb;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct gl_ws {
+    float* S;
+    rf_c32* R[2];
+    float* part;
+    size_t total;
+    int nchunks, PL;
+};
+
+static gl_ws gl_layout(const rf_plan* p, int B, int T, void* base) {
+    gl_ws w;
+    const size_t bt = static_cast<size_t>(B) * T * p->h.n_live;
+    w.nchunks = (T + RF_CHUNK - 1) / RF_CHUNK;
+    w.PL = (RF_CHUNK - 1) * p->h.H + p->h.W;
+    size_t off = 0;
+    unsigned char* b = static_cast<unsigned char*>(base);
+    w.S = reinterpret_cast<float*>(b + off);
+    off += align256(bt * 4);
+    w.R[0] = reinterpret_cast<rf_c32*>(b + off);
+    off += align256(bt * 8);
+    w.R[1] = reinterpret_cast<rf_c32*>(b + off);
+    off += align256(bt * 8);
+    w.part = reinterpret_cast<float*>(b + off);
+    off += align256(static_cast<size_t>(B) * 2 * w.nchunks * w.PL * 4);
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t rf_griffinlim_workspace_bytes(const rf_plan* p, int B, int T) {
+    if (!p || B <= 0 || T <= 0) return 0;
+    return gl_layout(p, B, T, nullptr).total;
+}
+
+static int check_T(const rf_plan* p, int T, const char* who) {
+    const int L = p->h.H * (T - 1);
+    if (T < 1 || L <= p->h.N / 2)
+        return rf_fail(RF_ERR_INVALID,
+                       std::string(who) + ": Padding size should be less than the corresponding input "
+                       "dimension (hop*(T-1) = " + std::to_string(L) + " must exceed n_fft/2 = " +
+                           std::to_string(p->h.N / 2) + ")");
+    return RF_OK;
+}
+
+static int set_smem_attrs() {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(k_istft_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(k_stft_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(k_stft_mel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(k_inverse_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    if (err != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+    return RF_OK;
+}
+
+static int launch_inverse_mel(rf_plan* p, const float* d_mel, int B, int T, int out_mode, float* out,
+                              cudaStream_t st) {
+    const rf_plan_host& h = p->h;
+    const size_t smem = static_cast<size_t>(h.n_mels) * 33 * 4;
+    dim3 grid((T + 31) / 32, B);
+    k_inverse_mel<<<grid, 256, smem, st>>>(d_mel, T, h.n_mels, h.n_live, h.F, p->d_thomas, p->d_binrow_ptr,
+                                           p->d_binrow_m, p->d_binrow_w, p->d_bins, out_mode, out);
+    RF_CUDA_LAUNCH_CHECK("k_inverse_mel");
+    return RF_OK;
+}
+
+// Griffin-Lim main loop on a prepared workspace (S and initial angles in R[1]).
+static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float momentum_in, float* d_wave,
+                   cudaStream_t st) {
+    const rf_plan_host& h = p->h;
+    const rf_gl_tables tb = make_tables(p);
+    const int L = h.H * (T - 1);
+    // momentum = momentum / (1 + momentum)  (TA/functional/functional.py:300), fp32 like python float->tensor op
+    const float m = static_cast<float>(static_cast<double>(momentum_in) / (1.0 + static_cast<double>(momentum_in)));
+    const size_t smem_i = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(w.PL) * 4;
+    const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
+    const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
+    for (int it = 0; it <= n_iter; ++it) {
+        const rf_c32* cur;
+        const rf_c32* prev = nullptr;
+        int mode;
+        if (it == 0) {
+            cur = w.R[1];
+            mode = 0;
+        } else {
+            cur = w.R[(it - 1) & 1];
+            mode = 1;
+            if (it >= 2 && m != 0.f) prev = w.R[it & 1];
+        }
+        k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
+                                                     w.part);
+        RF_CUDA_LAUNCH_CHECK("k_istft_chunk");
+        k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, p->d_win2, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L,
+                                               d_wave);
+        RF_CUDA_LAUNCH_CHECK("k_ola_assemble");
+        if (it == n_iter) break;
+        k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, w.R[it & 1]);
+        RF_CUDA_LAUNCH_CHECK("k_stft_pair");
+    }
+    return RF_OK;
+}
+
+static int gl_prepare_angles(rf_plan* p, const gl_ws& w, const void* d_init_angles, int B, int T,
+                             cudaStream_t st) {
+    const rf_plan_host& h = p->h;
+    if (d_init_angles) {
+        dim3 grid((h.n_live + 31) / 32, (T + 31) / 32, B), blk(32, 32);
+        k_gather_FT_to_TJ<float2><<<grid, blk, 0, st>>>(static_cast<const float2*>(d_init_angles), p->d_bins,
+                                                        h.F, T, h.n_live, reinterpret_cast<float2*>(w.R[1]));
+        RF_CUDA_LAUNCH_CHECK("k_gather_FT_to_TJ<angles>");
+    } else {
+        const size_t n = static_cast<size_t>(B) * T * h.n_live;
+        k_fill_c32<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(w.R[1], n, 1.f, 0.f);
+        RF_CUDA_LAUNCH_CHECK("k_fill_c32");
+    }
+    return RF_OK;
+}
+
+extern "C" int rf_griffinlim(rf_plan* p, const float* d_lin, const void* d_init_angles, int B, int T,
+                             int n_iter, float momentum, float* d_wave, void* d_ws, size_t ws_bytes,
+                             void* stream) {
+    if (!p || !d_lin || !d_wave || !d_ws || B <= 0 || n_iter < 0)
+        return rf_fail(RF_ERR_INVALID, "rf_griffinlim: bad argument");
+    if (!(momentum >= 0.f && momentum < 1.f))
+        return rf_fail(RF_ERR_INVALID, "momentum must be in range [0, 1). Found: " + std::to_string(momentum));
+    int rc = check_T(p, T, "rf_griffinlim");
+    if (rc) return rc;
+    if ((rc = rf_plan_upload(p))) return rc;
+    if ((rc = set_smem_attrs())) return rc;
+    const gl_ws w = gl_layout(p, B, T, d_ws);
+    if (ws_bytes < w.total) return rf_fail(RF_ERR_INVALID, "rf_griffinlim: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const rf_plan_host& h = p->h;
+    dim3 grid((h.n_live + 31) / 32, (T + 31) / 32, B), blk(32, 32);
+    k_gather_FT_to_TJ<float><<<grid, blk, 0, st>>>(d_lin, p->d_bins, h.F, T, h.n_live, w.S);
+    RF_CUDA_LAUNCH_CHECK("k_gather_FT_to_TJ<lin>");
+    if ((rc = gl_prepare_angles(p, w, d_init_angles, B, T, st))) return rc;
+    return gl_loop(p, w, B, T, n_iter, momentum, d_wave, st);
+}
+
+extern "C" int rf_mel_to_wave(rf_plan* p, const float* d_mel, const void* d_init_angles, int B, int T,
+                              int n_iter, float momentum, float* d_wave, void* d_ws, size_t ws_bytes,
+                              void* stream) {
+    if (!p || !d_mel || !d_wave || !d_ws || B <= 0 || n_iter < 0)
+        return rf_fail(RF_ERR_INVALID, "rf_mel_to_wave: bad argument");
+    if (!(momentum >= 0.f && momentum < 1.f))
+        return rf_fail(RF_ERR_INVALID, "momentum must be in range [0, 1). Found: " + std::to_string(momentum));
+    int rc = check_T(p, T, "rf_mel_to_wave");
+    if (rc) return rc;
+    if ((rc = rf_plan_upload(p))) return rc;
+    if ((rc = set_smem_attrs())) return rc;
+    const gl_ws w = gl_layout(p, B, T, d_ws);
+    if (ws_bytes < w.total) return rf_fail(RF_ERR_INVALID, "rf_mel_to_wave: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_inverse_mel(p, d_mel, B, T, 0, w.S, st))) return rc;
+    if ((rc = gl_prepare_angles(p, w, d_init_angles, B, T, st))) return rc;
+    return gl_loop(p, w, B, T, n_iter, momentum, d_wave, st);
+}
+
+extern "C" int rf_inverse_mel(rf_plan* p, const float* d_mel, int B, int T, float* d_lin, void* stream) {
+    if (!p || !d_mel || !d_lin || B <= 0 || T <= 0) return rf_fail(RF_ERR_INVALID, "rf_inverse_mel: bad argument");
+    int rc = rf_plan_upload(p);
+    if (rc) return rc;
+    if ((rc = set_smem_attrs())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RF_CUDA_TRY(cudaMemsetAsync(d_lin, 0, static_cast<size_t>(B) * p->h.F * T * 4, st));
+    return launch_inverse_mel(p, d_mel, B, T, 1, d_lin, st);
+}
+
+static int check_L(const rf_plan* p, int L, const char* who) {
+    if (L <= p->h.N / 2)
+        return rf_fail(RF_ERR_INVALID,
+                       std::string(who) + ": Padding size should be less than the corresponding input "
+                       "dimension (L = " + std::to_string(L) + " must exceed n_fft/2 = " +
+                           std::to_string(p->h.N / 2) + ")");
+    return RF_OK;
+}
+
+extern "C" int rf_stft_mel(rf_plan* p, const float* d_wave, int B, int L, float* d_mel, void* stream) {
+    if (!p || !d_wave || !d_mel || B <= 0) return rf_fail(RF_ERR_INVALID, "rf_stft_mel: bad argument");
+    int rc = check_L(p, L, "rf_stft_mel");
+    if (rc) return rc;
+    if ((rc = rf_plan_upload(p))) return rc;
+    if ((rc = set_smem_attrs())) return rc;
+    const rf_plan_host& h = p->h;
+    const int T = 1 + L / h.H;
+    const size_t xs_n = (RF_PW + h.H) + ((RF_PW + h.H) & 1);
+    const size_t smem = 2 * RF_PW * sizeof(rf_c32) + xs_n * 4 + 2 * static_cast<size_t>(h.n_live) * 8;
+    if (smem > 227 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "rf_stft_mel: live band too wide for the fused kernel");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((T + 1) / 2, B);
+    k_stft_mel_pair<<<grid, RF_NT, smem, st>>>(make_tables(p), d_wave, L, T, h.n_mels, p->d_melcol_ptr,
+                                               p->d_melcol_j, p->d_melcol_w, d_mel);
+    RF_CUDA_LAUNCH_CHECK("k_stft_mel_pair");
+    return RF_OK;
+}
+
+extern "C" int rf_stft(rf_plan* p, const float* d_wave, int B, int L, void* d_spec, void* stream) {
+    if (!p || !d_wave || !d_spec || B <= 0) return rf_fail(RF_ERR_INVALID, "rf_stft: bad argument");
+    int rc = check_L(p, L, "rf_stft");
+    if (rc) return rc;
+    if ((rc = rf_plan_upload(p))) return rc;
+    if ((rc = set_smem_attrs())) return rc;
+    const rf_plan_host& h = p->h;
+    const int T = 1 + L / h.H;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rf_c32* tmp = nullptr;
+    const size_t n = static_cast<size_t>(B) * T * h.n_live;
+    RF_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), n * 8, st));
+    const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
+    dim3 grid_f(((T + 1) / 2) * 2, B);
+    k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(make_tables(p), d_wave, L, T, tmp);
+    RF_CUDA_LAUNCH_CHECK("k_stft_pair");
+    RF_CUDA_TRY(cudaMemsetAsync(d_spec, 0, static_cast<size_t>(B) * h.F * T * 8, st));
+    dim3 grid((h.n_live + 31) / 32, (T + 31) / 32, B), blk(32, 32);
+    k_scatter_TJ_to_FT<float2><<<grid, blk, 0, st>>>(reinterpret_cast<const float2*>(tmp), p->d_bins, h.F, T,
+                                                     h.n_live, static_cast<float2*>(d_spec));
+    RF_CUDA_LAUNCH_CHECK("k_scatter_TJ_to_FT");
+    RF_CUDA_TRY(cudaFreeAsync(tmp, st));
+    return RF_OK;
+}
+
+extern "C" int rf_mel_scale(rf_plan* p, const float* d_spec, int B, int T, float* d_mel, void* stream) {
+    if (!p || !d_spec || !d_mel || B <= 0 || T <= 0) return rf_fail(RF_ERR_INVALID, "rf_mel_scale: bad argument");
+    int rc = rf_plan_upload(p);
+    if (rc) return rc;
+    const rf_plan_host& h = p->h;
+    dim3 grid((T + 127) / 128, h.n_mels, B);
+    k_mel_scale<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_spec, h.F, T, h.n_mels, p->d_melcol_ptr,
+                                                                   p->d_melcol_j, p->d_melcol_w, p->d_bins, d_mel);
+    RF_CUDA_LAUNCH_CHECK("k_mel_scale");
+    return RF_OK;
+}
+
+extern "C" int rf_image_to_mel(const uint8_t* d_img, int height, int width, int stereo, float power,
+                               float max_value, float* d_mel, void* stream) {
+    if (!d_img || !d_mel || height <= 0 || width <= 0 || !(power > 0.f))
+        return rf_fail(RF_ERR_INVALID, "rf_image_to_mel: bad argument");
+    dim3 grid((width + 127) / 128, height, stereo ? 2 : 1);
+    // np.power(data, 1 / power): the exponent is a python float (fp64) cast to the array dtype
+    const float inv_power = static_cast<float>(1.0 / static_cast<double>(power));
+    k_image_to_mel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_img, height, width, stereo, inv_power,
+                                                                      max_value, d_mel);
+    RF_CUDA_LAUNCH_CHECK("k_image_to_mel");
+    return RF_OK;
+}
+
+extern "C" int rf_mel_to_image(const float* d_mel, int channels, int height, int width, float power,
+                               uint8_t* d_img, float* d_max, void* stream) {
+    if (!d_mel || !d_img || !d_max || height <= 0 || width <= 0)
+        return rf_fail(RF_ERR_INVALID, "rf_mel_to_image: bad argument");
+    if (channels != 1 && channels != 2)
+        return rf_fail(RF_ERR_INVALID, "Unsupported number of channels: " + std::to_string(channels));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RF_CUDA_TRY(cudaMemsetAsync(d_max, 0, 4, st));
+    const size_t n = static_cast<size_t>(channels) * height * width;
+    k_absmax<<<296, 256, 0, st>>>(d_mel, n, 0, d_max);
+    RF_CUDA_LAUNCH_CHECK("k_absmax");
+    dim3 grid((width + 127) / 128, height);
+    k_mel_to_image<<<grid, 128, 0, st>>>(d_mel, channels, height, width, power, d_max, d_img);
+    RF_CUDA_LAUNCH_CHECK("k_mel_to_image");
+    return RF_OK;
+}
+
+extern "C" int rf_wave_to_int16(const float* d_wave, int channels, int L, int normalize, int16_t* d_pcm,
+                                float* d_scratch, void* stream) {
+    if (!d_wave || !d_pcm || !d_scratch || channels <= 0 || L <= 0)
+        return rf_fail(RF_ERR_INVALID, "rf_wave_to_int16: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (normalize) {
+        RF_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 4, st));
+        k_absmax<<<296, 256, 0, st>>>(d_wave, static_cast<size_t>(channels) * L, 1, d_scratch);
+        RF_CUDA_LAUNCH_CHECK("k_absmax");
+    }
+    k_wave_to_int16<<<(L + 255) / 256, 256, 0, st>>>(d_wave, channels, L, d_scratch, normalize, d_pcm);
+    RF_CUDA_LAUNCH_CHECK("k_wave_to_int16");
+    return RF_OK;
+}

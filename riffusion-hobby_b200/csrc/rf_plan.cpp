@@ -1,0 +1,258 @@
+// Host plan builder for path (a).  See rf_plan.h.
+//
+// Reference arithmetic restated here (for table construction only):
+//   window        torch.hann_window(win, periodic)    TA/transforms/_transforms.py:94
+//   mel fbanks    melscale_fbanks / _create_triangular_filterbank
+//                                                      TA/functional/functional.py:488-587
+//   inverse mel   relu(lstsq(fb^T, mel, "gels"))       TA/transforms/_transforms.py:508
+//                 == relu(fb (fb^T fb)^{-1} mel) (minimum-norm solution; fb^T fb is
+//                 tridiagonal because only neighbouring triangles overlap)
+#include "rf_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+// torch.linspace(start, end, steps) in fp32 (ATen RangeFactories: symmetric evaluation)
+std::vector<float> linspace_f32(float start, float end, int steps) {
+    std::vector<float> v(steps);
+    if (steps == 1) {
+        v[0] = start;
+        return v;
+    }
+    const float step = (end - start) / static_cast<float>(steps - 1);
+    const int half = steps / 2;
+    for (int i = 0; i < steps; ++i) {
+        if (i < half)
+            v[i] = start + step * static_cast<float>(i);
+        else
+            v[i] = end - step * static_cast<float>(steps - 1 - i);
+    }
+    return v;
+}
+
+double hz_to_mel(double f, bool slaney) {
+    if (!slaney) return 2595.0 * std::log10(1.0 + f / 700.0);
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0;
+    const double min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    if (f >= min_log_hz) return min_log_mel + std::log(f / min_log_hz) / logstep;
+    return f / f_sp;
+}
+
+// follows the fp32 op sequence of torchaudio (pow/log rounding may differ by 1 ulp from
+// torch's vectorised math; pass `fb` from Python for bit parity)
+std::vector<float> melscale_fbanks_f32(int n_freqs, float f_min, float f_max, int n_mels,
+                                       int sample_rate, bool norm_slaney, bool scale_slaney) {
+    std::vector<float> all_freqs = linspace_f32(0.0f, static_cast<float>(sample_rate / 2), n_freqs);
+    const float m_min = static_cast<float>(hz_to_mel(f_min, scale_slaney));
+    const float m_max = static_cast<float>(hz_to_mel(f_max, scale_slaney));
+    std::vector<float> m_pts = linspace_f32(m_min, m_max, n_mels + 2);
+    std::vector<float> f_pts(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i) {
+        if (!scale_slaney) {
+            float e = m_pts[i] / 2595.0f;
+            f_pts[i] = 700.0f * (std::pow(10.0f, e) - 1.0f);
+        } else {
+            const float f_sp = 200.0f / 3.0f, min_log_hz = 1000.0f;
+            const float min_log_mel = min_log_hz / f_sp;
+            const float logstep = static_cast<float>(std::log(6.4) / 27.0);
+            float f = f_sp * m_pts[i];
+            if (m_pts[i] >= min_log_mel) f = min_log_hz * std::exp(logstep * (m_pts[i] - min_log_mel));
+            f_pts[i] = f;
+        }
+    }
+    std::vector<float> fb(static_cast<size_t>(n_freqs) * n_mels);
+    for (int k = 0; k < n_freqs; ++k) {
+        for (int m = 0; m < n_mels; ++m) {
+            const float fd0 = f_pts[m + 1] - f_pts[m];
+            const float fd1 = f_pts[m + 2] - f_pts[m + 1];
+            const float down = (-1.0f * (f_pts[m] - all_freqs[k])) / fd0;
+            const float up = (f_pts[m + 2] - all_freqs[k]) / fd1;
+            float v = std::max(0.0f, std::min(down, up));
+            if (norm_slaney) v *= 2.0f / (f_pts[m + 2] - f_pts[m]);
+            fb[static_cast<size_t>(k) * n_mels + m] = v;
+        }
+    }
+    return fb;
+}
+
+}  // namespace
+
+std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const float* fb_in,
+                               rf_plan_host& p, int& code) {
+    code = RF_ERR_INVALID;
+    if (d.n_fft <= 0 || d.win_length <= 0 || d.hop_length <= 0 || d.n_mels <= 0 || d.sample_rate <= 0)
+        return "rf_plan_create: non-positive geometry";
+    if (d.win_length > d.n_fft) return "rf_plan_create: win_length > n_fft";
+    if (d.f_min > d.f_max) return "Require f_min <= f_max";  // TA/transforms/_transforms.py:473
+    code = RF_ERR_UNSUPPORTED;
+    if (d.win_length != RF_W || d.n_fft != RF_N)
+        return "rf_plan_create: this build only has the 4410-point prime-factor FFT engine "
+               "(win_length=4410, n_fft=17640: 44.1 kHz / 100 ms window / 400 ms padded); got "
+               "win_length=" + std::to_string(d.win_length) + " n_fft=" + std::to_string(d.n_fft);
+    if (d.hop_length > RF_W || (RF_W % d.hop_length) != 0)
+        return "rf_plan_create: hop_length must divide win_length";
+    p.d = d;
+    p.N = d.n_fft;
+    p.W = d.win_length;
+    p.H = d.hop_length;
+    p.F = d.n_fft / 2 + 1;
+    p.n_mels = d.n_mels;
+
+    // ---- window
+    p.window.resize(p.W);
+    for (int n = 0; n < p.W; ++n)
+        p.window[n] = window ? window[n]
+                             : static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * n / p.W));
+
+    // ---- filterbank
+    if (fb_in)
+        p.fb.assign(fb_in, fb_in + static_cast<size_t>(p.F) * p.n_mels);
+    else
+        p.fb = melscale_fbanks_f32(p.F, d.f_min, d.f_max, p.n_mels, d.sample_rate,
+                                   d.mel_norm_slaney != 0, d.mel_scale_slaney != 0);
+
+    // ---- live bins and private order: (even k | odd k), then r = k%4, then PFA position of k/4
+    struct Ent {
+        int k, r, idx;
+    };
+    std::vector<Ent> ents;
+    p.fb_nnz = 0;
+    for (int k = 0; k < p.F; ++k) {
+        bool live = d.full_band != 0;
+        for (int m = 0; m < p.n_mels; ++m)
+            if (p.fb[static_cast<size_t>(k) * p.n_mels + m] != 0.0f) {
+                live = true;
+                ++p.fb_nnz;
+            }
+        if (!live) continue;
+        const int mm = k >> 2;
+        ents.push_back({k, k & 3, rf_pfa_pos(mm % RF_NA, mm % RF_NB, mm % RF_NC)});
+    }
+    if (ents.empty()) {
+        code = RF_ERR_INVALID;
+        return "rf_plan_create: mel filterbank is identically zero";
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
+        const int gx = x.k & 1, gy = y.k & 1;
+        if (gx != gy) return gx < gy;
+        if (x.r != y.r) return x.r < y.r;
+        return x.idx < y.idx;
+    });
+    p.n_live = static_cast<int>(ents.size());
+    p.bins.resize(p.n_live);
+    p.pp.resize(p.n_live);
+    p.jofk.assign(p.F, -1);
+    p.n_even = 0;
+    p.k_lo = p.F;
+    p.k_hi = -1;
+    for (int j = 0; j < p.n_live; ++j) {
+        const int k = ents[j].k;
+        p.bins[j] = k;
+        p.jofk[k] = j;
+        if ((k & 1) == 0) ++p.n_even;
+        p.k_lo = std::min(p.k_lo, k);
+        p.k_hi = std::max(p.k_hi, k);
+        const int kp = (p.N - k) % p.N;
+        const int mp = kp >> 2;
+        const uint32_t idx2 = rf_pfa_pos(mp % RF_NA, mp % RF_NB, mp % RF_NC);
+        p.pp[j] = static_cast<uint32_t>(ents[j].r) | (static_cast<uint32_t>(ents[j].idx) << 2) |
+                  (idx2 << 15) | (static_cast<uint32_t>(k & 7) << 28);
+    }
+
+    // ---- modulation x window tables at PFA (time-side) positions
+    p.wt_fwd.assign(static_cast<size_t>(4) * p.W * 2, 0.f);
+    p.wt_inv.assign(static_cast<size_t>(4) * p.W * 2, 0.f);
+    for (int r = 0; r < 4; ++r)
+        for (int a = 0; a < RF_NA; ++a)
+            for (int b = 0; b < RF_NB; ++b)
+                for (int c = 0; c < RF_NC; ++c) {
+                    const int n = rf_pfa_n_of(a, b, c);
+                    const int pos = rf_pfa_pos(a, b, c);
+                    const long q = (static_cast<long>(r) * n) % p.N;
+                    const double ang = -2.0 * M_PI * static_cast<double>(q) / p.N;
+                    const double w = p.window[n];
+                    const size_t o = (static_cast<size_t>(r) * p.W + pos) * 2;
+                    p.wt_fwd[o] = static_cast<float>(w * std::cos(ang));
+                    p.wt_fwd[o + 1] = static_cast<float>(w * std::sin(ang));
+                    p.wt_inv[o] = static_cast<float>(w * std::cos(ang) / p.N);
+                    p.wt_inv[o + 1] = static_cast<float>(-w * std::sin(ang) / p.N);
+                }
+
+    // ---- sparse filterbank
+    p.melcol_ptr.assign(p.n_mels + 1, 0);
+    p.binrow_ptr.assign(p.n_live + 1, 0);
+    for (int m = 0; m < p.n_mels; ++m) {
+        for (int k = 0; k < p.F; ++k) {
+            const float v = p.fb[static_cast<size_t>(k) * p.n_mels + m];
+            if (v != 0.0f) {
+                p.melcol_j.push_back(p.jofk[k]);
+                p.melcol_w.push_back(v);
+            }
+        }
+        p.melcol_ptr[m + 1] = static_cast<int32_t>(p.melcol_j.size());
+    }
+    for (int j = 0; j < p.n_live; ++j) {
+        const int k = p.bins[j];
+        for (int m = 0; m < p.n_mels; ++m) {
+            const float v = p.fb[static_cast<size_t>(k) * p.n_mels + m];
+            if (v != 0.0f) {
+                p.binrow_m.push_back(m);
+                p.binrow_w.push_back(v);
+            }
+        }
+        p.binrow_ptr[j + 1] = static_cast<int32_t>(p.binrow_m.size());
+    }
+
+    // ---- Gram matrix (must be tridiagonal) + Thomas factors, fp64
+    p.tri.assign(static_cast<size_t>(3) * p.n_mels, 0.0);
+    bool tridiag = true;
+    for (int k = 0; k < p.F && tridiag; ++k) {
+        int first = -1, last = -1;
+        for (int m = 0; m < p.n_mels; ++m)
+            if (p.fb[static_cast<size_t>(k) * p.n_mels + m] != 0.0f) {
+                if (first < 0) first = m;
+                last = m;
+            }
+        if (first >= 0 && last - first > 1) tridiag = false;
+        if (first < 0) continue;
+        for (int m = first; m <= last; ++m) {
+            const double v = p.fb[static_cast<size_t>(k) * p.n_mels + m];
+            p.tri[p.n_mels + m] += v * v;
+            if (m + 1 <= last) {
+                const double v2 = p.fb[static_cast<size_t>(k) * p.n_mels + m + 1];
+                p.tri[2 * p.n_mels + m] += v * v2;      // super[m]   = G[m][m+1]
+                p.tri[m + 1] += v * v2;                 // sub[m+1]   = G[m+1][m]
+            }
+        }
+    }
+    if (!tridiag) {
+        code = RF_ERR_UNSUPPORTED;
+        return "rf_plan_create: mel filterbank rows overlap more than two filters; the "
+               "inverse-mel kernel needs a tridiagonal fb^T fb";
+    }
+    p.thomas.assign(static_cast<size_t>(2) * p.n_mels, 0.0);
+    {
+        const double* sub = &p.tri[0];
+        const double* dg = &p.tri[p.n_mels];
+        const double* sup = &p.tri[2 * p.n_mels];
+        double cprev = 0.0;
+        for (int i = 0; i < p.n_mels; ++i) {
+            const double den = dg[i] - (i ? sub[i] * cprev : 0.0);
+            if (!(std::fabs(den) > 1e-300) || !(dg[i] > 0.0)) {
+                code = RF_ERR_INVALID;
+                // torchaudio warns here (functional.py:579-584) and gels then assumes full rank
+                return "rf_plan_create: at least one mel filterbank has all zero values "
+                       "(n_mels too high for n_fft); inverse mel is singular";
+            }
+            const double c = sup[i] / den;
+            p.thomas[i] = c;
+            p.thomas[p.n_mels + i] = 1.0 / den;
+            cprev = c;
+        }
+    }
+    code = RF_OK;
+    return std::string();
+}

@@ -1,0 +1,48 @@
+// Host-side plan for path (a): every table the audio kernels read, built in fp64 and
+// rounded once to fp32.  Pure C++ (no CUDA) so that tests/hostemu can build it with g++.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rf_b200.h"
+
+// Fixed geometry of the prime-factor FFT engine: win = 10*9*49, n_fft = 4*win.
+constexpr int RF_W = 4410;
+constexpr int RF_N = 4 * RF_W;
+constexpr int RF_NA = 10, RF_NB = 9, RF_NC = 49;
+constexpr int RF_CHUNK = 16;  // frames per overlap-add chunk in the iSTFT kernel (even)
+
+struct rf_plan_host {
+    rf_plan_desc d{};
+    int N = 0, W = 0, H = 0, F = 0, n_mels = 0;
+    int n_live = 0, n_even = 0, k_lo = 0, k_hi = 0;
+
+    std::vector<float> window;    // [W] natural order
+    std::vector<float> fb;        // [F][n_mels]
+    std::vector<int32_t> bins;    // [n_live] private order j -> STFT bin k
+    std::vector<int32_t> jofk;    // [F] bin k -> j or -1
+    std::vector<uint32_t> pp;     // [n_live] r | idx<<2 | idx2<<15 | (k&7)<<28
+    std::vector<float> wt_fwd;    // [4][W][2]  w[n'] * exp(-2 pi i r n'/N) at PFA position
+    std::vector<float> wt_inv;    // [4][W][2]  w[n']/N * exp(+2 pi i r n'/N)
+    // mel filterbank in sparse forms over the private bin order
+    std::vector<int32_t> melcol_ptr;  // [n_mels+1]  CSR by mel column: entries (j, w)
+    std::vector<int32_t> melcol_j;
+    std::vector<float> melcol_w;
+    std::vector<int32_t> binrow_ptr;  // [n_live+1]  CSR by live bin: entries (m, w)
+    std::vector<int32_t> binrow_m;
+    std::vector<float> binrow_w;
+    // Gram matrix fb^T fb (tridiagonal) and its LU (Thomas) factors, fp64
+    std::vector<double> tri;     // [3][n_mels]: sub, diag, super
+    std::vector<double> thomas;  // [2][n_mels]: cprime (super/denominator), inv_den
+    int fb_nnz = 0;
+};
+
+// returns empty string on success, else an error message; `code` gets RF_ERR_*
+std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const float* fb,
+                               rf_plan_host& out, int& code);
+
+// PFA index helpers (time side: Ruritanian, spectral side: CRT)
+inline int rf_pfa_n_of(int a, int b, int c) { return (441 * a + 490 * b + 90 * c) % RF_W; }
+inline int rf_pfa_m_of(int a, int b, int c) { return (441 * a + 3430 * b + 540 * c) % RF_W; }
+inline int rf_pfa_pos(int a, int b, int c) { return a * 441 + b * 49 + c; }
