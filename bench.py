@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the hot path on N B200s of one node (driver contract).
+
+Workload at N=1 (config.workload): BASELINE.json configs[1] — inverse-mel + 32-iteration Griffin-Lim
+reconstruction of 512x512 mel spectrograms, batch 64 per GPU.  Until the denoising path (b) lands
+the "clip" of the clips/sec metric is one Griffin-Lim reconstructed clip (config.includes_denoise
+= false); the 50-step UNet part of BASELINE's metric is not in this number.
+
+One "step" = one pass of the hot path over one batch of 64 synthetic clips per GPU.
+  value  : clips/s, whole job, inputs (mel amplitudes + initial phases) resident in HBM
+  e2e    : clips/s through SpectrogramConverter.waveform_from_mel_amplitudes with HOST buffers:
+           pinned mel -> H2D, torch.rand phase init (as the reference does per call), kernels,
+           waveform D2H — all inside the timed region
+  roofline: dominant Griffin-Lim kernel, algorithmic bytes (36 B per live bin x frame x
+           iteration, split 12 B iSTFT / 24 B STFT) over its CUDA-event duration, vs MEASURED_PEAKS
+  cpu_baseline / --impl reference: the reference's own CPU arithmetic (installed torchaudio
+           transforms built with the reference's arguments, oracle/torchaudio_ref.py) on all host
+           cores, on a bounded sample (one clip per step).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "riffusion-hobby_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+N_FFT, WIN, HOP, N_MELS, T_FRAMES, F_LIVE, N_ITER = 17640, 4410, 441, 512, 512, 4000, 32
+BATCH_PER_GPU = 64
+L_WAVE = HOP * (T_FRAMES - 1)
+
+
+def algorithmic_bytes_per_clip() -> float:
+    """n_iter*36*F_live*T + 12*F_live*T + (2 n_iter+1)*4*hop*(T-1)"""
+    return N_ITER * 36 * F_LIVE * T_FRAMES + 12 * F_LIVE * T_FRAMES + (2 * N_ITER + 1) * 4 * L_WAVE
+
+
+def synthetic_mel(batch: int, seed: int) -> torch.Tensor:
+    """og_beat amplitudes perturbed per clip, mel_b = mel * exp(0.1 N(0,1))."""
+    g = np.load(ROOT / "tests" / "golden" / "og_beat.npz")
+    rgb = g["rgb"]
+    data = rgb[::-1].transpose(2, 0, 1)[0:1].astype(np.float32)
+    data = np.power((255 - data) / 255, 4.0).astype(np.float32) * np.float32(30e6)
+    base = torch.from_numpy(data)  # (1, 512, 512)
+    gen = torch.Generator().manual_seed(seed)
+    noise = torch.randn((batch, N_MELS, T_FRAMES), generator=gen)
+    return (base * torch.exp(0.1 * noise)).contiguous()
+
+
+def peaks() -> dict:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference(steps: int, warmup: int, threads: int) -> dict:
+    """The reference's CPU path (torchaudio transforms with the reference's arguments), one clip per
+    step, all host threads."""
+    from oracle.torchaudio_ref import TorchaudioConverter
+
+    torch.set_num_threads(threads)
+    conv = TorchaudioConverter(n_iter=N_ITER)
+    mel = synthetic_mel(1, seed=0)
+    torch.manual_seed(0)
+    for _ in range(warmup):
+        conv.waveform_from_mel_amplitudes(mel)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w = conv.waveform_from_mel_amplitudes(mel)
+    dt = time.perf_counter() - t0
+    assert w.shape == (1, L_WAVE)
+    return {"value": steps / dt, "seconds_per_clip": dt / steps, "cores": threads,
+            "sample": f"{steps} x 1 clip (512x512 mel, inverse-mel lstsq + 32-iter Griffin-Lim), torchaudio "
+                      f"{__import__('torchaudio').__version__} fp32, {threads} threads"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = (f"configs[1]: inverse-mel + Griffin-Lim {N_ITER}-iter reconstruction of {N_MELS}x{T_FRAMES} mel "
+                f"spectrograms, batch {args.batch} per GPU")
+    config = {"workload": workload, "includes_denoise": False, "n_fft": N_FFT, "win": WIN, "hop": HOP,
+              "live_bins": F_LIVE, "batch_per_gpu": args.batch,
+              "l2": "inputs+state (2.9 GB per step) larger than L2; no explicit flush",
+              "sharding": "independent clips per rank, no collective in the step"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 6))
+        r = time_reference(steps, max(1, min(args.warmup, 1)), cores)
+        line = {"impl": "reference", "metric": "clips/sec", "value": r["value"], "unit": "clips/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * r["seconds_per_clip"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "clips/s", "cores": r["cores"], "kind": "reference",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from riffusion import _native
+    from riffusion.spectrogram_converter import SpectrogramConverter, get_plan
+    from riffusion.spectrogram_params import SpectrogramParams
+
+    params = SpectrogramParams()
+    conv = SpectrogramConverter(params, device=str(dev))
+    plan = get_plan(params, full_band=False)
+    B = args.batch
+    F = plan.info.n_freq
+    mel_host = synthetic_mel(B, seed=rank).pin_memory()
+    mel = mel_host.to(dev)
+    torch.manual_seed(rank)
+    angles = torch.rand((B, F, T_FRAMES), dtype=torch.complex64, device=dev)
+    wave = torch.empty((B, L_WAVE), dtype=torch.float32, device=dev)
+    wave_host = torch.empty((B, L_WAVE), dtype=torch.float32).pin_memory()
+    lib = _native.lib()
+    nbytes = lib.rf_griffinlim_workspace_bytes(plan.handle, B, T_FRAMES)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        _native.check(lib.rf_mel_to_wave(plan.handle, mel.data_ptr(), angles.data_ptr(), B, T_FRAMES, N_ITER,
+                                         0.99, wave.data_ptr(), ws.data_ptr(), nbytes, stream.cuda_stream))
+
+    def step_e2e():
+        m = mel_host.to(dev, non_blocking=True)
+        w = conv.waveform_from_mel_amplitudes(m)      # draws torch.rand phases like the reference
+        wave_host.copy_(w, non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel CUDA-event timing of the same step (rank 0 reports)
+    ms_cls = (ctypes.c_float * 3)()
+    n_cls = (ctypes.c_int * 3)()
+    acc = np.zeros(3)
+    prof_steps = min(args.steps, 3)
+    for _ in range(prof_steps):
+        _native.check(lib.rf_mel_to_wave_profiled(plan.handle, mel.data_ptr(), angles.data_ptr(), B, T_FRAMES, N_ITER,
+                                                  0.99, wave.data_ptr(), ws.data_ptr(), nbytes, stream.cuda_stream,
+                                                  ms_cls, n_cls))
+        acc += np.array(list(ms_cls))
+    acc /= prof_steps
+    launches = list(n_cls)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    clips = B * world
+    value = clips / (ms_step / 1e3)
+    pk = peaks()
+    names = ["k_istft_chunk", "k_ola_assemble", "k_stft_pair"]
+    per_launch_bytes = [B * 12.0 * F_LIVE * T_FRAMES + B * 4.0 * L_WAVE, 0.0, B * 24.0 * F_LIVE * T_FRAMES + B * 4.0 * L_WAVE]
+    dom = int(np.argmax(acc))
+    dom_ms = acc[dom] / max(launches[dom], 1)
+    achieved = per_launch_bytes[dom] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    loop_ms = float(acc.sum())
+    loop_gbs = B * algorithmic_bytes_per_clip() / (loop_ms / 1e3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " (burst copy)",
+        "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": acc[dom] / (ms_step),
+        "algorithmic_bytes_per_launch": per_launch_bytes[dom],
+        "per_kernel_ms_per_step": dict(zip(names, [float(a) for a in acc])),
+        "loop": {"achieved": loop_gbs, "frac": loop_gbs / pk["hbm_gbs"], "unit": "GB/s",
+                 "algorithmic_bytes_per_step": B * algorithmic_bytes_per_clip(), "ms": loop_ms},
+    }
+    traffic_file = ROOT / "profiles" / "traffic_latest.json"
+    if traffic_file.exists():
+        try:
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(names[dom])
+        except (ValueError, OSError):
+            pass
+    ms_e2e_step = ms_e2e / args.steps
+    e2e = {"value": clips / (ms_e2e_step / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e_step,
+           "h2d_bytes_per_step": int(B * N_MELS * T_FRAMES * 4), "d2h_bytes_per_step": int(B * L_WAVE * 4),
+           "api": "SpectrogramConverter.waveform_from_mel_amplitudes (pinned host mel in, pinned host waveform out)"}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_reference(3, 1, cores)
+        cpu_baseline = {"value": r["value"], "unit": "clips/s", "cores": r["cores"], "kind": "reference",
+                        "sample": r["sample"]}
+    line = {
+        "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int((sum(launches) + 2) * args.steps), "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,14 @@ int rf_mel_to_wave(rf_plan* plan, const float* d_mel, const void* d_init_angles,
                    int n_iter, float momentum, float* d_wave, void* d_workspace,
                    size_t workspace_bytes, void* stream);
 
+/* rf_mel_to_wave with every Griffin-Lim kernel launch bracketed by CUDA events on `stream`
+ * (measurement aid for bench.py's roofline; synchronises the stream before returning).
+ *   ms_out[3]       host: summed device ms of {iSTFT chunk kernel, overlap-add assembly, STFT pair kernel}
+ *   launches_out[3] host: launches per class */
+int rf_mel_to_wave_profiled(rf_plan* plan, const float* d_mel, const void* d_init_angles, int B,
+                            int T, int n_iter, float momentum, float* d_wave, void* d_workspace,
+                            size_t workspace_bytes, void* stream, float* ms_out, int* launches_out);
+
 /* ---- path (a), forward: waveform -> mel amplitudes ---------------------------------
  * replaces SpectrogramConverter.mel_amplitudes_from_waveform
  * (riffusion/spectrogram_converter.py:165-185): Spectrogram(power=None) -> abs -> MelScale.

@@ -575,9 +575,21 @@ static int launch_inverse_mel(rf_plan* p, const float* d_mel, int B, int T, int 
     return RF_OK;
 }
 
+// optional per-kernel-class CUDA-event timing (bench.py's live roofline measurement)
+struct gl_prof {
+    std::vector<cudaEvent_t> ev[3][2];  // [istft, assemble, stft][begin,end]
+    cudaError_t mark(int cls, int end, cudaStream_t st) {
+        cudaEvent_t e;
+        cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) return rc;
+        ev[cls][end].push_back(e);
+        return cudaEventRecord(e, st);
+    }
+};
+
 // Griffin-Lim main loop on a prepared workspace (S and initial angles in R[1]).
 static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float momentum_in, float* d_wave,
-                   cudaStream_t st) {
+                   cudaStream_t st, gl_prof* prof = nullptr) {
     const rf_plan_host& h = p->h;
     const rf_gl_tables tb = make_tables(p);
     const int L = h.H * (T - 1);
@@ -598,15 +610,23 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
             mode = 1;
             if (it >= 2 && m != 0.f) prev = w.R[it & 1];
         }
+        if (prof) RF_CUDA_TRY(prof->mark(0, 0, st));
         k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
                                                      w.part);
         RF_CUDA_LAUNCH_CHECK("k_istft_chunk");
+        if (prof) {
+            RF_CUDA_TRY(prof->mark(0, 1, st));
+            RF_CUDA_TRY(prof->mark(1, 0, st));
+        }
         k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, p->d_win2, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L,
                                                d_wave);
         RF_CUDA_LAUNCH_CHECK("k_ola_assemble");
+        if (prof) RF_CUDA_TRY(prof->mark(1, 1, st));
         if (it == n_iter) break;
+        if (prof) RF_CUDA_TRY(prof->mark(2, 0, st));
         k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, w.R[it & 1]);
         RF_CUDA_LAUNCH_CHECK("k_stft_pair");
+        if (prof) RF_CUDA_TRY(prof->mark(2, 1, st));
     }
     return RF_OK;
 }
@@ -666,6 +686,43 @@ extern "C" int rf_mel_to_wave(rf_plan* p, const float* d_mel, const void* d_init
     if ((rc = launch_inverse_mel(p, d_mel, B, T, 0, w.S, st))) return rc;
     if ((rc = gl_prepare_angles(p, w, d_init_angles, B, T, st))) return rc;
     return gl_loop(p, w, B, T, n_iter, momentum, d_wave, st);
+}
+
+// Same as rf_mel_to_wave, with every Griffin-Lim kernel launch bracketed by CUDA events on
+// `stream`; synchronises the stream and returns the summed device time per kernel class.
+//   ms_out[3]       host: total ms of {k_istft_chunk, k_ola_assemble, k_stft_pair}
+//   launches_out[3] host: launches per class
+extern "C" int rf_mel_to_wave_profiled(rf_plan* p, const float* d_mel, const void* d_init_angles, int B, int T,
+                                       int n_iter, float momentum, float* d_wave, void* d_ws, size_t ws_bytes,
+                                       void* stream, float* ms_out, int* launches_out) {
+    if (!p || !d_mel || !d_wave || !d_ws || !ms_out || !launches_out || B <= 0 || n_iter < 0)
+        return rf_fail(RF_ERR_INVALID, "rf_mel_to_wave_profiled: bad argument");
+    int rc = check_T(p, T, "rf_mel_to_wave_profiled");
+    if (rc) return rc;
+    if ((rc = rf_plan_upload(p))) return rc;
+    if ((rc = set_smem_attrs())) return rc;
+    const gl_ws w = gl_layout(p, B, T, d_ws);
+    if (ws_bytes < w.total) return rf_fail(RF_ERR_INVALID, "rf_mel_to_wave_profiled: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_inverse_mel(p, d_mel, B, T, 0, w.S, st))) return rc;
+    if ((rc = gl_prepare_angles(p, w, d_init_angles, B, T, st))) return rc;
+    gl_prof prof;
+    rc = gl_loop(p, w, B, T, n_iter, momentum, d_wave, st, &prof);
+    cudaError_t e = cudaStreamSynchronize(st);
+    for (int c = 0; c < 3; ++c) {
+        ms_out[c] = 0.f;
+        launches_out[c] = static_cast<int>(prof.ev[c][1].size());
+        for (size_t i = 0; i < prof.ev[c][1].size() && i < prof.ev[c][0].size(); ++i) {
+            float ms = 0.f;
+            if (rc == RF_OK && e == cudaSuccess && cudaEventElapsedTime(&ms, prof.ev[c][0][i], prof.ev[c][1][i]) == cudaSuccess)
+                ms_out[c] += ms;
+        }
+        for (int k = 0; k < 2; ++k)
+            for (cudaEvent_t ev : prof.ev[c][k]) cudaEventDestroy(ev);
+    }
+    if (rc) return rc;
+    if (e != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    return RF_OK;
 }
 
 extern "C" int rf_inverse_mel(rf_plan* p, const float* d_mel, int B, int T, float* d_lin, void* stream) {
