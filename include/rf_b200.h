@@ -145,6 +145,50 @@ int rf_mel_to_image(const float* d_mel, int channels, int height, int width, flo
 int rf_wave_to_int16(const float* d_wave, int channels, int L, int normalize, int16_t* d_pcm,
                      float* d_scratch, void* stream);
 
+
+/* ==== path (b): tensor-core building blocks (tcgen05 / TMEM / TMA) ========================
+ * The reference reaches these through diffusers' UNet2DConditionModel / AutoencoderKL forward
+ * (riffusion/riffusion_pipeline.py:255,406-408,428): torch.nn.Linear / Conv2d / attention bmm.
+ * All tensors fp16, device pointers; activations are NHWC ("channels last"). */
+
+/* D[b2][b1][m][n] = act(alpha * sum_k A[..][m][k] * B[..][n][k] + bias) + residual  (both operands K-major).
+ * Strides are in elements; ld* = row pitch, s*1 / s*2 = strides of the two batch dimensions
+ * (ignored when the batch extent is 1).  Pointers 16-byte aligned, pitches multiples of 8. */
+typedef struct rf_gemm_desc {
+    int32_t M, N, K;
+    int32_t batch1, batch2;
+    const void* A; int64_t lda, sa1, sa2;
+    const void* B; int64_t ldb, sb1, sb2;
+    void* D;       int64_t ldd, sd1, sd2;
+    const void* bias;          /* fp16 [N] (bias_mode 1) or [M] (bias_mode 2), or NULL */
+    int32_t bias_mode;
+    const void* residual;      /* fp16, indexed like D with ldr/sr1/sr2, or NULL */
+    int64_t ldr, sr1, sr2;
+    float alpha;               /* 0 is treated as 1 */
+    int32_t act;               /* 0 none, 1 SiLU */
+    int32_t out_f32;           /* 1: D is fp32 */
+} rf_gemm_desc;
+int rf_gemm_f16(const rf_gemm_desc* desc, void* stream);
+
+/* torch.nn.Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2) as an implicit GEMM over NHWC input;
+ * the input may be the channel concatenation of two tensors (UNet skip connections,
+ * torch.cat([hidden, skip], dim=1)).  Weights are [Cout][ky][kx][C1+C2] fp16 (see
+ * riffusion.unet weight packing).  out = act(conv + bias + bias_per_image[b]) + residual. */
+typedef struct rf_conv_desc {
+    int32_t B, H, W;           /* input images, height, width */
+    int32_t C1, C2;            /* channels of x1 and x2 (C2 = 0 without x2); multiples of 64 */
+    int32_t Cout, ksize, stride;
+    const void* x1; const void* x2;
+    const void* w;
+    const void* bias;          /* fp16 [Cout] or NULL */
+    const void* bias_per_image;/* fp16 [B][Cout] or NULL (time-embedding projection) */
+    const void* residual;      /* fp16 NHWC like out, or NULL */
+    void* out;                 /* fp16 [B][Ho][Wo][Cout] */
+    float alpha;               /* 0 is treated as 1 */
+    int32_t act;
+} rf_conv_desc;
+int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,7 +184,6 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
-constexpr int RF_NT = 224;  // threads per CTA of the FFT kernels (441 = 2*224 - 7 radix-10 items)
 
 // ---- iSTFT of one overlap-add chunk (G frames) of one clip, one r-group ------------------
 // grid (nchunks*2, B). Output: part[b][g][chunk][PL] partial overlap-add sums.
@@ -221,9 +220,9 @@ k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __rest
         __syncthreads();
         rf_pass_c<true>(tid, RF_NT, V);
         __syncthreads();
-        rf_pass_b<true>(tid, RF_NT, V);
+        rf_pass_a<true>(tid, RF_NT, V);
         __syncthreads();
-        rf_istft_pass_a(tid, RF_NT, V, ola + 2 * pr * tb.hop, tb, g, has1);
+        rf_istft_pass_b(tid, RF_NT, V, ola + 2 * pr * tb.hop, tb, g, has1, 2);
         __syncthreads();
     }
     float* dst = part + ((static_cast<size_t>(b) * 2 + g) * nchunks + chunk) * PL;
@@ -232,14 +231,19 @@ k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __rest
 
 // ---- overlap-add assembly: x[b][i] = sum(parts) / envelope, kept region only --------------
 // (torch.istft: y / window_envelope, trimmed by n_fft/2 each side)
-__global__ void k_ola_assemble(const float* __restrict__ part, const float* __restrict__ win2,
+__global__ void k_envelope(const float* __restrict__ win2, int T, int H, int W, int L, float* __restrict__ env) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L) env[i] = rf_envelope(i, win2, T, H, W);
+}
+
+__global__ void k_ola_assemble(const float* __restrict__ part, const float* __restrict__ env,
                                int T, int G, int PL, int nchunks, int H, int W, int L,
                                float* __restrict__ x) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= L) return;
     x[static_cast<size_t>(b) * L + i] =
-        rf_ola_sample(i, part + static_cast<size_t>(b) * 2 * nchunks * PL, win2, T, G, PL, nchunks, H, W);
+        rf_ola_sample(i, part + static_cast<size_t>(b) * 2 * nchunks * PL, env[i], T, G, PL, nchunks, H, W);
 }
 
 // ---- STFT of one frame pair, one r-group ------------------------------------------------
@@ -253,11 +257,11 @@ k_stft_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, rf_c32* 
     const int g = blockIdx.x & 1, pr = blockIdx.x >> 1, b = blockIdx.y;
     const int t0 = 2 * pr;
     const bool has1 = t0 + 1 < T;
-    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop, has1);
+    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop);
     __syncthreads();
-    rf_stft_pass_a(tid, RF_NT, V, xs, tb, g);
+    rf_stft_pass_b(tid, RF_NT, V, xs, tb, g, has1);
     __syncthreads();
-    rf_pass_b<false>(tid, RF_NT, V);
+    rf_pass_a<false>(tid, RF_NT, V);
     __syncthreads();
     rf_pass_c<false>(tid, RF_NT, V);
     __syncthreads();
@@ -280,12 +284,12 @@ k_stft_mel_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int 
     const int pr = blockIdx.x, b = blockIdx.y;
     const int t0 = 2 * pr;
     const bool has1 = t0 + 1 < T;
-    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop, has1);
+    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop);
     __syncthreads();
     for (int g = 0; g < 2; ++g) {
-        rf_stft_pass_a(tid, RF_NT, V, xs, tb, g);
+        rf_stft_pass_b(tid, RF_NT, V, xs, tb, g, has1);
         __syncthreads();
-        rf_pass_b<false>(tid, RF_NT, V);
+        rf_pass_a<false>(tid, RF_NT, V);
         __syncthreads();
         rf_pass_c<false>(tid, RF_NT, V);
         __syncthreads();
@@ -510,6 +514,7 @@ struct gl_ws {
     float* S;
     rf_c32* R[2];
     float* part;
+    float* env;
     size_t total;
     int nchunks, PL;
 };
@@ -529,6 +534,8 @@ static gl_ws gl_layout(const rf_plan* p, int B, int T, void* base) {
     off += align256(bt * 8);
     w.part = reinterpret_cast<float*>(b + off);
     off += align256(static_cast<size_t>(B) * 2 * w.nchunks * w.PL * 4);
+    w.env = reinterpret_cast<float*>(b + off);
+    off += align256(static_cast<size_t>(p->h.H) * (T > 0 ? T - 1 : 0) * 4);
     w.total = off;
     return w;
 }
@@ -598,6 +605,8 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const size_t smem_i = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(w.PL) * 4;
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
     const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
+    k_envelope<<<(L + 255) / 256, 256, 0, st>>>(p->d_win2, T, h.H, h.W, L, w.env);
+    RF_CUDA_LAUNCH_CHECK("k_envelope");
     for (int it = 0; it <= n_iter; ++it) {
         const rf_c32* cur;
         const rf_c32* prev = nullptr;
@@ -618,7 +627,7 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
             RF_CUDA_TRY(prof->mark(0, 1, st));
             RF_CUDA_TRY(prof->mark(1, 0, st));
         }
-        k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, p->d_win2, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L,
+        k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, w.env, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L,
                                                d_wave);
         RF_CUDA_LAUNCH_CHECK("k_ola_assemble");
         if (prof) RF_CUDA_TRY(prof->mark(1, 1, st));

@@ -1,0 +1,409 @@
+// Path (b) tensor-core workhorse: one tcgen05/TMEM kernel that computes
+//     D[b][m][n] = act(alpha * sum_k A[b][m][k] * B[b][n][k] + bias) + residual          (fp16 in, fp32 accumulate)
+// either as a batched "TN" GEMM (both operands K-major; linears, 1x1 convs, QK^T, PV) or as an
+// implicit-GEMM 3x3 / strided convolution over NHWC activations (the im2col gather is done by the
+// TMA engine: one 4-D box load per filter tap with out-of-bounds zero fill supplying the padding).
+//
+// CTA = one 128 x BN output tile.  Warp roles: warp 0 = TMA producer (one thread), warp 1 = TMEM
+// allocation + MMA issue (one thread), warps 2-5 = epilogue (TMEM -> registers -> global).
+// K is streamed in 64-element (128-byte, SWIZZLE_128B) slabs through a STAGES-deep mbarrier ring.
+//
+// Reference arithmetic this replaces (diffusers 0.9 modules reached from
+// riffusion/riffusion_pipeline.py:406-408,428): torch.nn.Conv2d / Linear / baddbmm+bmm attention,
+// which resolve to cuDNN / cuBLAS in the reference; none of those libraries is used here.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+
+#include "rf_common.h"
+#include "rf_tc.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+
+struct TcParams {
+    // problem
+    int M, N, K;            // GEMM mode: per-batch extents. conv mode: N = Cout, K unused
+    int batch1, batch2;     // grid.z = batch1 * batch2
+    int num_kb;             // K slabs
+    // conv mode
+    int conv;               // 0 = GEMM, 1 = conv
+    int taps;               // 1 or 9
+    int kc1, kc2;           // 64-channel slabs in source tensor 1 / 2 (channel concat)
+    int stride, pad;        // conv stride and padding
+    int Ho, Wo, Bn;         // output image size and image count
+    int bw, bh, bb;         // output pixels per tile: bw * bh * bb == 128
+    int tiles_x, tiles_y;   // tiles per image row / column
+    // epilogue
+    __half* out;
+    long ldo, so1, so2;     // GEMM: row pitch and batch strides of D (elements)
+    const __half* bias;     // [N] (bias_mode 1) or [M] (bias_mode 2)
+    int bias_mode;
+    const __half* bias2;    // conv: per-image bias [Bn][N] (time embedding), may be null
+    const __half* residual; // same indexing as out, may be null
+    long ldr, sr1, sr2;
+    float alpha;
+    int act;                // 0 none, 1 SiLU
+    float* out_f32;         // optional fp32 output instead of fp16 (same indexing)
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return v / (1.f + __expf(-v));
+    return v;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+          const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int B_TILE_BYTES = BN * BK * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_TILE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    const int b1 = blockIdx.z % p.batch1, b2 = blockIdx.z / p.batch1;
+
+    // conv tile origin
+    int tx = 0, ty = 0, tb = 0;
+    if (p.conv) {
+        tx = m_blk % p.tiles_x;
+        ty = (m_blk / p.tiles_x) % p.tiles_y;
+        tb = m_blk / (p.tiles_x * p.tiles_y);
+    }
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            tc::mbar_init(&full[i], 1);
+            tc::mbar_init(&empty[i], 1);
+        }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&mapA0);
+        tc::tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------ TMA producer
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int stage = kb % STAGES;
+            const uint32_t phase = (kb / STAGES) & 1;
+            tc::mbar_wait(&empty[stage], phase ^ 1);
+            tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
+            void* dstA = sA + stage * A_TILE_BYTES;
+            void* dstB = sB + stage * B_TILE_BYTES;
+            if (!p.conv) {
+                tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1, b2);
+                tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, b1, b2);
+            } else {
+                const int kct = p.kc1 + p.kc2;
+                const int tap = kb / kct, kc = kb - tap * kct;
+                const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
+                const int x0 = tx * p.bw * p.stride + dx - p.pad;
+                const int y0 = ty * p.bh * p.stride + dy - p.pad;
+                if (kc < p.kc1)
+                    tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
+                else
+                    tc::tma_load_4d(&mapA1, &full[stage], dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
+                tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, 0, 0);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = tc::make_idesc_f16(BM, BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int stage = kb % STAGES;
+            const uint32_t phase = (kb / STAGES) & 1;
+            tc::mbar_wait(&full[stage], phase);
+            tc::fence_after_sync();
+            const uint32_t a_base = tc::smem_u32(sA + stage * A_TILE_BYTES);
+            const uint32_t b_base = tc::smem_u32(sB + stage * B_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
+                const uint64_t db = tc::make_desc_sw128(b_base + k * 32);
+                tc::mma_f16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+            }
+            tc::mma_commit(&empty[stage]);
+        }
+        tc::mma_commit(tmem_full);
+    } else if (warp >= 2) {
+        // ------------------------------------------------------------ epilogue
+        tc::mbar_wait(tmem_full, 0);
+        tc::fence_after_sync();
+        const int q = warp & 3;             // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;      // row of the 128-row tile == TMEM lane
+        // output row address
+        bool row_ok;
+        long out_off, res_off;
+        int img = 0;
+        if (!p.conv) {
+            const int m = m_blk * BM + row;
+            row_ok = m < p.M;
+            out_off = static_cast<long>(b2) * p.so2 + static_cast<long>(b1) * p.so1 + static_cast<long>(m) * p.ldo;
+            res_off = static_cast<long>(b2) * p.sr2 + static_cast<long>(b1) * p.sr1 + static_cast<long>(m) * p.ldr;
+        } else {
+            const int xi = row % p.bw, yi = (row / p.bw) % p.bh, bi = row / (p.bw * p.bh);
+            const int x = tx * p.bw + xi, y = ty * p.bh + yi;
+            img = tb * p.bb + bi;
+            row_ok = (x < p.Wo) && (y < p.Ho) && (img < p.Bn);
+            out_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldo;
+            res_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldr;
+        }
+        const int m_glob = m_blk * BM + row;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+            tc::tmem_wait_ld();
+            const int n0 = n_blk * BN + c0;
+            if (!row_ok || n0 >= p.N) continue;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float acc = __uint_as_float(v[i]) * p.alpha;
+                const int n = n0 + i;
+                if (n < p.N) {
+                    if (p.bias_mode == 1) acc += __half2float(p.bias[n]);
+                    else if (p.bias_mode == 2) acc += __half2float(p.bias[m_glob]);
+                    if (p.bias2) acc += __half2float(p.bias2[static_cast<long>(img) * p.N + n]);
+                    acc = apply_act(acc, p.act);
+                    if (p.residual) acc += __half2float(p.residual[res_off + n]);
+                }
+                f[i] = acc;
+            }
+            if (p.out_f32) {
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + i < p.N) p.out_f32[out_off + n0 + i] = f[i];
+            } else if (n0 + 32 <= p.N && ((out_off + n0) & 7) == 0) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + out_off + n0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
+                    __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
+                    __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
+                    __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    dst[i] = pk;
+                }
+            } else {
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + i < p.N) p.out[out_off + n0 + i] = __float2half_rn(f[i]);
+            }
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(sym);
+    });
+    return fn;
+}
+
+// fp16 tensor map, rank 4, dims/strides innermost first (strides in elements; stride[0] must be 1)
+int make_map(CUtensorMap* map, const void* ptr, const long dims[4], const long strides[4], const int box[4],
+             const int estrides[4]) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return rf_fail(RF_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bx[4], es[4];
+    for (int i = 0; i < 4; ++i) {
+        gdim[i] = static_cast<cuuint64_t>(dims[i]);
+        bx[i] = static_cast<cuuint32_t>(box[i]);
+        es[i] = static_cast<cuuint32_t>(estrides[i]);
+        if (i) {
+            gstr[i - 1] = static_cast<cuuint64_t>(strides[i]) * 2;
+            if (gstr[i - 1] % 16) return rf_fail(RF_ERR_INVALID, "tensor map: stride not a multiple of 16 bytes");
+        }
+    }
+    if (reinterpret_cast<uintptr_t>(ptr) % 16) return rf_fail(RF_ERR_INVALID, "tensor map: base not 16-byte aligned");
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return rf_fail(RF_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+    return RF_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
+           cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(STAGES) * (A_TILE_BYTES + BN * BK * 2) + 1024;
+    static std::once_flag once;
+    static cudaError_t aerr = cudaSuccess;
+    std::call_once(once, [&] {
+        aerr = cudaFuncSetAttribute(k_tc_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    });
+    if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(aerr));
+    k_tc_gemm<BN, STAGES><<<grid, 192, smem, st>>>(a0, a1, b, p);
+    RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
+    return RF_OK;
+}
+
+int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, int tiles_m,
+             int nbatch, cudaStream_t st) {
+    if (N > 64) {
+        dim3 grid((N + 127) / 128, tiles_m, nbatch);
+        return launch<128, 4>(a0, a1, b, p, grid, st);
+    }
+    dim3 grid((N + 63) / 64, tiles_m, nbatch);
+    return launch<64, 6>(a0, a1, b, p, grid, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ C-ABI
+extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
+    if (!d || !d->A || !d->B || !d->D || d->M <= 0 || d->N <= 0 || d->K <= 0)
+        return rf_fail(RF_ERR_INVALID, "rf_gemm_f16: bad argument");
+    const int b1 = d->batch1 > 0 ? d->batch1 : 1, b2 = d->batch2 > 0 ? d->batch2 : 1;
+    CUtensorMap ma, mb;
+    {
+        const long dims[4] = {d->K, d->M, b1, b2};
+        const long str[4] = {1, d->lda, b1 > 1 ? d->sa1 : d->lda, b2 > 1 ? d->sa2 : d->lda};
+        const int box[4] = {BK, BM, 1, 1};
+        const int es[4] = {1, 1, 1, 1};
+        int rc = make_map(&ma, d->A, dims, str, box, es);
+        if (rc) return rc;
+    }
+    const int BN = d->N > 64 ? 128 : 64;
+    {
+        const long dims[4] = {d->K, d->N, b1, b2};
+        const long str[4] = {1, d->ldb, b1 > 1 ? d->sb1 : d->ldb, b2 > 1 ? d->sb2 : d->ldb};
+        const int box[4] = {BK, BN, 1, 1};
+        const int es[4] = {1, 1, 1, 1};
+        int rc = make_map(&mb, d->B, dims, str, box, es);
+        if (rc) return rc;
+    }
+    TcParams p{};
+    p.M = d->M; p.N = d->N; p.K = d->K;
+    p.batch1 = b1; p.batch2 = b2;
+    p.num_kb = (d->K + BK - 1) / BK;
+    p.conv = 0;
+    p.out = static_cast<__half*>(d->out_f32 ? nullptr : d->D);
+    p.out_f32 = static_cast<float*>(d->out_f32 ? d->D : nullptr);
+    p.ldo = d->ldd; p.so1 = d->sd1; p.so2 = d->sd2;
+    p.bias = static_cast<const __half*>(d->bias);
+    p.bias_mode = d->bias ? d->bias_mode : 0;
+    p.bias2 = nullptr;
+    p.residual = static_cast<const __half*>(d->residual);
+    p.ldr = d->ldr; p.sr1 = d->sr1; p.sr2 = d->sr2;
+    p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+    p.act = d->act;
+    return dispatch(d->N, ma, ma, mb, p, (d->M + BM - 1) / BM, b1 * b2, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
+    if (!d || !d->x1 || !d->w || !d->out || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C1 <= 0 || d->Cout <= 0)
+        return rf_fail(RF_ERR_INVALID, "rf_conv2d_f16: bad argument");
+    if (d->ksize != 1 && d->ksize != 3) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: kernel size must be 1 or 3");
+    if (d->stride != 1 && d->stride != 2) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: stride must be 1 or 2");
+    if ((d->C1 % BK) || (d->x2 && (d->C2 % BK)))
+        return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: channel counts must be multiples of 64 (use the direct "
+                                           "convolution for the 4- and 3-channel layers)");
+    const int pad = d->ksize == 3 ? 1 : 0;
+    const int Ho = (d->H + 2 * pad - d->ksize) / d->stride + 1;
+    const int Wo = (d->W + 2 * pad - d->ksize) / d->stride + 1;
+    // output pixels per tile
+    int bw = Wo >= 128 ? 128 : Wo;
+    while (BM % bw) --bw;  // bw must divide 128
+    int bh = BM / bw;
+    if (bh > Ho) bh = Ho;
+    while ((BM / bw) % bh) --bh;
+    const int bb = BM / (bw * bh);
+    const int C2 = d->x2 ? d->C2 : 0;
+    CUtensorMap m1, m2, mb;
+    const int s = d->stride;
+    {
+        const long dims[4] = {d->C1, d->W, d->H, d->B};
+        const long str[4] = {1, d->C1, static_cast<long>(d->W) * d->C1, static_cast<long>(d->H) * d->W * d->C1};
+        const int box[4] = {BK, (bw - 1) * s + 1, (bh - 1) * s + 1, bb};
+        const int es[4] = {1, s, s, 1};
+        int rc = make_map(&m1, d->x1, dims, str, box, es);
+        if (rc) return rc;
+    }
+    m2 = m1;
+    if (d->x2) {
+        const long dims[4] = {C2, d->W, d->H, d->B};
+        const long str[4] = {1, C2, static_cast<long>(d->W) * C2, static_cast<long>(d->H) * d->W * C2};
+        const int box[4] = {BK, (bw - 1) * s + 1, (bh - 1) * s + 1, bb};
+        const int es[4] = {1, s, s, 1};
+        int rc = make_map(&m2, d->x2, dims, str, box, es);
+        if (rc) return rc;
+    }
+    const int taps = d->ksize * d->ksize;
+    const long Ktot = static_cast<long>(taps) * (d->C1 + C2);
+    const int BN = d->Cout > 64 ? 128 : 64;
+    {
+        const long dims[4] = {Ktot, d->Cout, 1, 1};
+        const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
+        const int box[4] = {BK, BN, 1, 1};
+        const int es[4] = {1, 1, 1, 1};
+        int rc = make_map(&mb, d->w, dims, str, box, es);
+        if (rc) return rc;
+    }
+    TcParams p{};
+    p.M = 0; p.N = d->Cout; p.K = static_cast<int>(Ktot);
+    p.batch1 = 1; p.batch2 = 1;
+    p.conv = 1; p.taps = taps;
+    p.kc1 = d->C1 / BK; p.kc2 = C2 / BK;
+    p.num_kb = taps * (p.kc1 + p.kc2);
+    p.stride = s; p.pad = pad;
+    p.Ho = Ho; p.Wo = Wo; p.Bn = d->B;
+    p.bw = bw; p.bh = bh; p.bb = bb;
+    p.tiles_x = (Wo + bw - 1) / bw;
+    p.tiles_y = (Ho + bh - 1) / bh;
+    const int tiles_b = (d->B + bb - 1) / bb;
+    p.out = static_cast<__half*>(d->out);
+    p.out_f32 = nullptr;
+    p.ldo = d->Cout; p.ldr = d->Cout;
+    p.bias = static_cast<const __half*>(d->bias);
+    p.bias_mode = d->bias ? 1 : 0;
+    p.bias2 = static_cast<const __half*>(d->bias_per_image);
+    p.residual = static_cast<const __half*>(d->residual);
+    p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+    p.act = d->act;
+    return dispatch(d->Cout, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+}

@@ -141,6 +141,31 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
         if (x.r != y.r) return x.r < y.r;
         return x.idx < y.idx;
     });
+    // Within each r block, interleave the positions round-robin over (idx mod 16) so that any 16
+    // consecutive bins (a half warp of 8-byte shared-memory accesses at V[idx] and at the partner
+    // position 4409-idx) fall in 16 distinct bank pairs.
+    {
+        std::vector<Ent> out;
+        out.reserve(ents.size());
+        size_t i0 = 0;
+        while (i0 < ents.size()) {
+            size_t i1 = i0;
+            while (i1 < ents.size() && ents[i1].r == ents[i0].r && ((ents[i1].k ^ ents[i0].k) & 1) == 0) ++i1;
+            std::vector<std::vector<Ent>> cls(16);
+            for (size_t i = i0; i < i1; ++i) cls[ents[i].idx & 15].push_back(ents[i]);
+            std::vector<size_t> cur(16, 0);
+            size_t left = i1 - i0;
+            while (left) {
+                for (int c = 0; c < 16; ++c)
+                    if (cur[c] < cls[c].size()) {
+                        out.push_back(cls[c][cur[c]++]);
+                        --left;
+                    }
+            }
+            i0 = i1;
+        }
+        ents.swap(out);
+    }
     p.n_live = static_cast<int>(ents.size());
     p.bins.resize(p.n_live);
     p.pp.resize(p.n_live);
@@ -162,7 +187,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
                   (idx2 << 15) | (static_cast<uint32_t>(k & 7) << 28);
     }
 
-    // ---- modulation x window tables at PFA (time-side) positions
+    // ---- modulation x window tables, time-side (Ruritanian) index n'(a,b,c), stored [r][b][c][a]
     p.wt_fwd.assign(static_cast<size_t>(4) * p.W * 2, 0.f);
     p.wt_inv.assign(static_cast<size_t>(4) * p.W * 2, 0.f);
     for (int r = 0; r < 4; ++r)
@@ -170,7 +195,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
             for (int b = 0; b < RF_NB; ++b)
                 for (int c = 0; c < RF_NC; ++c) {
                     const int n = rf_pfa_n_of(a, b, c);
-                    const int pos = rf_pfa_pos(a, b, c);
+                    const int pos = b * 490 + c * 10 + a;  // table order [b][c][a]: lanes run over a
                     const long q = (static_cast<long>(r) * n) % p.N;
                     const double ang = -2.0 * M_PI * static_cast<double>(q) / p.N;
                     const double w = p.window[n];

@@ -23,8 +23,8 @@ struct rf_plan_host {
     std::vector<int32_t> bins;    // [n_live] private order j -> STFT bin k
     std::vector<int32_t> jofk;    // [F] bin k -> j or -1
     std::vector<uint32_t> pp;     // [n_live] r | idx<<2 | idx2<<15 | (k&7)<<28
-    std::vector<float> wt_fwd;    // [4][W][2]  w[n'] * exp(-2 pi i r n'/N) at PFA position
-    std::vector<float> wt_inv;    // [4][W][2]  w[n']/N * exp(+2 pi i r n'/N)
+    std::vector<float> wt_fwd;    // [4][9][49][10][2]  w[n'] * exp(-2 pi i r n'/N), n' = n_of(a,b,c)
+    std::vector<float> wt_inv;    // same layout, w[n']/N * exp(+2 pi i r n'/N)
     // mel filterbank in sparse forms over the private bin order
     std::vector<int32_t> melcol_ptr;  // [n_mels+1]  CSR by mel column: entries (j, w)
     std::vector<int32_t> melcol_j;

@@ -37,6 +37,28 @@ class PlanDesc(C.Structure):
     ]
 
 
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("batch1", C.c_int32), ("batch2", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("sa1", C.c_int64), ("sa2", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("sb1", C.c_int64), ("sb2", C.c_int64),
+        ("D", C.c_void_p), ("ldd", C.c_int64), ("sd1", C.c_int64), ("sd2", C.c_int64),
+        ("bias", C.c_void_p), ("bias_mode", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int64), ("sr1", C.c_int64), ("sr2", C.c_int64),
+        ("alpha", C.c_float), ("act", C.c_int32), ("out_f32", C.c_int32),
+    ]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C1", C.c_int32), ("C2", C.c_int32),
+        ("Cout", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("x1", C.c_void_p), ("x2", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
+        ("bias_per_image", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("alpha", C.c_float), ("act", C.c_int32),
+    ]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [
         ("n_freq", C.c_int32),
@@ -68,6 +90,8 @@ SIGNATURES = {
     "rf_stft_mel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_mel_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rf_gemm_f16": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "rf_conv2d_f16": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "rf_image_to_mel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                   C.c_void_p]),
     "rf_mel_to_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,

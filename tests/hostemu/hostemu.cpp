@@ -2,7 +2,7 @@
 //
 // TEST INFRASTRUCTURE ONLY.  This file re-uses the exact phase functions the CUDA kernels
 // call (riffusion-hobby_b200/csrc/rf_gl_phases.cuh, compiled for the host) and replaces
-// "224 threads + __syncthreads()" by loops over tid, so that the index tables, the
+// "256 threads + __syncthreads()" by loops over tid, so that the index tables, the
 // prime-factor FFT passes, the pair packing and the overlap-add chunking can be checked
 // against torch on a box without a GPU.  It is never linked into librf_b200.so and the
 // product has no CPU path.
@@ -18,7 +18,7 @@
 #include "rf_plan.h"
 
 namespace {
-constexpr int NT = 224;
+constexpr int NT = RF_NT;
 std::string g_err;
 
 template <typename F>
@@ -46,9 +46,9 @@ void emu_stft_clip(const rf_plan_host& h, const float* x, int L, int T, rf_c32* 
         for (int g = 0; g < 2; ++g) {
             const int t0 = 2 * pr;
             const bool has1 = t0 + 1 < T;
-            phase([&](int tid) { rf_stage_x(tid, NT, xs.data(), x, L, t0, h.H, has1); });
-            phase([&](int tid) { rf_stft_pass_a(tid, NT, V.data(), xs.data(), tb, g); });
-            phase([&](int tid) { rf_pass_b<false>(tid, NT, V.data()); });
+            phase([&](int tid) { rf_stage_x(tid, NT, xs.data(), x, L, t0, h.H); });
+            phase([&](int tid) { rf_stft_pass_b(tid, NT, V.data(), xs.data(), tb, g, has1); });
+            phase([&](int tid) { rf_pass_a<false>(tid, NT, V.data()); });
             phase([&](int tid) { rf_pass_c<false>(tid, NT, V.data()); });
             const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
             rf_c32* out0 = R + static_cast<size_t>(t0) * tb.n_live;
@@ -90,15 +90,18 @@ void emu_istft_clip(const rf_plan_host& h, const float* S, const rf_c32* cur, co
                 in.momentum = momentum;
                 phase([&](int tid) { rf_istft_load(tid, NT, V.data(), tb, j0, j1, in); });
                 phase([&](int tid) { rf_pass_c<true>(tid, NT, V.data()); });
-                phase([&](int tid) { rf_pass_b<true>(tid, NT, V.data()); });
-                phase([&](int tid) { rf_istft_pass_a(tid, NT, V.data(), ola.data() + 2 * pr * h.H, tb, g, has1); });
+                phase([&](int tid) { rf_pass_a<true>(tid, NT, V.data()); });
+                // device: one call with which=2 (barrier between the real- and imaginary-part adds)
+                phase([&](int tid) { rf_istft_pass_b(tid, NT, V.data(), ola.data() + 2 * pr * h.H, tb, g, has1, 0); });
+                phase([&](int tid) { rf_istft_pass_b(tid, NT, V.data(), ola.data() + 2 * pr * h.H, tb, g, has1, 1); });
             }
             std::memcpy(&part[(static_cast<size_t>(g) * nchunks + chunk) * PL], ola.data(), PL * sizeof(float));
         }
     std::vector<float> win2(h.W);
     for (int i = 0; i < h.W; ++i) win2[i] = h.window[i] * h.window[i];
     const int L = h.H * (T - 1);
-    for (int i = 0; i < L; ++i) x[i] = rf_ola_sample(i, part.data(), win2.data(), T, G, PL, nchunks, h.H, h.W);
+    for (int i = 0; i < L; ++i)
+        x[i] = rf_ola_sample(i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PL, nchunks, h.H, h.W);
 }
 }  // namespace
 
