@@ -189,6 +189,42 @@ typedef struct rf_conv_desc {
 } rf_conv_desc;
 int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
 
+/* Memory-bound UNet/VAE operators (fp16 activations, fp32 statistics).  NHWC images, row-major tokens.
+ * Each restates the torch op diffusers calls [diffusers 0.9, absent here: restated from memory]. */
+/* torch.nn.GroupNorm(groups, C, eps) (+ optional SiLU): x,y fp16 [B][HW][C]; d_stats: fp32 scratch [B][groups][2] */
+int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups, const void* gamma, const void* beta,
+                      float eps, int act, void* y, float* d_stats, void* stream);
+/* torch.nn.LayerNorm(C, eps) over rows */
+int rf_layer_norm_f16(const void* x, int rows, int C, const void* gamma, const void* beta, float eps, void* y,
+                      void* stream);
+/* GEGLU: x [rows][2*inner] = (hidden | gate) -> y [rows][inner] = hidden * gelu_erf(gate) */
+int rf_geglu_f16(const void* x, long rows, int inner, void* y, void* stream);
+/* softmax over the first n entries of each row (row pitch `pitch` elements); padding is zeroed */
+int rf_softmax_rows_f16(const void* x, long rows, int n, int pitch, void* y, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest"): [B][H][W][C] -> [B][2H][2W][C] */
+int rf_upsample2x_f16(const void* x, int B, int H, int W, int C, void* y, void* stream);
+/* torch.cat([a, b], dim=1) for NHWC tensors: [pixels][Ca] + [pixels][Cb] -> [pixels][Ca+Cb] */
+int rf_concat_channels_f16(const void* a, const void* b, long pixels, int Ca, int Cb, void* y, void* stream);
+/* conv_in: Conv2d(Cin<=8 -> Cout, 3x3, pad 1) reading NCHW fp16, writing NHWC; w = torch layout [Cout][Cin][3][3] */
+int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int H, int W, int Cout,
+                   void* y_nhwc, void* stream);
+/* conv_out: Conv2d(Cin -> Cout<=8, 3x3, pad 1) reading NHWC, writing NCHW fp16; w packed [Cout][3][3][Cin] */
+int rf_conv_out_f16(const void* x_nhwc, const void* w_packed, const void* bias, int B, int H, int W, int Cin,
+                    int Cout, void* y_nchw, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): t fp32 [B] -> fp16 [B][dim] */
+int rf_timestep_embedding_f16(const float* d_t, int B, int dim, void* out, void* stream);
+int rf_silu_f16(const void* x, long n, void* y, void* stream);
+/* classifier-free guidance + PNDM/PLMS multistep update on n = elements of ONE batch half:
+ *   eps = eps_u + g (eps_t - eps_u) (riffusion_pipeline.py:411-415); e = c0 eps + c1 h1 + c2 h2 + c3 h3;
+ *   prev = ca * sample - cb * e (PNDMScheduler._get_prev_sample).  eps_pair = [uncond | text] (2n). coef4: HOST float[4].
+ *   eps_out (optional) receives the guided eps for the scheduler history. */
+int rf_cfg_pndm_step_f16(const void* eps_pair, long n, float guidance, const void* h1, const void* h2,
+                         const void* h3, const float* coef4, const void* sample, float ca, float cb,
+                         void* eps_out, void* prev_sample, void* stream);
+/* y = a*x + b*noise (scheduler.add_noise), optionally y = y*mask + z*(1-mask) (riffusion_pipeline.py:421-425) */
+int rf_axpby_f16(const void* x, const void* noise, float a, float b, const void* mask, const void* z, long n,
+                 void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

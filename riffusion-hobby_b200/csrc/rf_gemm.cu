@@ -32,6 +32,7 @@ struct TcParams {
     int M, N, K;            // GEMM mode: per-batch extents. conv mode: N = Cout, K unused
     int batch1, batch2;     // grid.z = batch1 * batch2
     int num_kb;             // K slabs
+    int a_m1, a_m2, b_m1, b_m2;  // 0 when the operand is broadcast along that batch dimension (stride 0)
     // conv mode
     int conv;               // 0 = GEMM, 1 = conv
     int taps;               // 1 or 9
@@ -114,8 +115,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             void* dstA = sA + stage * A_TILE_BYTES;
             void* dstB = sB + stage * B_TILE_BYTES;
             if (!p.conv) {
-                tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1, b2);
-                tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, b1, b2);
+                tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
+                tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, b1 * p.b_m1, b2 * p.b_m2);
             } else {
                 const int kct = p.kc1 + p.kc2;
                 const int tap = kb / kct, kc = kb - tap * kct;
@@ -299,10 +300,13 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
     if (!d || !d->A || !d->B || !d->D || d->M <= 0 || d->N <= 0 || d->K <= 0)
         return rf_fail(RF_ERR_INVALID, "rf_gemm_f16: bad argument");
     const int b1 = d->batch1 > 0 ? d->batch1 : 1, b2 = d->batch2 > 0 ? d->batch2 : 1;
+    // a batch stride of 0 means "broadcast": the map gets extent 1 there and the kernel passes coordinate 0
+    const int a_m1 = (b1 > 1 && d->sa1 != 0) ? 1 : 0, a_m2 = (b2 > 1 && d->sa2 != 0) ? 1 : 0;
+    const int b_m1 = (b1 > 1 && d->sb1 != 0) ? 1 : 0, b_m2 = (b2 > 1 && d->sb2 != 0) ? 1 : 0;
     CUtensorMap ma, mb;
     {
-        const long dims[4] = {d->K, d->M, b1, b2};
-        const long str[4] = {1, d->lda, b1 > 1 ? d->sa1 : d->lda, b2 > 1 ? d->sa2 : d->lda};
+        const long dims[4] = {d->K, d->M, a_m1 ? b1 : 1, a_m2 ? b2 : 1};
+        const long str[4] = {1, d->lda, a_m1 ? d->sa1 : d->lda, a_m2 ? d->sa2 : d->lda};
         const int box[4] = {BK, BM, 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&ma, d->A, dims, str, box, es);
@@ -310,8 +314,8 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
     }
     const int BN = d->N > 64 ? 128 : 64;
     {
-        const long dims[4] = {d->K, d->N, b1, b2};
-        const long str[4] = {1, d->ldb, b1 > 1 ? d->sb1 : d->ldb, b2 > 1 ? d->sb2 : d->ldb};
+        const long dims[4] = {d->K, d->N, b_m1 ? b1 : 1, b_m2 ? b2 : 1};
+        const long str[4] = {1, d->ldb, b_m1 ? d->sb1 : d->ldb, b_m2 ? d->sb2 : d->ldb};
         const int box[4] = {BK, BN, 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&mb, d->B, dims, str, box, es);
@@ -322,6 +326,7 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
     p.batch1 = b1; p.batch2 = b2;
     p.num_kb = (d->K + BK - 1) / BK;
     p.conv = 0;
+    p.a_m1 = a_m1; p.a_m2 = a_m2; p.b_m1 = b_m1; p.b_m2 = b_m2;
     p.out = static_cast<__half*>(d->out_f32 ? nullptr : d->D);
     p.out_f32 = static_cast<float*>(d->out_f32 ? d->D : nullptr);
     p.ldo = d->ldd; p.so1 = d->sd1; p.so2 = d->sd2;

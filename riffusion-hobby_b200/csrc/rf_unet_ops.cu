@@ -1,0 +1,446 @@
+// Path (b) memory-bound operators around the tensor-core GEMM/conv kernel: GroupNorm(+SiLU),
+// LayerNorm, GEGLU, row softmax, nearest-2x upsample, the 4-/3-channel edge convolutions, the
+// sinusoidal timestep embedding, and the scheduler / guidance element-wise steps.
+// Activations fp16 (NHWC), statistics and arithmetic fp32.
+//
+// Reference arithmetic (reached from riffusion/riffusion_pipeline.py:379,403-425 through diffusers
+// 0.9 [restated from memory, package absent]): torch.nn.GroupNorm / LayerNorm / F.gelu / softmax /
+// F.interpolate(nearest) / Conv2d, PNDMScheduler.step, classifier-free guidance combine.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "rf_common.h"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+
+// ---------------------------------------------------------------- GroupNorm (NHWC)
+// pass 1: per (image, group) sum and sum of squares. grid (slabs, B); each CTA reduces a slab of
+// pixels for all channels, then one atomicAdd per (group, stat).  Accumulating E[x] and E[x^2] in
+// fp32 over <= 4096*40 values of O(1) magnitude keeps ~1e-6 relative accuracy on the variance.
+__global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int slab,
+                           float* __restrict__ stats /*[B][G][2]*/) {
+    extern __shared__ float sh[];  // [2*G]
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int cpg = C / G;   // even for every SD layer (4 ... 80)
+    const int C2 = C >> 1;   // half2 units
+    const int CW = C2 < static_cast<int>(blockDim.x) ? C2 : static_cast<int>(blockDim.x);  // lanes across channels
+    const int R = blockDim.x / CW;                                                         // pixel rows in flight
+    const int prow = threadIdx.x / CW, lc = threadIdx.x - prow * CW;
+    const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
+    if (prow < R) {
+        for (int c2 = lc; c2 < C2; c2 += CW) {
+            float s = 0.f, ss = 0.f;
+            for (int p = p0 + prow; p < p1; p += R) {
+                const float2 v = __half22float2(xb[static_cast<size_t>(p) * C2 + c2]);
+                s += v.x + v.y;
+                ss += v.x * v.x + v.y * v.y;
+            }
+            const int g = (2 * c2) / cpg;
+            atomicAdd(&sh[2 * g], s);
+            atomicAdd(&sh[2 * g + 1], ss);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
+        atomicAdd(&stats[static_cast<size_t>(b) * 2 * G + i], sh[i]);
+}
+
+// pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU
+__global__ void k_gn_apply(const __half* __restrict__ x, const float* __restrict__ stats,
+                           const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C,
+                           int G, float eps, int act, __half* __restrict__ y) {
+    const int b = blockIdx.y;
+    const size_t n2 = static_cast<size_t>(HW) * C / 2;
+    const int cpg = C / G;
+    const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
+    const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
+    __half2* yb = reinterpret_cast<__half2*>(y + static_cast<size_t>(b) * HW * C);
+    const __half2* g2 = reinterpret_cast<const __half2*>(gamma);
+    const __half2* b2 = reinterpret_cast<const __half2*>(beta);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c2 = static_cast<int>(i % (C / 2));
+        const int g = (2 * c2) / cpg;
+        const float mean = stats[(static_cast<size_t>(b) * G + g) * 2] * inv_n;
+        const float var = fmaxf(stats[(static_cast<size_t>(b) * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float2 v = __half22float2(xb[i]);
+        const float2 ga = __half22float2(g2[c2]);
+        const float2 be = __half22float2(b2[c2]);
+        float o0 = (v.x - mean) * rstd * ga.x + be.x;
+        float o1 = (v.y - mean) * rstd * ga.y + be.y;
+        if (act) {
+            o0 = silu(o0);
+            o1 = silu(o1);
+        }
+        yb[i] = __floats2half2_rn(o0, o1);
+    }
+}
+
+// ---------------------------------------------------------------- LayerNorm over the last dim
+__global__ void k_layernorm(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                            const __half* __restrict__ beta, int rows, int C, float eps, __half* __restrict__ y) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half2* xr = reinterpret_cast<const __half2*>(x + static_cast<size_t>(row) * C);
+    float s = 0.f, ss = 0.f;
+    for (int i = lane; i < C / 2; i += 32) {
+        const float2 v = __half22float2(xr[i]);
+        s += v.x + v.y;
+        ss += v.x * v.x + v.y * v.y;
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const float mean = s / C;
+    const float rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+    __half2* yr = reinterpret_cast<__half2*>(y + static_cast<size_t>(row) * C);
+    const __half2* g2 = reinterpret_cast<const __half2*>(gamma);
+    const __half2* b2 = reinterpret_cast<const __half2*>(beta);
+    for (int i = lane; i < C / 2; i += 32) {
+        const float2 v = __half22float2(xr[i]);
+        const float2 ga = __half22float2(g2[i]);
+        const float2 be = __half22float2(b2[i]);
+        yr[i] = __floats2half2_rn((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y);
+    }
+}
+
+// ---------------------------------------------------------------- GEGLU: y = h * gelu(gate), [rows][2*inner] -> [rows][inner]
+__global__ void k_geglu(const __half* __restrict__ x, size_t rows, int inner, __half* __restrict__ y) {
+    const size_t n2 = rows * (inner / 2);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / (inner / 2);
+        const int c2 = static_cast<int>(i % (inner / 2));
+        const __half2* xr = reinterpret_cast<const __half2*>(x + r * 2 * inner);
+        const float2 h = __half22float2(xr[c2]);
+        const float2 g = __half22float2(xr[inner / 2 + c2]);
+        const float g0 = 0.5f * g.x * (1.f + erff(g.x * 0.70710678118654752f));  // exact (erf) GELU
+        const float g1 = 0.5f * g.y * (1.f + erff(g.y * 0.70710678118654752f));
+        reinterpret_cast<__half2*>(y + r * inner)[c2] = __floats2half2_rn(h.x * g0, h.y * g1);
+    }
+}
+
+// ---------------------------------------------------------------- row softmax (fp16 in/out, fp32 math), one warp per row
+__global__ void k_softmax_rows(const __half* __restrict__ x, size_t rows, int n, int pitch, __half* __restrict__ y) {
+    const size_t row = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half* xr = x + row * pitch;
+    __half* yr = y + row * pitch;
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, __half2float(xr[i]));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) s += __expf(__half2float(xr[i]) - m);
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int i = lane; i < n; i += 32) yr[i] = __float2half_rn(__expf(__half2float(xr[i]) - m) * inv);
+    for (int i = n + lane; i < pitch; i += 32) yr[i] = __float2half_rn(0.f);  // zero the pitch padding
+}
+
+// ---------------------------------------------------------------- nearest 2x upsample (NHWC)
+__global__ void k_upsample2x(const __half* __restrict__ x, int B, int H, int W, int C, __half* __restrict__ y) {
+    const int C8 = C / 8;
+    const size_t n = static_cast<size_t>(B) * 2 * H * 2 * W * C8;
+    const uint4* xs = reinterpret_cast<const uint4*>(x);
+    uint4* ys = reinterpret_cast<uint4*>(y);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C8);
+        size_t p = i / C8;
+        const int xo = static_cast<int>(p % (2 * W));
+        p /= 2 * W;
+        const int yo = static_cast<int>(p % (2 * H));
+        const int b = static_cast<int>(p / (2 * H));
+        ys[i] = xs[((static_cast<size_t>(b) * H + yo / 2) * W + xo / 2) * C8 + c];
+    }
+}
+
+// ---------------------------------------------------------------- edge convolutions (tiny channel counts)
+// conv_in: NCHW fp16 (B, Cin<=8, H, W) -> NHWC fp16 (B, H, W, Cout), 3x3 pad 1. weights [Cout][Cin][3][3] fp16.
+__global__ void k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                          int B, int Cin, int H, int W, int Cout, __half* __restrict__ y) {
+    extern __shared__ float wsm[];  // [Cout][Cin*9]
+    const int K = Cin * 9;
+    for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) wsm[i] = __half2float(w[i]);
+    __syncthreads();
+    const size_t pix = static_cast<size_t>(blockIdx.x);  // one pixel per CTA
+    const int xq = static_cast<int>(pix % W), yq = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float in[72];
+    for (int c = 0; c < Cin; ++c)
+        for (int t = 0; t < 9; ++t) {
+            const int yy = yq + t / 3 - 1, xx = xq + t % 3 - 1;
+            in[c * 9 + t] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                ? __half2float(x[((static_cast<size_t>(b) * Cin + c) * H + yy) * W + xx])
+                                : 0.f;
+        }
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+        float acc = bias ? __half2float(bias[co]) : 0.f;
+        for (int k = 0; k < K; ++k) acc += wsm[co * K + k] * in[k];
+        y[pix * Cout + co] = __float2half_rn(acc);
+    }
+}
+
+// conv_out: NHWC fp16 (B, H, W, Cin) -> NCHW fp16/fp32 (B, Cout<=8, H, W), 3x3 pad 1. weights packed [Cout][3][3][Cin].
+// One warp per output pixel; lanes split the channels.
+__global__ void k_conv_out(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                           int B, int H, int W, int Cin, int Cout, __half* __restrict__ y) {
+    const size_t pix = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= static_cast<size_t>(B) * H * W) return;
+    const int xq = static_cast<int>(pix % W), yq = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int t = 0; t < 9; ++t) {
+        const int yy = yq + t / 3 - 1, xx = xq + t % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const __half* xp = x + ((static_cast<size_t>(b) * H + yy) * W + xx) * Cin;
+        for (int c = lane; c < Cin; c += 32) {
+            const float v = __half2float(xp[c]);
+            for (int o = 0; o < Cout; ++o) acc[o] += v * __half2float(w[(static_cast<size_t>(o) * 9 + t) * Cin + c]);
+        }
+    }
+    for (int o = 0; o < Cout; ++o) {
+        const float s = warp_sum(acc[o]);
+        if (lane == 0)
+            y[((static_cast<size_t>(b) * Cout + o) * H + yq) * W + xq] = __float2half_rn(s + (bias ? __half2float(bias[o]) : 0.f));
+    }
+}
+
+// ---------------------------------------------------------------- sinusoidal timestep embedding
+// diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i), sin(t f_i)], f_i = 10000^(-i/half)
+__global__ void k_timestep_embedding(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half_dim = dim / 2;
+    if (i >= B * half_dim) return;
+    const int b = i / half_dim, k = i % half_dim;
+    const float freq = expf(-logf(10000.f) * static_cast<float>(k) / static_cast<float>(half_dim));
+    const float a = t[b] * freq;
+    out[static_cast<size_t>(b) * dim + k] = __float2half_rn(cosf(a));
+    out[static_cast<size_t>(b) * dim + half_dim + k] = __float2half_rn(sinf(a));
+}
+
+__global__ void k_silu(const __half* __restrict__ x, size_t n, __half* __restrict__ y) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        y[i] = __float2half_rn(silu(__half2float(x[i])));
+}
+
+// ---------------------------------------------------------------- guidance + scheduler element-wise step
+// eps = eps_u + g (eps_t - eps_u)            (riffusion_pipeline.py:411-415, fp16 arithmetic like torch)
+// e   = sum_j coef[j] * hist_j  (hist_0 = eps)  PNDM/PLMS linear multistep combination
+// x'  = ca * x - cb * e                       PNDMScheduler._get_prev_sample
+// All tensors fp16 NCHW (B,4,64,64); eps_pair holds [uncond batch | text batch].
+__global__ void k_cfg_pndm_step(const __half* __restrict__ eps_pair, size_t n, float guidance,
+                                const __half* __restrict__ h1, const __half* __restrict__ h2,
+                                const __half* __restrict__ h3, float c0, float c1, float c2, float c3,
+                                const __half* __restrict__ sample, float ca, float cb,
+                                __half* __restrict__ eps_out, __half* __restrict__ prev_sample) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const __half eu = eps_pair[i], et = eps_pair[n + i];
+        // torch evaluates this in fp16: (et - eu) rounded, * g rounded, + eu rounded
+        const __half d = __hsub(et, eu);
+        const __half gd = __float2half_rn(__half2float(d) * guidance);
+        const __half e0 = __hadd(eu, gd);
+        if (eps_out) eps_out[i] = e0;
+        float e = c0 * __half2float(e0);
+        if (h1) e += c1 * __half2float(h1[i]);
+        if (h2) e += c2 * __half2float(h2[i]);
+        if (h3) e += c3 * __half2float(h3[i]);
+        prev_sample[i] = __float2half_rn(ca * __half2float(sample[i]) - cb * e);
+    }
+}
+
+// add_noise / mask blend: y = a*x + b*n (scheduler.add_noise), optionally blended y*m + z*(1-m)
+__global__ void k_axpby(const __half* __restrict__ x, const __half* __restrict__ nz, float a, float b,
+                        const __half* __restrict__ mask, const __half* __restrict__ z, size_t n,
+                        __half* __restrict__ y) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float v = a * __half2float(x[i]) + b * __half2float(nz[i]);
+        if (mask) {
+            const float m = __half2float(mask[i]);
+            v = v * m + __half2float(z[i]) * (1.f - m);
+        }
+        y[i] = __float2half_rn(v);
+    }
+}
+
+// channel concatenation of two NHWC tensors (torch.cat([a, b], dim=1) in NCHW terms)
+__global__ void k_concat_channels(const __half* __restrict__ a, const __half* __restrict__ b, size_t pixels, int Ca,
+                                  int Cb, __half* __restrict__ y) {
+    const int C8 = (Ca + Cb) / 8, A8 = Ca / 8;
+    const size_t n = pixels * C8;
+    const uint4* as = reinterpret_cast<const uint4*>(a);
+    const uint4* bs = reinterpret_cast<const uint4*>(b);
+    uint4* ys = reinterpret_cast<uint4*>(y);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t p = i / C8;
+        const int c = static_cast<int>(i % C8);
+        ys[i] = c < A8 ? as[p * A8 + c] : bs[p * (Cb / 8) + (c - A8)];
+    }
+}
+
+inline unsigned grid_for(size_t n, int block) {
+    size_t g = (n + block - 1) / block;
+    return static_cast<unsigned>(g > 148 * 16 ? 148 * 16 : (g ? g : 1));
+}
+
+}  // namespace
+
+extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups, const void* gamma, const void* beta,
+                                 float eps, int act, void* y, float* d_stats, void* stream) {
+    if (!x || !y || !gamma || !beta || !d_stats || B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups ||
+        ((C / groups) & 1))
+        return rf_fail(RF_ERR_INVALID, "rf_group_norm_f16: bad argument (channels per group must be even)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RF_CUDA_TRY(cudaMemsetAsync(d_stats, 0, static_cast<size_t>(B) * groups * 2 * sizeof(float), st));
+    const int slab = 64;
+    dim3 grid((HW + slab - 1) / slab, B);
+    k_gn_stats<<<grid, 256, 2 * groups * sizeof(float), st>>>(static_cast<const __half*>(x), HW, C, groups, slab,
+                                                                  d_stats);
+    RF_CUDA_LAUNCH_CHECK("k_gn_stats");
+    const size_t n2 = static_cast<size_t>(HW) * C / 2;
+    dim3 grid2(grid_for(n2, 256), B);
+    k_gn_apply<<<grid2, 256, 0, st>>>(static_cast<const __half*>(x), d_stats, static_cast<const __half*>(gamma),
+                                      static_cast<const __half*>(beta), HW, C, groups, eps, act,
+                                      static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_gn_apply");
+    return RF_OK;
+}
+
+extern "C" int rf_layer_norm_f16(const void* x, int rows, int C, const void* gamma, const void* beta, float eps, void* y,
+                                 void* stream) {
+    if (!x || !y || !gamma || !beta || rows <= 0 || C <= 0 || (C & 1)) return rf_fail(RF_ERR_INVALID, "rf_layer_norm_f16: bad argument");
+    k_layernorm<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<const __half*>(gamma), static_cast<const __half*>(beta), rows, C, eps,
+        static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_layernorm");
+    return RF_OK;
+}
+
+extern "C" int rf_geglu_f16(const void* x, long rows, int inner, void* y, void* stream) {
+    if (!x || !y || rows <= 0 || inner <= 0 || (inner & 1)) return rf_fail(RF_ERR_INVALID, "rf_geglu_f16: bad argument");
+    const size_t n2 = static_cast<size_t>(rows) * (inner / 2);
+    k_geglu<<<grid_for(n2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x),
+                                                                             static_cast<size_t>(rows), inner,
+                                                                             static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_geglu");
+    return RF_OK;
+}
+
+extern "C" int rf_softmax_rows_f16(const void* x, long rows, int n, int pitch, void* y, void* stream) {
+    if (!x || !y || rows <= 0 || n <= 0 || pitch < n) return rf_fail(RF_ERR_INVALID, "rf_softmax_rows_f16: bad argument");
+    const size_t blocks = (static_cast<size_t>(rows) + 7) / 8;
+    k_softmax_rows<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<size_t>(rows), n, pitch, static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_softmax_rows");
+    return RF_OK;
+}
+
+extern "C" int rf_upsample2x_f16(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+    if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) return rf_fail(RF_ERR_INVALID, "rf_upsample2x_f16: bad argument");
+    const size_t n = static_cast<size_t>(B) * 4 * H * W * (C / 8);
+    k_upsample2x<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x), B, H, W,
+                                                                                 C, static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_upsample2x");
+    return RF_OK;
+}
+
+extern "C" int rf_concat_channels_f16(const void* a, const void* b, long pixels, int Ca, int Cb, void* y, void* stream) {
+    if (!a || !b || !y || pixels <= 0 || Ca <= 0 || Cb <= 0 || (Ca % 8) || (Cb % 8))
+        return rf_fail(RF_ERR_INVALID, "rf_concat_channels_f16: bad argument");
+    const size_t n = static_cast<size_t>(pixels) * ((Ca + Cb) / 8);
+    k_concat_channels<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<size_t>(pixels), Ca, Cb,
+        static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_concat_channels");
+    return RF_OK;
+}
+
+extern "C" int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int H, int W,
+                              int Cout, void* y_nhwc, void* stream) {
+    if (!x_nchw || !w || !y_nhwc || B <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0) return rf_fail(RF_ERR_INVALID, "rf_conv_in_f16: bad argument");
+    const size_t smem = static_cast<size_t>(Cout) * Cin * 9 * sizeof(float);
+    if (smem > 96 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv_in_f16: weights too large");
+    static bool attr = false;
+    if (!attr) {
+        RF_CUDA_TRY(cudaFuncSetAttribute(k_conv_in, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    k_conv_in<<<static_cast<unsigned>(static_cast<size_t>(B) * H * W), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x_nchw), static_cast<const __half*>(w), static_cast<const __half*>(bias), B, Cin, H, W,
+        Cout, static_cast<__half*>(y_nhwc));
+    RF_CUDA_LAUNCH_CHECK("k_conv_in");
+    return RF_OK;
+}
+
+extern "C" int rf_conv_out_f16(const void* x_nhwc, const void* w_packed, const void* bias, int B, int H, int W, int Cin,
+                               int Cout, void* y_nchw, void* stream) {
+    if (!x_nhwc || !w_packed || !y_nchw || B <= 0 || Cout <= 0 || Cout > 8) return rf_fail(RF_ERR_INVALID, "rf_conv_out_f16: bad argument");
+    const size_t pix = static_cast<size_t>(B) * H * W;
+    k_conv_out<<<static_cast<unsigned>((pix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x_nhwc), static_cast<const __half*>(w_packed), static_cast<const __half*>(bias), B, H,
+        W, Cin, Cout, static_cast<__half*>(y_nchw));
+    RF_CUDA_LAUNCH_CHECK("k_conv_out");
+    return RF_OK;
+}
+
+extern "C" int rf_timestep_embedding_f16(const float* d_t, int B, int dim, void* out, void* stream) {
+    if (!d_t || !out || B <= 0 || dim <= 0 || (dim & 1)) return rf_fail(RF_ERR_INVALID, "rf_timestep_embedding_f16: bad argument");
+    k_timestep_embedding<<<(B * dim / 2 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_t, B, dim, static_cast<__half*>(out));
+    RF_CUDA_LAUNCH_CHECK("k_timestep_embedding");
+    return RF_OK;
+}
+
+extern "C" int rf_silu_f16(const void* x, long n, void* y, void* stream) {
+    if (!x || !y || n <= 0) return rf_fail(RF_ERR_INVALID, "rf_silu_f16: bad argument");
+    k_silu<<<grid_for(static_cast<size_t>(n), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<size_t>(n), static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_silu");
+    return RF_OK;
+}
+
+extern "C" int rf_cfg_pndm_step_f16(const void* eps_pair, long n, float guidance, const void* h1, const void* h2,
+                                    const void* h3, const float* coef4, const void* sample, float ca, float cb,
+                                    void* eps_out, void* prev_sample, void* stream) {
+    if (!eps_pair || !sample || !prev_sample || !coef4 || n <= 0) return rf_fail(RF_ERR_INVALID, "rf_cfg_pndm_step_f16: bad argument");
+    k_cfg_pndm_step<<<grid_for(static_cast<size_t>(n), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(eps_pair), static_cast<size_t>(n), guidance, static_cast<const __half*>(h1),
+        static_cast<const __half*>(h2), static_cast<const __half*>(h3), coef4[0], coef4[1], coef4[2], coef4[3],
+        static_cast<const __half*>(sample), ca, cb, static_cast<__half*>(eps_out), static_cast<__half*>(prev_sample));
+    RF_CUDA_LAUNCH_CHECK("k_cfg_pndm_step");
+    return RF_OK;
+}
+
+extern "C" int rf_axpby_f16(const void* x, const void* noise, float a, float b, const void* mask, const void* z, long n,
+                            void* y, void* stream) {
+    if (!x || !noise || !y || n <= 0 || (mask && !z)) return rf_fail(RF_ERR_INVALID, "rf_axpby_f16: bad argument");
+    k_axpby<<<grid_for(static_cast<size_t>(n), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<const __half*>(noise), a, b, static_cast<const __half*>(mask),
+        static_cast<const __half*>(z), static_cast<size_t>(n), static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_axpby");
+    return RF_OK;
+}

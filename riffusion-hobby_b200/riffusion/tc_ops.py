@@ -40,8 +40,9 @@ def gemm(
         a = a.unsqueeze(0)
     while b.dim() < 4:
         b = b.unsqueeze(0)
-    B2, B1, M, K = a.shape
-    N = b.shape[2]
+    M, K, N = a.shape[2], a.shape[3], b.shape[2]
+    B2, B1 = max(a.shape[0], b.shape[0]), max(a.shape[1], b.shape[1])
+    a = a.expand(B2, B1, M, K)          # broadcast batch dims get stride 0 (handled in the C-ABI)
     b = b.expand(B2, B1, N, K)
     assert b.shape[3] == K and a.stride(3) == 1 and b.stride(3) == 1
     if out is None:
@@ -104,3 +105,137 @@ def conv2d(
     with torch.cuda.device(x.device):
         _native.check(_native.lib().rf_conv2d_f16(C.byref(d), _stream(x)))
     return out
+
+
+# ------------------------------------------------------------------------------ memory-bound operators
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool) -> torch.Tensor:
+    """x: (B, H, W, C) or (B, HW, C) fp16 NHWC -> same shape; GroupNorm (+ SiLU)."""
+    _f16(x, "x")
+    assert x.is_contiguous()
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    y = torch.empty_like(x)
+    stats = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_group_norm_f16(x.data_ptr(), B, HW, C, groups, gamma.data_ptr(), beta.data_ptr(),
+                                                      float(eps), int(silu), y.data_ptr(), stats.data_ptr(), _stream(x)))
+    return y
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _f16(x, "x")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_layer_norm_f16(x.data_ptr(), x.numel() // C, C, gamma.data_ptr(), beta.data_ptr(),
+                                                      float(eps), y.data_ptr(), _stream(x)))
+    return y
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    _f16(x, "x")
+    assert x.is_contiguous()
+    inner = x.shape[-1] // 2
+    y = torch.empty(x.shape[:-1] + (inner,), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_geglu_f16(x.data_ptr(), x.numel() // (2 * inner), inner, y.data_ptr(), _stream(x)))
+    return y
+
+
+def softmax_rows_(x: torch.Tensor, n: int) -> torch.Tensor:
+    """In-place softmax over the first n entries of every row of a contiguous (..., pitch) fp16 tensor."""
+    _f16(x, "x")
+    assert x.is_contiguous()
+    pitch = x.shape[-1]
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_softmax_rows_f16(x.data_ptr(), x.numel() // pitch, n, pitch, x.data_ptr(), _stream(x)))
+    return x
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _f16(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_upsample2x_f16(x.data_ptr(), B, H, W, C, y.data_ptr(), _stream(x)))
+    return y
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _f16(a, "a"), _f16(b, "b")
+    assert a.shape[:-1] == b.shape[:-1] and a.is_contiguous() and b.is_contiguous()
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    y = torch.empty(a.shape[:-1] + (Ca + Cb,), dtype=torch.float16, device=a.device)
+    with torch.cuda.device(a.device):
+        _native.check(_native.lib().rf_concat_channels_f16(a.data_ptr(), b.data_ptr(), a.numel() // Ca, Ca, Cb,
+                                                           y.data_ptr(), _stream(a)))
+    return y
+
+
+def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """(B, Cin<=8, H, W) NCHW fp16 -> (B, H, W, Cout) NHWC; w: torch layout (Cout, Cin, 3, 3) fp16."""
+    _f16(x_nchw, "x")
+    B, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    y = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x_nchw.device)
+    with torch.cuda.device(x_nchw.device):
+        _native.check(_native.lib().rf_conv_in_f16(x_nchw.contiguous().data_ptr(), w.data_ptr(), bias.data_ptr(), B, Cin,
+                                                   H, W, Cout, y.data_ptr(), _stream(x_nchw)))
+    return y
+
+
+def conv_out(x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """(B, H, W, Cin) NHWC -> (B, Cout<=8, H, W) NCHW; w_packed: (Cout, 3, 3, Cin)."""
+    _f16(x_nhwc, "x")
+    B, H, W, Cin = x_nhwc.shape
+    Cout = w_packed.shape[0]
+    y = torch.empty((B, Cout, H, W), dtype=torch.float16, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        _native.check(_native.lib().rf_conv_out_f16(x_nhwc.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), B, H, W, Cin,
+                                                    Cout, y.data_ptr(), _stream(x_nhwc)))
+    return y
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """t: fp32 (B,) device tensor -> (B, dim) fp16 [cos | sin]."""
+    assert t.is_cuda and t.dtype == torch.float32
+    out = torch.empty((t.shape[0], dim), dtype=torch.float16, device=t.device)
+    with torch.cuda.device(t.device):
+        _native.check(_native.lib().rf_timestep_embedding_f16(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream(t)))
+    return out
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    _f16(x, "x")
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_silu_f16(x.data_ptr(), x.numel(), y.data_ptr(), _stream(x)))
+    return y
+
+
+def cfg_pndm_step(eps_pair, guidance, hist, coef, sample, ca, cb, want_eps=True):
+    """eps_pair: (2B, ...) fp16 [uncond | text]; hist: up to 3 earlier guided eps tensors (most recent first);
+    coef: 4 floats; returns (guided eps or None, prev_sample)."""
+    _f16(eps_pair, "eps_pair"), _f16(sample, "sample")
+    n = sample.numel()
+    assert eps_pair.numel() == 2 * n and eps_pair.is_contiguous() and sample.is_contiguous()
+    eps_out = torch.empty_like(sample) if want_eps else None
+    prev = torch.empty_like(sample)
+    h = [None if i >= len(hist) else hist[i].data_ptr() for i in range(3)]
+    c4 = (C.c_float * 4)(*[float(v) for v in coef])
+    with torch.cuda.device(sample.device):
+        _native.check(_native.lib().rf_cfg_pndm_step_f16(
+            eps_pair.data_ptr(), n, float(guidance), h[0], h[1], h[2], c4, sample.data_ptr(), float(ca), float(cb),
+            None if eps_out is None else eps_out.data_ptr(), prev.data_ptr(), _stream(sample)))
+    return eps_out, prev
+
+
+def axpby(x, noise, a, b, mask=None, z=None):
+    _f16(x, "x")
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _native.check(_native.lib().rf_axpby_f16(x.data_ptr(), noise.data_ptr(), float(a), float(b),
+                                                 None if mask is None else mask.data_ptr(),
+                                                 None if z is None else z.data_ptr(), x.numel(), y.data_ptr(), _stream(x)))
+    return y

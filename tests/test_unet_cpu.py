@@ -1,0 +1,52 @@
+"""CPU checks that pin the path (b) oracle as far as the environment allows (diffusers is not installable):
+published parameter count, scheduler constants and the PLMS start-index table of SURVEY Appendix B."""
+import torch
+
+from oracle import unet_oracle as uo
+
+
+def test_sd15_parameter_count_matches_published():
+    with torch.device("meta"):
+        m = uo.UNet2DConditionOracle()
+    assert sum(p.numel() for p in m.parameters()) == 859_520_964     # "860M" UNet of Stable Diffusion 1.x
+
+
+def test_pndm_tables_and_constants():
+    s = uo.PNDMSchedulerOracle()
+    assert abs(float(s.alphas_cumprod[0]) - 0.99915) < 1e-6 and abs(float(s.alphas_cumprod[999]) - 0.0046601) < 1e-6
+    s.set_timesteps(50)
+    ts = s.timesteps.tolist()
+    assert len(ts) == 51 and ts[:4] == [981, 961, 961, 941] and ts[-2:] == [21, 1]
+    # riffusion_pipeline.py:358-396 start arithmetic with steps_offset = 1
+    for strength, t0, n_evals in ((0.75, 741, 38), (1.0, 961, 50), (0.5, 501, 26)):
+        init = min(int(50 * strength) + 1, 50)
+        assert ts[-init] == t0
+        assert len(ts[max(50 - init + 1, 0):]) == n_evals
+    assert abs(float(s.alphas_cumprod[741]) ** 0.5 - 0.245674) < 1e-5
+
+
+def test_plms_step_sequence_on_a_linear_model():
+    """the counter==1 re-step and the Adams-Bashforth weights: with a constant model output e the update
+    x' = ca x - cb e must be applied exactly once per call (the 2nd call restarts from the saved sample)"""
+    s = uo.PNDMSchedulerOracle()
+    s.set_timesteps(50)
+    x = torch.ones(1, 4, 2, 2)
+    e = torch.full_like(x, 0.5)
+    ts = s.timesteps[13:].tolist()
+    x1 = s.step(e, ts[0], x)
+    ca, cb = s.coefficients(741, 721)
+    assert torch.allclose(x1, ca * x - cb * e)
+    x2 = s.step(e, ts[1], x1)                    # counter == 1: redo 741 -> 721 from the saved sample
+    assert torch.allclose(x2, ca * x - cb * e)
+    x3 = s.step(e, ts[2], x2)
+    ca3, cb3 = s.coefficients(701, 681)
+    assert torch.allclose(x3, ca3 * x2 - cb3 * e)
+
+
+def test_small_unet_runs_and_slerp_lerp_fallback():
+    m = uo.init_weights_(uo.UNet2DConditionOracle(block_out_channels=(64, 128, 128, 128), heads=4, cross_attention_dim=64))
+    y = m(torch.randn(2, 4, 16, 16), 741, torch.randn(2, 77, 64))
+    assert y.shape == (2, 4, 16, 16) and torch.isfinite(y).all()
+    a = torch.randn(16384)
+    out = uo.slerp(0.3, a, a * 1.0001)           # |dot| > 0.9995 -> lerp (torch_util.py:34-35)
+    assert torch.allclose(out, 0.7 * a + 0.3 * a * 1.0001, atol=1e-6)

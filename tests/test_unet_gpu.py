@@ -1,0 +1,142 @@
+"""GPU parity of path (b): memory-bound operators, the UNet forward (UNetB200) and the guidance + PNDM step
+against the plain-PyTorch oracle (oracle/unet_oracle.py) evaluated in fp32 with the same (random-init) weights
+and the same inputs.  The oracle's parity is UNPINNED (diffusers is not installable here); its architecture is
+checked by parameter count and scheduler constants in tests/test_unet_cpu.py.
+
+Tolerance for whole-network outputs ("within 1e-3 relative fp16"): our fp16 network and a torch
+fp16 run of the oracle are two differently-rounded fp16 evaluations of the same function, so the bar is
+    rel_l2(ours, fp32 oracle) <= max(1e-3, 1.5 * rel_l2(torch-fp16 oracle, fp32 oracle)).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+def test_elementwise_ops_match_torch(native_lib):
+    from riffusion import tc_ops as ops
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    for (B, H, W, C) in ((2, 16, 16, 320), (1, 8, 8, 2560), (3, 5, 7, 192)):
+        x = torch.randn(B, H, W, C, device="cuda").half()
+        g = (1 + 0.1 * torch.randn(C, device="cuda")).half()
+        b = (0.1 * torch.randn(C, device="cuda")).half()
+        for silu in (False, True):
+            ref = F.group_norm(x.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), eps=1e-5)
+            ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+            got = ops.group_norm(x, g, b, 32, 1e-5, silu)
+            assert (got.float() - ref).abs().max() < 4e-3
+    x = torch.randn(77, 640, device="cuda").half()
+    g = (1 + 0.1 * torch.randn(640, device="cuda")).half()
+    b = (0.1 * torch.randn(640, device="cuda")).half()
+    assert (ops.layer_norm(x, g, b).float() - F.layer_norm(x.float(), (640,), g.float(), b.float())).abs().max() < 4e-3
+    x = torch.randn(50, 2 * 1280, device="cuda").half()
+    h, gate = x.float().chunk(2, dim=-1)
+    assert (ops.geglu(x).float() - h * F.gelu(gate)).abs().max() < 4e-3
+    s = (torch.randn(3, 8, 40, 80, device="cuda") * 3).half()
+    ref = torch.softmax(s.float()[..., :77], dim=-1)
+    got = ops.softmax_rows_(s.clone(), 77)
+    assert (got.float()[..., :77] - ref).abs().max() < 1e-3 and float(got[..., 77:].abs().max()) == 0
+    x = torch.randn(2, 4, 6, 64, device="cuda").half()
+    assert torch.equal(ops.upsample2x(x), F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1))
+    a, bb = torch.randn(2, 3, 3, 128, device="cuda").half(), torch.randn(2, 3, 3, 64, device="cuda").half()
+    assert torch.equal(ops.concat_channels(a, bb), torch.cat([a, bb], dim=-1))
+    # edge convolutions
+    x = torch.randn(2, 4, 12, 12, device="cuda").half()
+    w = (torch.randn(320, 4, 3, 3, device="cuda") * 0.1).half()
+    bias = torch.randn(320, device="cuda").half()
+    ref = F.conv2d(x.float(), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+    assert (ops.conv_in(x, w, bias).float() - ref).abs().max() < 5e-3
+    x = torch.randn(2, 12, 12, 320, device="cuda").half()
+    w = (torch.randn(4, 320, 3, 3, device="cuda") * 0.02).half()
+    bias = torch.randn(4, device="cuda").half()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)
+    assert (ops.conv_out(x, ops.pack_conv_weight(w), bias).float() - ref).abs().max() < 5e-3
+    # sinusoidal embedding
+    from oracle.unet_oracle import timestep_sinusoid
+
+    t = torch.tensor([741.0, 1.0, 981.0], device="cuda")
+    assert (ops.timestep_embedding(t, 320).float() - timestep_sinusoid(t, 320)).abs().max() < 2e-3
+
+
+def _build(cfg, seed=0):
+    from oracle import unet_oracle as uo
+    from riffusion.unet_b200 import UNetB200
+
+    oracle = uo.init_weights_(uo.UNet2DConditionOracle(**cfg), seed=seed).cuda().eval()
+    # round the weights to fp16 once so both sides see identical parameters
+    with torch.no_grad():
+        for p in oracle.parameters():
+            p.copy_(p.half().float())
+    ours = UNetB200(oracle.state_dict(), device="cuda", block_out_channels=cfg.get("block_out_channels", (320, 640, 1280, 1280)),
+                    heads=cfg.get("heads", 8))
+    return oracle, ours
+
+
+@torch.no_grad()
+def _compare(oracle, ours, B, HW, ctx_dim, t):
+    torch.manual_seed(1)
+    x = torch.randn(B, 4, HW, HW, device="cuda").half()
+    ctx = torch.randn(B, 77, ctx_dim, device="cuda").half()
+    ref32 = oracle(x.float(), t, ctx.float())
+    ref16 = oracle.half()(x, t, ctx).float()
+    oracle.float()
+    got = ours(x, t, encoder_hidden_states=ctx).sample
+    assert got.shape == ref32.shape and got.dtype == torch.float16
+    e_ours, e_t16 = rel_l2(got, ref32), rel_l2(ref16, ref32)
+    print(f"rel_l2 ours vs fp32 oracle {e_ours:.3e}; torch fp16 vs fp32 oracle {e_t16:.3e}")
+    assert torch.isfinite(got).all()
+    assert e_ours <= max(1e-3, 1.5 * e_t16)
+    return e_ours, e_t16
+
+
+def test_unet_small_config_matches_oracle(native_lib):
+    cfg = dict(block_out_channels=(64, 128, 128, 128), heads=4, cross_attention_dim=64)
+    oracle, ours = _build(cfg)
+    _compare(oracle, ours, B=2, HW=16, ctx_dim=64, t=741)
+    _compare(oracle, ours, B=3, HW=32, ctx_dim=64, t=1)
+
+
+def test_unet_sd15_full_size_matches_oracle(native_lib):
+    """BASELINE config 3/4 shape: SD-1.5 channels, 64x64 latents, CFG pair (batch 2), random-init weights"""
+    oracle, ours = _build({})
+    _compare(oracle, ours, B=2, HW=64, ctx_dim=768, t=741)
+    # cross-attention K/V cache gives identical results
+    torch.manual_seed(2)
+    x = torch.randn(2, 4, 64, 64, device="cuda").half()
+    ctx = torch.randn(2, 77, 768, device="cuda").half()
+    cache = {}
+    a = ours(x, 501, encoder_hidden_states=ctx, ctx_cache=cache).sample
+    b = ours(x, 501, encoder_hidden_states=ctx, ctx_cache=cache).sample
+    c = ours(x, 501, encoder_hidden_states=ctx).sample
+    assert len(cache) == 16 and torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_cfg_pndm_step_matches_oracle_scheduler(native_lib):
+    from oracle import unet_oracle as uo
+    from riffusion import tc_ops as ops
+
+    torch.manual_seed(3)
+    sch = uo.PNDMSchedulerOracle()
+    sch.set_timesteps(50)
+    x = torch.randn(1, 4, 64, 64, device="cuda").half()
+    hist = [torch.randn_like(x) for _ in range(3)]
+    pair = torch.randn(2, 4, 64, 64, device="cuda").half()
+    g = 7.0
+    eu, et = pair.float().chunk(2)
+    eps = (eu + g * (et - eu))
+    ca, cb = sch.coefficients(701, 681)
+    coef = (55 / 24, -59 / 24, 37 / 24, -9 / 24)
+    e = coef[0] * eps + coef[1] * hist[0].float() + coef[2] * hist[1].float() + coef[3] * hist[2].float()
+    ref = ca * x.float() - cb * e
+    eps_out, prev = ops.cfg_pndm_step(pair, g, hist, coef, x, ca, cb)
+    assert (prev.float() - ref).abs().max() < 2e-2 * ref.abs().max()
+    assert rel_l2(prev, ref) < 2e-3 and rel_l2(eps_out, eps) < 2e-3
+    n = torch.randn_like(x)
+    a = float(sch.alphas_cumprod[741])
+    assert rel_l2(ops.axpby(x, n, a ** 0.5, (1 - a) ** 0.5), sch.add_noise(x.float(), n.float(), 741)) < 1e-3
