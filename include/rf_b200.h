@@ -186,6 +186,9 @@ typedef struct rf_conv_desc {
     void* out;                 /* fp16 [B][Ho][Wo][Cout] */
     float alpha;               /* 0 is treated as 1 */
     int32_t act;
+    int32_t pad_mode;          /* 0: symmetric padding ksize/2 (torch padding=1 for 3x3);
+                                  1: no left/top padding, implicit zero padding on the right/bottom edge
+                                     (diffusers VAE Downsample2D: F.pad(x, (0,1,0,1)) then conv padding=0) */
 } rf_conv_desc;
 int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
 
@@ -205,6 +208,10 @@ int rf_softmax_rows_f16(const void* x, long rows, int n, int pitch, void* y, voi
 int rf_upsample2x_f16(const void* x, int B, int H, int W, int C, void* y, void* stream);
 /* torch.cat([a, b], dim=1) for NHWC tensors: [pixels][Ca] + [pixels][Cb] -> [pixels][Ca+Cb] */
 int rf_concat_channels_f16(const void* a, const void* b, long pixels, int Ca, int Cb, void* y, void* stream);
+/* Conv2d(Cin<=8 -> Cout<=8, 1x1) on NCHW fp16 with an input pre-scale: the VAE's quant_conv / post_quant_conv
+ * (and the latents / 0.18215 of riffusion_pipeline.py:427 folded into in_scale) */
+int rf_conv1x1_small_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int Cout, long HW,
+                         float in_scale, void* y_nchw, void* stream);
 /* conv_in: Conv2d(Cin<=8 -> Cout, 3x3, pad 1) reading NCHW fp16, writing NHWC; w = torch layout [Cout][Cin][3][3] */
 int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int H, int W, int Cout,
                    void* y_nhwc, void* stream);

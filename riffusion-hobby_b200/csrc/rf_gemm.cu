@@ -348,9 +348,10 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     if ((d->C1 % BK) || (d->x2 && (d->C2 % BK)))
         return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: channel counts must be multiples of 64 (use the direct "
                                            "convolution for the 4- and 3-channel layers)");
-    const int pad = d->ksize == 3 ? 1 : 0;
-    const int Ho = (d->H + 2 * pad - d->ksize) / d->stride + 1;
-    const int Wo = (d->W + 2 * pad - d->ksize) / d->stride + 1;
+    const int pad = (d->ksize == 3 && d->pad_mode == 0) ? 1 : 0;
+    const int extra = (d->ksize == 3 && d->pad_mode == 1) ? 1 : 0;   // one implicit zero row/column at the far edge
+    const int Ho = (d->H + 2 * pad + extra - d->ksize) / d->stride + 1;
+    const int Wo = (d->W + 2 * pad + extra - d->ksize) / d->stride + 1;
     // output pixels per tile
     int bw = Wo >= 128 ? 128 : Wo;
     while (BM % bw) --bw;  // bw must divide 128

@@ -302,6 +302,23 @@ __global__ void k_concat_channels(const __half* __restrict__ a, const __half* __
     }
 }
 
+// 1x1 convolution on tiny channel counts, NCHW: y[b][o][p] = bias[o] + sum_i w[o][i] * (in_scale * x[b][i][p])
+__global__ void k_conv1x1_small(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                                int B, int Cin, int Cout, size_t HW, float in_scale, __half* __restrict__ y) {
+    const size_t n = static_cast<size_t>(B) * HW;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t b = i / HW, p = i % HW;
+        float in[8];
+        for (int c = 0; c < Cin; ++c) in[c] = in_scale * __half2float(x[(b * Cin + c) * HW + p]);
+        for (int o = 0; o < Cout; ++o) {
+            float acc = bias ? __half2float(bias[o]) : 0.f;
+            for (int c = 0; c < Cin; ++c) acc += __half2float(w[o * Cin + c]) * in[c];
+            y[(b * Cout + o) * HW + p] = __float2half_rn(acc);
+        }
+    }
+}
+
 inline unsigned grid_for(size_t n, int block) {
     size_t g = (n + block - 1) / block;
     return static_cast<unsigned>(g > 148 * 16 ? 148 * 16 : (g ? g : 1));
@@ -376,6 +393,17 @@ extern "C" int rf_concat_channels_f16(const void* a, const void* b, long pixels,
         static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<size_t>(pixels), Ca, Cb,
         static_cast<__half*>(y));
     RF_CUDA_LAUNCH_CHECK("k_concat_channels");
+    return RF_OK;
+}
+
+extern "C" int rf_conv1x1_small_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int Cout, long HW,
+                                    float in_scale, void* y_nchw, void* stream) {
+    if (!x_nchw || !w || !y_nchw || B <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0 || Cout > 8 || HW <= 0)
+        return rf_fail(RF_ERR_INVALID, "rf_conv1x1_small_f16: bad argument");
+    k_conv1x1_small<<<grid_for(static_cast<size_t>(B) * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x_nchw), static_cast<const __half*>(w), static_cast<const __half*>(bias), B, Cin, Cout,
+        static_cast<size_t>(HW), in_scale, static_cast<__half*>(y_nchw));
+    RF_CUDA_LAUNCH_CHECK("k_conv1x1_small");
     return RF_OK;
 }
 

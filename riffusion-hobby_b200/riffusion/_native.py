@@ -55,7 +55,7 @@ class ConvDesc(C.Structure):
         ("Cout", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
         ("x1", C.c_void_p), ("x2", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
         ("bias_per_image", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
-        ("alpha", C.c_float), ("act", C.c_int32),
+        ("alpha", C.c_float), ("act", C.c_int32), ("pad_mode", C.c_int32),
     ]
 
 
@@ -100,6 +100,8 @@ SIGNATURES = {
     "rf_softmax_rows_f16": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_upsample2x_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_concat_channels_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rf_conv1x1_small_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_float,
+                                       C.c_void_p, C.c_void_p]),
     "rf_conv_in_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "rf_conv_out_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -79,17 +79,18 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 def conv2d(
     x: torch.Tensor, w_packed: torch.Tensor, *, x2: T.Optional[torch.Tensor] = None,
     bias: T.Optional[torch.Tensor] = None, bias_per_image: T.Optional[torch.Tensor] = None,
-    residual: T.Optional[torch.Tensor] = None, stride: int = 1, act: int = ACT_NONE,
+    residual: T.Optional[torch.Tensor] = None, stride: int = 1, act: int = ACT_NONE, pad_far_edge_only: bool = False,
 ) -> torch.Tensor:
     """x (and optional x2, concatenated along channels): (B, H, W, C) fp16 NHWC contiguous.
-    w_packed: (Cout, k, k, C1+C2).  Returns (B, Ho, Wo, Cout)."""
+    w_packed: (Cout, k, k, C1+C2).  Returns (B, Ho, Wo, Cout).  `pad_far_edge_only`: F.pad(x,(0,1,0,1)) + padding=0."""
     _f16(x, "x"), _f16(w_packed, "w")
     B, H, W, C1 = x.shape
     C2 = 0 if x2 is None else x2.shape[3]
     Cout, k, _, Cin = w_packed.shape
     assert Cin == C1 + C2 and x.is_contiguous() and w_packed.is_contiguous()
-    pad = 1 if k == 3 else 0
-    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    pad = 1 if (k == 3 and not pad_far_edge_only) else 0
+    extra = 1 if (k == 3 and pad_far_edge_only) else 0
+    Ho, Wo = (H + 2 * pad + extra - k) // stride + 1, (W + 2 * pad + extra - k) // stride + 1
     out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float16, device=x.device)
     d = _native.ConvDesc()
     d.B, d.H, d.W, d.C1, d.C2, d.Cout, d.ksize, d.stride = B, H, W, C1, C2, Cout, k, stride
@@ -101,7 +102,7 @@ def conv2d(
     if residual is not None:
         assert residual.shape == out.shape and residual.is_contiguous()
         d.residual = _f16(residual, "residual").data_ptr()
-    d.out, d.alpha, d.act = out.data_ptr(), 1.0, int(act)
+    d.out, d.alpha, d.act, d.pad_mode = out.data_ptr(), 1.0, int(act), int(pad_far_edge_only)
     with torch.cuda.device(x.device):
         _native.check(_native.lib().rf_conv2d_f16(C.byref(d), _stream(x)))
     return out
@@ -238,4 +239,16 @@ def axpby(x, noise, a, b, mask=None, z=None):
         _native.check(_native.lib().rf_axpby_f16(x.data_ptr(), noise.data_ptr(), float(a), float(b),
                                                  None if mask is None else mask.data_ptr(),
                                                  None if z is None else z.data_ptr(), x.numel(), y.data_ptr(), _stream(x)))
+    return y
+
+
+def conv1x1_small(x_nchw: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, in_scale: float = 1.0) -> torch.Tensor:
+    """(B, Cin<=8, H, W) NCHW -> (B, Cout<=8, H, W); w: (Cout, Cin) fp16."""
+    _f16(x_nchw, "x")
+    B, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    y = torch.empty((B, Cout, H, W), dtype=torch.float16, device=x_nchw.device)
+    with torch.cuda.device(x_nchw.device):
+        _native.check(_native.lib().rf_conv1x1_small_f16(x_nchw.contiguous().data_ptr(), w.data_ptr(), bias.data_ptr(), B, Cin,
+                                                         Cout, H * W, float(in_scale), y.data_ptr(), _stream(x_nchw)))
     return y

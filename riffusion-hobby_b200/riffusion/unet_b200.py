@@ -41,11 +41,11 @@ class UNetB200:
         self.c = tuple(block_out_channels)
         self.heads, self.groups = heads, groups
         self.max_score_bytes = max_score_bytes
-        self.in_channels = int(state_dict["conv_in.weight"].shape[1])
+        self.in_channels = int(state_dict["conv_in.weight"].shape[1]) if "conv_in.weight" in state_dict else 4
         self.w: T.Dict[str, torch.Tensor] = {}
         dev = self.device
         for name, p in state_dict.items():
-            if p.dim() == 4 and p.shape[2] == 3 and name not in ("conv_in.weight",):
+            if p.dim() == 4 and p.shape[2] == 3 and not name.endswith("conv_in.weight"):
                 self.w[name] = ops.pack_conv_weight(p.to(dev))               # (Cout, 3, 3, Cin)
             elif p.dim() == 4 and p.shape[2] == 1:
                 self.w[name] = _h(p.reshape(p.shape[0], p.shape[1]), dev)    # 1x1 conv == linear over pixels

@@ -50,3 +50,18 @@ def test_small_unet_runs_and_slerp_lerp_fallback():
     a = torch.randn(16384)
     out = uo.slerp(0.3, a, a * 1.0001)           # |dot| > 0.9995 -> lerp (torch_util.py:34-35)
     assert torch.allclose(out, 0.7 * a + 0.3 * a * 1.0001, atol=1e-6)
+
+
+def test_product_spec_matches_oracle_state_dicts():
+    """riffusion.sd15_spec (product side, used for random init / checkpoint validation) enumerates exactly the
+    parameters of the oracle modules"""
+    from oracle.vae_oracle import AutoencoderKLOracle
+    from riffusion import sd15_spec
+
+    with torch.device("meta"):
+        u, v = uo.UNet2DConditionOracle(), AutoencoderKLOracle()
+    for spec, module in ((sd15_spec.unet_spec(), u), (sd15_spec.vae_spec(), v)):
+        want = {k: tuple(p.shape) for k, p in module.state_dict().items()}
+        got = dict(spec)
+        assert len(got) == len(spec) and got == want
+    assert sum(p.numel() for p in v.parameters()) == 83_653_863       # published SD VAE size
