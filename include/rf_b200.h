@@ -192,11 +192,19 @@ typedef struct rf_conv_desc {
 } rf_conv_desc;
 int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
 
+/* Measurement aid (bench.py roofline): between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed by
+ * CUDA events on its stream; end synchronises the device and returns the summed kernel time (ms), the algorithmic
+ * FLOPs (2*M*N*K, true extents) and the launch count.  Not for use inside CUDA-graph capture. */
+int rf_tc_profile_begin(void);
+int rf_tc_profile_end(double* ms_out, double* flops_out, long* launches_out);
+
 /* Memory-bound UNet/VAE operators (fp16 activations, fp32 statistics).  NHWC images, row-major tokens.
  * Each restates the torch op diffusers calls [diffusers 0.9, absent here: restated from memory]. */
-/* torch.nn.GroupNorm(groups, C, eps) (+ optional SiLU): x,y fp16 [B][HW][C]; d_stats: fp32 scratch [B][groups][2] */
+/* torch.nn.GroupNorm(groups, C, eps) (+ optional SiLU): x,y fp16 [B][HW][C]; d_scratch: fp32 device scratch of
+ * rf_group_norm_scratch_floats(B, HW, groups) floats.  Deterministic (fixed-order reductions, no atomics). */
+size_t rf_group_norm_scratch_floats(int B, int HW, int groups);
 int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups, const void* gamma, const void* beta,
-                      float eps, int act, void* y, float* d_stats, void* stream);
+                      float eps, int act, void* y, float* d_scratch, void* stream);
 /* torch.nn.LayerNorm(C, eps) over rows */
 int rf_layer_norm_f16(const void* x, int rows, int C, const void* gamma, const void* beta, float eps, void* y,
                       void* stream);

@@ -15,8 +15,11 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "rf_common.h"
 #include "rf_tc.cuh"
@@ -268,6 +271,18 @@ int make_map(CUtensorMap* map, const void* ptr, const long dims[4], const long s
     return RF_OK;
 }
 
+// optional live measurement (bench.py): CUDA events around every tensor-core launch + algorithmic FLOP count
+struct TcProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;   // begin/end pairs
+    double flops = 0.0;
+    long launches = 0;
+    struct Rec { int conv, M, N, K, batch; };
+    std::vector<Rec> recs;
+};
+TcProfile g_prof;
+std::mutex g_prof_mu;
+
 template <int BN, int STAGES>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
            cudaStream_t st) {
@@ -278,8 +293,25 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         aerr = cudaFuncSetAttribute(k_tc_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     });
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(aerr));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = g_prof.on;
+    if (prof) {
+        RF_CUDA_TRY(cudaEventCreate(&e0));
+        RF_CUDA_TRY(cudaEventCreate(&e1));
+        RF_CUDA_TRY(cudaEventRecord(e0, st));
+    }
     k_tc_gemm<BN, STAGES><<<grid, 192, smem, st>>>(a0, a1, b, p);
     RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
+    if (prof) {
+        RF_CUDA_TRY(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.ev.push_back(e0);
+        g_prof.ev.push_back(e1);
+        g_prof.launches += 1;
+        const double m = p.conv ? static_cast<double>(p.Bn) * p.Ho * p.Wo : static_cast<double>(p.M) * p.batch1 * p.batch2;
+        g_prof.flops += 2.0 * m * p.N * p.K;
+        g_prof.recs.push_back({p.conv, p.conv ? p.Bn * p.Ho * p.Wo : p.M, p.N, p.K, p.batch1 * p.batch2});
+    }
     return RF_OK;
 }
 
@@ -412,4 +444,43 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.act = d->act;
     return dispatch(d->Cout, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+}
+
+// Live measurement aid for bench.py: between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed
+// by CUDA events on its stream and its algorithmic FLOPs (2*M*N*K with the true, un-padded extents) are summed.
+extern "C" int rf_tc_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.on = true;
+    g_prof.flops = 0.0;
+    g_prof.launches = 0;
+    g_prof.recs.clear();
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear();
+    return RF_OK;
+}
+extern "C" int rf_tc_profile_end(double* ms_out, double* flops_out, long* launches_out) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.on = false;
+    double ms = 0.0;
+    cudaError_t err = cudaDeviceSynchronize();
+    FILE* dump = nullptr;
+    if (const char* path = getenv("RF_TC_PROFILE_DUMP")) dump = fopen(path, "w");   // per-launch csv for profiles/
+    if (dump) fprintf(dump, "conv,M,N,K,batch,ms\n");
+    for (size_t i = 0; i + 1 < g_prof.ev.size() && err == cudaSuccess; i += 2) {
+        float t = 0.f;
+        err = cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+        ms += t;
+        if (dump && i / 2 < g_prof.recs.size()) {
+            const TcProfile::Rec& r = g_prof.recs[i / 2];
+            fprintf(dump, "%d,%d,%d,%d,%d,%.4f\n", r.conv, r.M, r.N, r.K, r.batch, t);
+        }
+    }
+    if (dump) fclose(dump);
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear();
+    if (ms_out) *ms_out = ms;
+    if (flops_out) *flops_out = g_prof.flops;
+    if (launches_out) *launches_out = g_prof.launches;
+    if (err != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("rf_tc_profile_end: ") + cudaGetErrorString(err));
+    return RF_OK;
 }

@@ -27,21 +27,21 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
-// ---------------------------------------------------------------- GroupNorm (NHWC)
-// pass 1: per (image, group) sum and sum of squares. grid (slabs, B); each CTA reduces a slab of
-// pixels for all channels, then one atomicAdd per (group, stat).  Accumulating E[x] and E[x^2] in
-// fp32 over <= 4096*40 values of O(1) magnitude keeps ~1e-6 relative accuracy on the variance.
-__global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int slab,
-                           float* __restrict__ stats /*[B][G][2]*/) {
-    extern __shared__ float sh[];  // [2*G]
+// ---------------------------------------------------------------- GroupNorm (NHWC), deterministic
+// pass 1: per (image, slab of 64 pixels, group) partial sum and sum of squares.  Threads read coalesced
+//         half2 channel pairs, park their partials in shared memory, and one thread per group adds them in a
+//         fixed order (no atomics: repeated runs are bit-identical).
+// pass 2: one warp per (image, group) adds the slab partials in a fixed order -> (mean, rstd).
+// pass 3: y = (x - mean) * rstd * gamma + beta, optional SiLU.
+__global__ void k_gn_partial(const __half* __restrict__ x, int HW, int C, int G, int slab, int nslabs,
+                             float* __restrict__ part /*[B][nslabs][G][2]*/) {
+    extern __shared__ float2 shp[];  // [R][C2]
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
-    const int cpg = C / G;   // even for every SD layer (4 ... 80)
-    const int C2 = C >> 1;   // half2 units
-    const int CW = C2 < static_cast<int>(blockDim.x) ? C2 : static_cast<int>(blockDim.x);  // lanes across channels
-    const int R = blockDim.x / CW;                                                         // pixel rows in flight
+    const int cpg2 = (C / G) >> 1;  // half2 pairs per group
+    const int C2 = C >> 1;
+    const int CW = C2 < static_cast<int>(blockDim.x) ? C2 : static_cast<int>(blockDim.x);
+    const int R = blockDim.x / CW;
     const int prow = threadIdx.x / CW, lc = threadIdx.x - prow * CW;
     const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
     if (prow < R) {
@@ -52,24 +52,51 @@ __global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, i
                 s += v.x + v.y;
                 ss += v.x * v.x + v.y * v.y;
             }
-            const int g = (2 * c2) / cpg;
-            atomicAdd(&sh[2 * g], s);
-            atomicAdd(&sh[2 * g + 1], ss);
+            shp[prow * C2 + c2] = make_float2(s, ss);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
-        atomicAdd(&stats[static_cast<size_t>(b) * 2 * G + i], sh[i]);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float s = 0.f, ss = 0.f;
+        for (int r = 0; r < R; ++r)
+            for (int k = 0; k < cpg2; ++k) {
+                const float2 v = shp[r * C2 + g * cpg2 + k];
+                s += v.x;
+                ss += v.y;
+            }
+        float* o = part + ((static_cast<size_t>(b) * nslabs + blockIdx.x) * G + g) * 2;
+        o[0] = s;
+        o[1] = ss;
+    }
 }
 
-// pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU
+__global__ void k_gn_finalize(const float* __restrict__ part, int nslabs, int G, float inv_n, float eps,
+                              float* __restrict__ stats /*[B][G][2] = mean, rstd*/) {
+    const int bg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b, g) flattened
+    const int lane = threadIdx.x & 31;
+    const int b = bg / G, g = bg % G;
+    float s = 0.f, ss = 0.f;
+    for (int i = lane; i < nslabs; i += 32) {
+        const float* o = part + ((static_cast<size_t>(b) * nslabs + i) * G + g) * 2;
+        s += o[0];
+        ss += o[1];
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+        const float mean = s * inv_n;
+        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+        stats[static_cast<size_t>(bg) * 2] = mean;
+        stats[static_cast<size_t>(bg) * 2 + 1] = rsqrtf(var + eps);
+    }
+}
+
 __global__ void k_gn_apply(const __half* __restrict__ x, const float* __restrict__ stats,
                            const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C,
-                           int G, float eps, int act, __half* __restrict__ y) {
+                           int G, int act, __half* __restrict__ y) {
     const int b = blockIdx.y;
     const size_t n2 = static_cast<size_t>(HW) * C / 2;
     const int cpg = C / G;
-    const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
     const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
     __half2* yb = reinterpret_cast<__half2*>(y + static_cast<size_t>(b) * HW * C);
     const __half2* g2 = reinterpret_cast<const __half2*>(gamma);
@@ -78,9 +105,8 @@ __global__ void k_gn_apply(const __half* __restrict__ x, const float* __restrict
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int c2 = static_cast<int>(i % (C / 2));
         const int g = (2 * c2) / cpg;
-        const float mean = stats[(static_cast<size_t>(b) * G + g) * 2] * inv_n;
-        const float var = fmaxf(stats[(static_cast<size_t>(b) * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
+        const float mean = stats[(static_cast<size_t>(b) * G + g) * 2];
+        const float rstd = stats[(static_cast<size_t>(b) * G + g) * 2 + 1];
         const float2 v = __half22float2(xb[i]);
         const float2 ga = __half22float2(g2[c2]);
         const float2 be = __half22float2(b2[c2]);
@@ -326,23 +352,37 @@ inline unsigned grid_for(size_t n, int block) {
 
 }  // namespace
 
+extern "C" size_t rf_group_norm_scratch_floats(int B, int HW, int groups) {
+    const int nslabs = (HW + 63) / 64;
+    return static_cast<size_t>(B) * groups * 2 * (static_cast<size_t>(nslabs) + 1);
+}
+
 extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups, const void* gamma, const void* beta,
-                                 float eps, int act, void* y, float* d_stats, void* stream) {
-    if (!x || !y || !gamma || !beta || !d_stats || B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups ||
+                                 float eps, int act, void* y, float* d_scratch, void* stream) {
+    if (!x || !y || !gamma || !beta || !d_scratch || B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups ||
         ((C / groups) & 1))
         return rf_fail(RF_ERR_INVALID, "rf_group_norm_f16: bad argument (channels per group must be even)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    RF_CUDA_TRY(cudaMemsetAsync(d_stats, 0, static_cast<size_t>(B) * groups * 2 * sizeof(float), st));
     const int slab = 64;
-    dim3 grid((HW + slab - 1) / slab, B);
-    k_gn_stats<<<grid, 256, 2 * groups * sizeof(float), st>>>(static_cast<const __half*>(x), HW, C, groups, slab,
-                                                                  d_stats);
-    RF_CUDA_LAUNCH_CHECK("k_gn_stats");
+    const int nslabs = (HW + slab - 1) / slab;
+    float* stats = d_scratch;                                          // [B][G][2]
+    float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
+    const int C2 = C / 2;
+    const int CW = C2 < 256 ? C2 : 256;
+    const int R = 256 / CW;
+    const size_t smem = static_cast<size_t>(R) * C2 * sizeof(float2);
+    if (smem > 48 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: too many channels");
+    dim3 grid(nslabs, B);
+    k_gn_partial<<<grid, 256, smem, st>>>(static_cast<const __half*>(x), HW, C, groups, slab, nslabs, part);
+    RF_CUDA_LAUNCH_CHECK("k_gn_partial");
+    const int nbg = B * groups;
+    if (nbg % 8) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: B*groups must be a multiple of 8");
+    k_gn_finalize<<<nbg / 8, 256, 0, st>>>(part, nslabs, groups, 1.f / (static_cast<float>(HW) * (C / groups)), eps, stats);
+    RF_CUDA_LAUNCH_CHECK("k_gn_finalize");
     const size_t n2 = static_cast<size_t>(HW) * C / 2;
     dim3 grid2(grid_for(n2, 256), B);
-    k_gn_apply<<<grid2, 256, 0, st>>>(static_cast<const __half*>(x), d_stats, static_cast<const __half*>(gamma),
-                                      static_cast<const __half*>(beta), HW, C, groups, eps, act,
-                                      static_cast<__half*>(y));
+    k_gn_apply<<<grid2, 256, 0, st>>>(static_cast<const __half*>(x), stats, static_cast<const __half*>(gamma),
+                                      static_cast<const __half*>(beta), HW, C, groups, act, static_cast<__half*>(y));
     RF_CUDA_LAUNCH_CHECK("k_gn_apply");
     return RF_OK;
 }

@@ -44,6 +44,8 @@ class RiffusionPipeline:
         self.text_encoder, self.tokenizer = text_encoder, tokenizer
         self._device = torch.device(device)
         self._moment_cache: T.Dict[int, T.Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.use_cuda_graph = True      # replay each CFG UNet evaluation as one CUDA graph
+        self._graphs: T.Dict[T.Tuple, T.Any] = {}
 
     # ------------------------------------------------------------------------------ construction
     @classmethod
@@ -200,11 +202,19 @@ class RiffusionPipeline:
         t_start = max(num_inference_steps - init_timestep + offset, 0)                             # :392
         timesteps = self.scheduler.timesteps[t_start:]
         ctx_cache: T.Dict[str, T.Any] = {}
+        graphed = None
+        if self.use_cuda_graph and do_cfg:
+            from riffusion.graphed import GraphedUNet
+
+            graphed = GraphedUNet(self.unet, latents.shape, context)
         n_evals = 0
         for t in timesteps:                                                                        # :398
             t_int = int(t)
-            model_in = torch.cat([latents] * 2) if do_cfg else latents                             # :400-403
-            eps_pair = self.unet(model_in, t_int, encoder_hidden_states=context, ctx_cache=ctx_cache).sample
+            if graphed is not None:
+                eps_pair = graphed(latents, t_int)
+            else:
+                model_in = torch.cat([latents] * 2) if do_cfg else latents                         # :400-403
+                eps_pair = self.unet(model_in, t_int, encoder_hidden_states=context, ctx_cache=ctx_cache).sample
             n_evals += 1
             if not do_cfg:
                 eps_pair = torch.cat([eps_pair, eps_pair])

@@ -116,7 +116,7 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     B, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * C)
     y = torch.empty_like(x)
-    stats = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
+    stats = torch.empty((_native.lib().rf_group_norm_scratch_floats(B, HW, groups),), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _native.check(_native.lib().rf_group_norm_f16(x.data_ptr(), B, HW, C, groups, gamma.data_ptr(), beta.data_ptr(),
                                                       float(eps), int(silu), y.data_ptr(), stats.data_ptr(), _stream(x)))
