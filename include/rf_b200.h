@@ -186,11 +186,19 @@ typedef struct rf_conv_desc {
     void* out;                 /* fp16 [B][Ho][Wo][Cout] */
     float alpha;               /* 0 is treated as 1 */
     int32_t act;
+    int32_t bias_per_image_pitch; /* row pitch (elements) of bias_per_image; 0 = Cout */
     int32_t pad_mode;          /* 0: symmetric padding ksize/2 (torch padding=1 for 3x3);
                                   1: no left/top padding, implicit zero padding on the right/bottom edge
                                      (diffusers VAE Downsample2D: F.pad(x, (0,1,0,1)) then conv padding=0) */
 } rf_conv_desc;
 int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
+
+/* Fused attention softmax(Q K^T * scale) V per (image, head) — diffusers CrossAttention's baddbmm/softmax/bmm
+ * [restated from memory] without materialising the scores.  q [B][Nq][heads*d], k [B][Nk][heads*d],
+ * vt [B][heads*d][vt_pitch] (V transposed, as produced by rf_gemm_f16 with swapped operands), out [B][Nq][heads*d];
+ * fp16, d a multiple of 8 and <= 192, vt_pitch a multiple of 8 >= Nk. */
+int rf_attention_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Nq, int Nk,
+                     int d, int vt_pitch, float scale, void* stream);
 
 /* Measurement aid (bench.py roofline): between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed by
  * CUDA events on its stream; end synchronises the device and returns the summed kernel time (ms), the algorithmic

@@ -1,0 +1,415 @@
+// Fused multi-head attention for the UNet's transformer blocks: O = softmax(Q K^T * scale) V per (image, head),
+// scores never leave the SM.  tcgen05 MMAs with TMEM accumulators, TMA-fed K / V^T tiles.
+//
+// Two passes over the keys instead of an online-softmax rescale:
+//   pass 1: S = Q K^T per 128-key tile -> running row maximum           (QK^T MMAs only)
+//   pass 2: S = Q K^T again, P = exp2((S - max) * scale*log2e) in fp16 -> shared memory, O += P V (TMEM
+//           accumulates across all key tiles, no correction step), row sums accumulated on the side;
+//           epilogue O / rowsum.
+// QK^T is computed twice (+1 MMA in 3 for d=40) but exp is evaluated once and O is never rescaled.
+//
+// CTA = 128 queries of one (image, head); 320 threads:
+//   warp 0      TMA producer (K tiles in pass 1, K + V^T tiles in pass 2), 1 thread
+//   warp 1      MMA issuer, 1 thread; TMEM allocation (512 columns: S0 | S1 | O)
+//   warps 2-5   softmax group A: even key tiles, one query row per thread (row == TMEM lane)
+//   warps 6-9   softmax group B: odd key tiles (ping-pong on the two S buffers / two P buffers)
+//
+// Replaces the baddbmm -> softmax -> bmm sequence of diffusers' CrossAttention (reached from
+// riffusion/riffusion_pipeline.py:406-408) [diffusers absent: restated from memory].
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+
+#include "rf_common.h"
+#include "rf_tc.cuh"
+
+namespace {
+
+constexpr int TQ = 128;   // queries per CTA
+constexpr int TK = 128;   // keys per tile
+
+struct AttnParams {
+    int Nq, Nk, d, heads;
+    int n_tiles;          // ceil(Nk / 128)
+    float c;              // scale * log2(e)
+    __half* out;          // [B][Nq][C]
+    long out_pitch;       // C
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// DPAD: head dim rounded up to 64 (Q/K slabs of 64 elements); NV: head dim rounded up to 16 (UMMA N of the PV product)
+template <int DPAD, int NV, int NS>
+__global__ void __launch_bounds__(320, 1)
+k_flash_attn(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+             const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NSLAB = DPAD / 64;
+    constexpr int Q_BYTES = NSLAB * TQ * 128;
+    constexpr int K_BYTES = NSLAB * TK * 128;
+    constexpr int V_SLAB = ((NV * 128 + 1023) / 1024) * 1024;   // one 64-key slab of V^T, padded to the swizzle atom
+    constexpr int V_BYTES = 2 * V_SLAB;
+    constexpr int P_BYTES = 2 * TQ * 128;                        // 128 x 128 fp16
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + Q_BYTES;                 // [NS][K_BYTES]
+    uint8_t* sV = sK + NS * K_BYTES;            // [NS][V_BYTES]
+    uint8_t* sP = sV + NS * V_BYTES;            // [2][P_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint64_t* q_full = bars;                    // 1
+    uint64_t* kv_full = bars + 1;               // NS
+    uint64_t* kv_empty = kv_full + NS;          // NS
+    uint64_t* s_full = kv_empty + NS;           // 2
+    uint64_t* s_empty = s_full + 2;             // 2
+    uint64_t* p_full = s_empty + 2;             // 2
+    uint64_t* p_empty = p_full + 2;             // 2
+    uint64_t* o_full = p_empty + 2;             // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    float* xchg = reinterpret_cast<float*>(tmem_slot + 2);   // [2][128] row max / row sum exchange between groups
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int T = p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(q_full, 1);
+        for (int i = 0; i < NS; ++i) {
+            tc::mbar_init(&kv_full[i], 1);
+            tc::mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s_full[i], 1);
+            tc::mbar_init(&s_empty[i], 128);
+            tc::mbar_init(&p_full[i], 128);
+            tc::mbar_init(&p_empty[i], 1);
+        }
+        tc::mbar_init(o_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_O = tmem_base + 256;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        tc::mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+        for (int s = 0; s < NSLAB; ++s) tc::tma_load_4d(&mapQ, q_full, sQ + s * TQ * 128, s * 64, q_blk * TQ, head, b);
+        int it = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int j = 0; j < T; ++j, ++it) {
+                const int st = it % NS;
+                tc::mbar_wait(&kv_empty[st], ((it / NS) & 1) ^ 1);
+                tc::mbar_expect_tx(&kv_full[st], K_BYTES + (pass ? 2 * NV * 128 : 0));
+#pragma unroll
+                for (int s = 0; s < NSLAB; ++s)
+                    tc::tma_load_4d(&mapK, &kv_full[st], sK + st * K_BYTES + s * TK * 128, s * 64, j * TK, head, b);
+                if (pass) {
+                    tc::tma_load_4d(&mapVt, &kv_full[st], sV + st * V_BYTES, j * TK, 0, head, b);
+                    tc::tma_load_4d(&mapVt, &kv_full[st], sV + st * V_BYTES + V_SLAB, j * TK + 64, 0, head, b);
+                }
+            }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_qk = tc::make_idesc_f16(TQ, TK);
+        constexpr uint32_t idesc_pv = tc::make_idesc_f16(TQ, NV);
+        tc::mbar_wait(q_full, 0);
+        tc::fence_after_sync();
+        const uint32_t q_base = tc::smem_u32(sQ);
+        auto issue_qk = [&](int it, int j) {     // S_{j&1} = Q K_j^T
+            const int st = it % NS;
+            tc::mbar_wait(&kv_full[st], (it / NS) & 1);
+            tc::fence_after_sync();
+            const uint32_t k_base = tc::smem_u32(sK + st * K_BYTES);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16(tmem_base + (j & 1) * 128, tc::make_desc_sw128(q_base + s * TQ * 128 + k * 32),
+                                tc::make_desc_sw128(k_base + s * TK * 128 + k * 32), idesc_qk, (s | k) ? 1u : 0u);
+            tc::mma_commit(&s_full[j & 1]);
+        };
+        int se_cnt[2] = {0, 0};                  // completed uses of each S buffer (for s_empty parity)
+        // ---- pass 1: scores only
+        for (int j = 0; j < T; ++j) {
+            const int i = j & 1;
+            if (se_cnt[i] > 0) {
+                tc::mbar_wait(&s_empty[i], (se_cnt[i] - 1) & 1);
+                tc::fence_after_sync();
+            }
+            issue_qk(j, j);
+            ++se_cnt[i];
+            tc::mma_commit(&kv_empty[j % NS]);   // K_j is free once this QK^T has completed
+        }
+        // ---- pass 2: scores, then P V
+        int pe_cnt[2] = {0, 0};
+        auto qk2 = [&](int j) {
+            const int i = j & 1;
+            if (se_cnt[i] > 0) {
+                tc::mbar_wait(&s_empty[i], (se_cnt[i] - 1) & 1);
+                tc::fence_after_sync();
+            }
+            issue_qk(T + j, j);
+            ++se_cnt[i];
+        };
+        // look-ahead: with >= 2 K/V stages the next two score tiles are issued before the first P V (ping-pong on the
+        // two S buffers); with a single stage the stage is only released by the P V that consumed it
+        constexpr int LA = NS >= 2 ? 2 : 1;
+        for (int j = 0; j < LA && j < T; ++j) qk2(j);
+        for (int j = 0; j < T; ++j) {
+            const int i = j & 1;
+            const int it = T + j, st = it % NS;
+            tc::mbar_wait(&p_full[i], pe_cnt[i] & 1);
+            tc::fence_after_sync();
+            const uint32_t p_base = tc::smem_u32(sP + i * P_BYTES);
+            const uint32_t v_base = tc::smem_u32(sV + st * V_BYTES);
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16(tmem_O, tc::make_desc_sw128(p_base + s * TQ * 128 + k * 32),
+                                tc::make_desc_sw128(v_base + s * V_SLAB + k * 32), idesc_pv, (j | s | k) ? 1u : 0u);
+            tc::mma_commit(&p_empty[i]);
+            tc::mma_commit(&kv_empty[st]);       // K_j and V_j free once P V (and the earlier QK^T) have completed
+            ++pe_cnt[i];
+            if (j + LA < T) qk2(j + LA);
+        }
+        tc::mma_commit(o_full);
+    } else if (warp >= 2) {
+        // ------------------------------------------------------------------ softmax groups
+        const int g = (warp - 2) >> 2;           // 0: even tiles, 1: odd tiles
+        const int q = warp & 3;                  // TMEM lane quarter
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        int sf_phase = 0;
+        float m = -INFINITY;
+        // ---- pass 1: row maximum of the raw scores over this group's tiles
+        for (int j = g; j < T; j += 2) {
+            tc::mbar_wait(&s_full[g], sf_phase);
+            sf_phase ^= 1;
+            tc::fence_after_sync();
+            const int kmax = p.Nk - j * TK;      // valid keys in this tile
+#pragma unroll 1
+            for (int c0 = 0; c0 < TK; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(t_row + g * 128 + c0, v);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < kmax) m = fmaxf(m, __uint_as_float(v[i]));
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(&s_empty[g]);
+        }
+        xchg[g * 128 + row] = m;
+        named_bar_sync(1, 256);
+        m = fmaxf(xchg[row], xchg[128 + row]);
+        const float mc = m * p.c;
+        named_bar_sync(1, 256);                  // everyone has read the maxima before xchg is reused for the sums
+        // ---- pass 2: P = exp2(S*c - m*c), row sums, P -> shared memory (K-major, 128-byte swizzle)
+        float l = 0.f;
+        int pe_phase = 0, n_mine = 0;
+        uint8_t* myP = sP + g * P_BYTES;
+        for (int j = g; j < T; j += 2, ++n_mine) {
+            tc::mbar_wait(&s_full[g], sf_phase);
+            sf_phase ^= 1;
+            tc::fence_after_sync();
+            if (n_mine > 0) {                    // the previous P V that read this P buffer must have completed
+                tc::mbar_wait(&p_empty[g], pe_phase);
+                pe_phase ^= 1;
+            }
+            const int kmax = p.Nk - j * TK;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TK; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(t_row + g * 128 + c0, v);
+                tc::tmem_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (c0 + i < kmax) ? exp2f(fmaf(__uint_as_float(v[i]), p.c, -mc)) : 0.f;
+                    float p1 = (c0 + i + 1 < kmax) ? exp2f(fmaf(__uint_as_float(v[i + 1]), p.c, -mc)) : 0.f;
+                    const __half2 h = __floats2half2_rn(p0, p1);
+                    // accumulate the row sum from the rounded values the P V product will actually use
+                    const float2 hr = __half22float2(h);
+                    l += hr.x + hr.y;
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                // columns c0..c0+31 = 4 chunks of 8 halves; slab = c0 / 64, chunk index within the 128-byte row
+                const int slab = c0 >> 6;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int chunk = ((c0 & 63) >> 3) + ch;
+                    uint4 val = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+                    *reinterpret_cast<uint4*>(myP + slab * TQ * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) = val;
+                }
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(&s_empty[g]);        // S buffer may be overwritten by the next QK^T
+            fence_async_smem();                  // make the P stores visible to the tensor-core (async) proxy
+            tc::mbar_arrive(&p_full[g]);
+        }
+        xchg[g * 128 + row] = l;
+        named_bar_sync(1, 256);
+        if (g == 0) {
+            // ---- epilogue (group A): O / rowsum -> fp16
+            const float inv = 1.f / (xchg[row] + xchg[128 + row]);
+            tc::mbar_wait(o_full, 0);
+            tc::fence_after_sync();
+            const int qi = q_blk * TQ + row;
+            __half* dst = p.out + (static_cast<long>(b) * p.Nq + qi) * p.out_pitch + head * p.d;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NV; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_row + 256 + c0, v);
+                tc::tmem_wait_ld();
+                if (qi < p.Nq) {
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const int col = c0 + 8 * ch;
+                        if (col < p.d) {         // d is a multiple of 8
+                            __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * ch + 0]) * inv, __uint_as_float(v[8 * ch + 1]) * inv);
+                            __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * ch + 2]) * inv, __uint_as_float(v[8 * ch + 3]) * inv);
+                            __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * ch + 4]) * inv, __uint_as_float(v[8 * ch + 5]) * inv);
+                            __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * ch + 6]) * inv, __uint_as_float(v[8 * ch + 7]) * inv);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(dst + col) = pk;
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode2() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(sym);
+    });
+    return fn;
+}
+
+int map4(CUtensorMap* map, const void* ptr, const long dims[4], const long strides[4], const int box[4]) {
+    PFN_encodeTiled enc = get_encode2();
+    if (!enc) return rf_fail(RF_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
+        gdim[i] = static_cast<cuuint64_t>(dims[i]);
+        bx[i] = static_cast<cuuint32_t>(box[i]);
+        if (i) {
+            gstr[i - 1] = static_cast<cuuint64_t>(strides[i]) * 2;
+            if (gstr[i - 1] % 16) return rf_fail(RF_ERR_INVALID, "rf_attention_f16: stride not a multiple of 16 bytes");
+        }
+    }
+    if (reinterpret_cast<uintptr_t>(ptr) % 16) return rf_fail(RF_ERR_INVALID, "rf_attention_f16: pointer not 16-byte aligned");
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return rf_fail(RF_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+    return RF_OK;
+}
+
+template <int DPAD, int NV, int NS>
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, dim3 grid,
+                cudaStream_t st) {
+    constexpr int NSLAB = DPAD / 64;
+    constexpr int V_SLAB = ((NV * 128 + 1023) / 1024) * 1024;
+    const size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NS) * (NSLAB * TK * 128 + 2 * V_SLAB) +
+                        2 * (2 * TQ * 128) + 256 + 2 * 128 * 4 + 1024;
+    static std::once_flag once;
+    static cudaError_t aerr = cudaSuccess;
+    std::call_once(once, [&] {
+        aerr = cudaFuncSetAttribute(k_flash_attn<DPAD, NV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    });
+    if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn): ") + cudaGetErrorString(aerr));
+    k_flash_attn<DPAD, NV, NS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
+    RF_CUDA_LAUNCH_CHECK("k_flash_attn");
+    return RF_OK;
+}
+
+}  // namespace
+
+// q: [B][Nq][heads*d], k: [B][Nk][heads*d], vt: [B][heads*d][vt_pitch] (V transposed), out: [B][Nq][heads*d]; fp16.
+extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Nq, int Nk,
+                                int d, int vt_pitch, float scale, void* stream) {
+    if (!q || !k || !vt || !out || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d <= 0 || (d % 8) || vt_pitch < Nk ||
+        (vt_pitch % 8))
+        return rf_fail(RF_ERR_INVALID, "rf_attention_f16: bad argument");
+    if (d > 192) return rf_fail(RF_ERR_UNSUPPORTED, "rf_attention_f16: head dim > 192 (use the GEMM + softmax path)");
+    const long C = static_cast<long>(heads) * d;
+    CUtensorMap mq, mk, mv;
+    {
+        const long dims[4] = {d, Nq, heads, B};
+        const long str[4] = {1, C, d, static_cast<long>(Nq) * C};
+        const int box[4] = {64, TQ, 1, 1};
+        int rc = map4(&mq, q, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const long dims[4] = {d, Nk, heads, B};
+        const long str[4] = {1, C, d, static_cast<long>(Nk) * C};
+        const int box[4] = {64, TK, 1, 1};
+        int rc = map4(&mk, k, dims, str, box);
+        if (rc) return rc;
+    }
+    const int NV = (d + 15) / 16 * 16;
+    {
+        const long dims[4] = {Nk, d, heads, B};
+        const long str[4] = {1, vt_pitch, static_cast<long>(d) * vt_pitch, C * vt_pitch};
+        const int box[4] = {64, NV, 1, 1};
+        int rc = map4(&mv, vt, dims, str, box);
+        if (rc) return rc;
+    }
+    AttnParams p;
+    p.Nq = Nq; p.Nk = Nk; p.d = d; p.heads = heads;
+    p.n_tiles = (Nk + TK - 1) / TK;
+    p.c = scale * 1.4426950408889634f;
+    p.out = static_cast<__half*>(out);
+    p.out_pitch = C;
+    dim3 grid((Nq + TQ - 1) / TQ, heads, B);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d <= 48) return launch_attn<64, 48, 3>(mq, mk, mv, p, grid, st);
+    if (d <= 64) return launch_attn<64, 64, 3>(mq, mk, mv, p, grid, st);
+    if (d <= 80) return launch_attn<128, 80, 2>(mq, mk, mv, p, grid, st);
+    if (d <= 128) return launch_attn<128, 128, 2>(mq, mk, mv, p, grid, st);
+    if (d <= 160) return launch_attn<192, 160, 1>(mq, mk, mv, p, grid, st);
+    return launch_attn<192, 192, 1>(mq, mk, mv, p, grid, st);
+}

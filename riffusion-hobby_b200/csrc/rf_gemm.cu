@@ -49,7 +49,8 @@ struct TcParams {
     long ldo, so1, so2;     // GEMM: row pitch and batch strides of D (elements)
     const __half* bias;     // [N] (bias_mode 1) or [M] (bias_mode 2)
     int bias_mode;
-    const __half* bias2;    // conv: per-image bias [Bn][N] (time embedding), may be null
+    const __half* bias2;    // conv: per-image bias [Bn][bias2_pitch] (time embedding), may be null
+    int bias2_pitch;
     const __half* residual; // same indexing as out, may be null
     long ldr, sr1, sr2;
     float alpha;
@@ -63,7 +64,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 3)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -191,7 +192,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 if (n < p.N) {
                     if (p.bias_mode == 1) acc += __half2float(p.bias[n]);
                     else if (p.bias_mode == 2) acc += __half2float(p.bias[m_glob]);
-                    if (p.bias2) acc += __half2float(p.bias2[static_cast<long>(img) * p.N + n]);
+                    if (p.bias2) acc += __half2float(p.bias2[static_cast<long>(img) * p.bias2_pitch + n]);
                     acc = apply_act(acc, p.act);
                     if (p.residual) acc += __half2float(p.residual[res_off + n]);
                 }
@@ -317,12 +318,16 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 
 int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, int tiles_m,
              int nbatch, cudaStream_t st) {
+    // Shallow per-CTA rings (2-3 stages, <= 72 KB) so that three CTAs are co-resident per SM: their TMA latency,
+    // MMA main loops and epilogues overlap each other (3 x 128 TMEM columns, 3 x 192 x 96 registers fit).
     if (N > 64) {
         dim3 grid((N + 127) / 128, tiles_m, nbatch);
-        return launch<128, 4>(a0, a1, b, p, grid, st);
+        if (p.num_kb == 1) return launch<128, 1>(a0, a1, b, p, grid, st);
+        return launch<128, 2>(a0, a1, b, p, grid, st);
     }
     dim3 grid((N + 63) / 64, tiles_m, nbatch);
-    return launch<64, 6>(a0, a1, b, p, grid, st);
+    if (p.num_kb == 1) return launch<64, 1>(a0, a1, b, p, grid, st);
+    return launch<64, 3>(a0, a1, b, p, grid, st);
 }
 
 }  // namespace
@@ -440,6 +445,7 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     p.bias = static_cast<const __half*>(d->bias);
     p.bias_mode = d->bias ? 1 : 0;
     p.bias2 = static_cast<const __half*>(d->bias_per_image);
+    p.bias2_pitch = d->bias_per_image_pitch > 0 ? d->bias_per_image_pitch : d->Cout;
     p.residual = static_cast<const __half*>(d->residual);
     p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.act = d->act;

@@ -55,7 +55,7 @@ class ConvDesc(C.Structure):
         ("Cout", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
         ("x1", C.c_void_p), ("x2", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
         ("bias_per_image", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
-        ("alpha", C.c_float), ("act", C.c_int32), ("pad_mode", C.c_int32),
+        ("alpha", C.c_float), ("act", C.c_int32), ("bias_per_image_pitch", C.c_int32), ("pad_mode", C.c_int32),
     ]
 
 
@@ -114,6 +114,8 @@ SIGNATURES = {
                                        C.c_void_p]),
     "rf_axpby_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_long,
                                C.c_void_p, C.c_void_p]),
+    "rf_attention_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "rf_tc_profile_begin": (C.c_int, []),
     "rf_tc_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "rf_image_to_mel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,

@@ -98,7 +98,10 @@ def conv2d(
     d.x2 = None if x2 is None else _f16(x2, "x2").contiguous().data_ptr()
     d.w = w_packed.data_ptr()
     d.bias = None if bias is None else _f16(bias, "bias").data_ptr()
-    d.bias_per_image = None if bias_per_image is None else _f16(bias_per_image, "bias_per_image").contiguous().data_ptr()
+    if bias_per_image is not None:      # (B, Cout) view; rows may be slices of a wider matrix
+        assert bias_per_image.shape == (B, Cout) and bias_per_image.stride(1) == 1
+        d.bias_per_image = _f16(bias_per_image, "bias_per_image").data_ptr()
+        d.bias_per_image_pitch = bias_per_image.stride(0)
     if residual is not None:
         assert residual.shape == out.shape and residual.is_contiguous()
         d.residual = _f16(residual, "residual").data_ptr()
@@ -252,3 +255,16 @@ def conv1x1_small(x_nchw: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, in_
         _native.check(_native.lib().rf_conv1x1_small_f16(x_nchw.contiguous().data_ptr(), w.data_ptr(), bias.data_ptr(), B, Cin,
                                                          Cout, H * W, float(in_scale), y.data_ptr(), _stream(x_nchw)))
     return y
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, heads: int, nk: int) -> torch.Tensor:
+    """q: (B, Nq, C), k: (B, >=nk, C), vt: (B, C, pitch>=nk) fp16 contiguous -> (B, Nq, C); fused tcgen05 kernel."""
+    _f16(q, "q"), _f16(k, "k"), _f16(vt, "vt")
+    B, Nq, C = q.shape
+    d = C // heads
+    assert q.is_contiguous() and k.is_contiguous() and vt.is_contiguous() and k.shape[1] == nk
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        _native.check(_native.lib().rf_attention_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Nq,
+                                                     nk, d, vt.shape[-1], float(d) ** -0.5, _stream(q)))
+    return out

@@ -41,6 +41,7 @@ class UNetB200:
         self.c = tuple(block_out_channels)
         self.heads, self.groups = heads, groups
         self.max_score_bytes = max_score_bytes
+        self.fused_attention = True     # False: materialise fp16 scores (GEMM -> softmax -> GEMM), as the reference does
         self.in_channels = int(state_dict["conv_in.weight"].shape[1]) if "conv_in.weight" in state_dict else 4
         self.w: T.Dict[str, torch.Tensor] = {}
         dev = self.device
@@ -51,16 +52,27 @@ class UNetB200:
                 self.w[name] = _h(p.reshape(p.shape[0], p.shape[1]), dev)    # 1x1 conv == linear over pixels
             else:
                 self.w[name] = _h(p, dev)
-        self._ctx_cache: T.Dict[int, T.Dict[str, T.Tuple[torch.Tensor, torch.Tensor]]] = {}
+        # all resnets' time_emb_proj (Linear 1280 -> cout) stacked into one GEMM per forward
+        names = [n[: -len("time_emb_proj.weight")] for n in self.w if n.endswith("time_emb_proj.weight")]
+        self._temb_slices: T.Dict[str, T.Tuple[int, int]] = {}
+        if names:
+            off = 0
+            for n in names:
+                co = self.w[n + "time_emb_proj.weight"].shape[0]
+                self._temb_slices[n] = (off, off + co)
+                off += co
+            self._temb_w = torch.cat([self.w[n + "time_emb_proj.weight"] for n in names]).contiguous()
+            self._temb_b = torch.cat([self.w[n + "time_emb_proj.bias"] for n in names]).contiguous()
+        self._temb_all: T.Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ building blocks
     def _resnet(self, pfx: str, x: torch.Tensor, st: T.Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
         w = self.w
         h = ops.group_norm(x, w[pfx + "norm1.weight"], w[pfx + "norm1.bias"], self.groups, eps, silu=True)
         tproj = None
-        if st is not None and (pfx + "time_emb_proj.weight") in w:
-            tproj = ops.gemm(st, w[pfx + "time_emb_proj.weight"], bias=w[pfx + "time_emb_proj.bias"])
-            tproj = tproj.reshape(st.shape[0], -1)
+        if st is not None and pfx in self._temb_slices:
+            a, b = self._temb_slices[pfx]
+            tproj = self._temb_all[:, a:b]
         h = ops.conv2d(h, w[pfx + "conv1.weight"], bias=w[pfx + "conv1.bias"], bias_per_image=tproj)
         h = ops.group_norm(h, w[pfx + "norm2.weight"], w[pfx + "norm2.bias"], self.groups, eps, silu=True)
         if (pfx + "conv_shortcut.weight") in w:
@@ -75,6 +87,8 @@ class UNetB200:
         B, Nq, C = q.shape
         h = self.heads
         d = C // h
+        if d <= 192 and self.fused_attention:
+            return ops.attention(q.contiguous(), k.contiguous(), vt.contiguous(), h, nk)    # scores stay on the SM
         pitch = (nk + 7) // 8 * 8
         out = torch.empty((B, Nq, C), dtype=torch.float16, device=q.device)
         per_b = h * Nq * pitch * 2
@@ -157,6 +171,7 @@ class UNetB200:
         e1 = ops.gemm(emb, w["time_embedding.linear_1.weight"], bias=w["time_embedding.linear_1.bias"], act=ops.ACT_SILU)
         e2 = ops.gemm(e1.reshape(B, -1), w["time_embedding.linear_2.weight"], bias=w["time_embedding.linear_2.bias"])
         st = ops.silu(e2.reshape(B, -1))                       # every resnet applies SiLU to temb first
+        self._temb_all = ops.gemm(st, self._temb_w, bias=self._temb_b).reshape(B, -1)
 
         x = ops.conv_in(x_in, w["conv_in.weight"], w["conv_in.bias"])
         skips = [x]

@@ -84,3 +84,28 @@ def test_conv_matches_torch(native_lib, B, H, W, C1, C2, Cout, k, stride):
     res = torch.randn_like(got)
     got2 = tc_ops.conv2d(x, wp, x2=x2, bias=bias, residual=res, stride=stride)
     _close(got2, ref - temb.float()[:, None, None, :] + res.float())
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160),
+                                             (3, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (1, 8, 1024, 77, 80),
+                                             (2, 8, 256, 77, 160), (1, 4, 200, 300, 16), (1, 2, 128, 129, 64)])
+def test_fused_attention_matches_torch(native_lib, B, heads, Nq, Nk, d):
+    """fused QK^T -> softmax -> PV (tcgen05, two-pass) vs fp32 torch attention on the same fp16 inputs;
+    UNet self-/cross-attention shapes plus ragged sizes (query / key tails, single and odd tile counts)"""
+    from riffusion import tc_ops
+
+    torch.manual_seed(Nq + Nk + d)
+    C = heads * d
+    q = (torch.randn(B, Nq, C, device="cuda") * 1.5).half()
+    k = (torch.randn(B, Nk, C, device="cuda") * 1.5).half()
+    v = torch.randn(B, Nk, C, device="cuda").half()
+    pitch = (Nk + 7) // 8 * 8
+    vt = torch.zeros(B, C, pitch, dtype=torch.float16, device="cuda")
+    vt[..., :Nk] = v.transpose(1, 2)
+    qh, kh, vh = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, dim=-1) @ vh
+    ref = ref.transpose(1, 2).reshape(B, Nq, C)
+    got = tc_ops.attention(q, k, vt, heads, Nk)
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    _close(got, ref, tol=4e-3)
+    assert float((got.float() - ref).norm() / ref.norm()) < 2e-3
