@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py — throughput of the hot path on N B200s of one node (driver contract).
 
-Workload at N=1 (config.workload): BASELINE.json configs[1] — inverse-mel + 32-iteration Griffin-Lim
-reconstruction of 512x512 mel spectrograms, batch 64 per GPU.  Until the denoising path (b) lands
-the "clip" of the clips/sec metric is one Griffin-Lim reconstructed clip (config.includes_denoise
-= false); the 50-step UNet part of BASELINE's metric is not in this number.
+Two workloads:
+  --workload clip (default): BASELINE's metric — clips/sec of a full 512x512 clip: 50 UNet evaluations (img2img with
+      denoising 1.0, classifier-free guidance, PNDM) + VAE decode + image -> mel -> inverse mel -> 32-iteration
+      Griffin-Lim, random-init SD-1.5 weights (BASELINE config 4: no network for the checkpoint), `--clips` clips
+      per GPU per step.  roofline = the tcgen05 GEMM/conv kernel (tensor bound).  The Griffin-Lim sub-benchmark of
+      configs[1] is run too and reported under "griffinlim" (its own HBM roofline = "GL HBM GB/s" of the metric).
+  --workload gl: only BASELINE configs[1] — inverse-mel + 32-iteration Griffin-Lim, 512x512 mel, batch 64 per GPU.
 
-One "step" = one pass of the hot path over one batch of 64 synthetic clips per GPU.
+gl workload: one "step" = one pass of the hot path over one batch of 64 synthetic clips per GPU.
   value  : clips/s, whole job, inputs (mel amplitudes + initial phases) resident in HBM
   e2e    : clips/s through SpectrogramConverter.waveform_from_mel_amplitudes with HOST buffers:
            pinned mel -> H2D, torch.rand phase init (as the reference does per call), kernels,
@@ -153,12 +156,17 @@ def time_reference(steps: int, warmup: int, host_cores: int) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="clip", choices=["clip", "gl"])
+    ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step (clip workload)")
+    ap.add_argument("--evals", type=int, default=50, help="scheduler steps = UNet evaluations per clip (denoising 1.0)")
     args = ap.parse_args()
+    if args.workload == "clip" and args.impl == "b200":
+        return main_clip(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -316,6 +324,246 @@ def main() -> None:
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": e2e, "gpu_launches": int((sum(launches) + 2) * args.steps), "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# =============================================================================== clip workload
+UNET_TFLOP_PER_SAMPLE = 0.803     # 401.6 GMAC per sample-forward
+VAE_DEC_TFLOP = 2.515
+
+
+def tensor_peaks() -> dict:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"burst": float(d["bf16_tflops"]), "sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "source": "fallback"}
+
+
+def time_reference_clip(host_cores: int, budget_s: float = 25.0) -> dict:
+    """CPU baseline for the clip workload on a bounded sample: the reference's arithmetic for one clip is
+    n_evals x (CFG UNet forward, fp32 on CPU as riffusion_pipeline.py:88-90 forces) + VAE decode + torchaudio
+    inverse-mel/Griffin-Lim.  diffusers is not installable, so the UNet/VAE are the torch-eager restatement
+    (oracle/unet_oracle.py, kind = "port"); ONE CFG UNet evaluation and the torchaudio audio path are timed and the
+    per-clip time is n_evals * t_unet + t_audio (the VAE decode, ~3 % of the FLOPs, is extrapolated from the UNet
+    rate) — stated in `sample`."""
+    from oracle import unet_oracle as uo
+
+    threads = min(host_cores, 32)
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        unet = uo.init_weights_(uo.UNet2DConditionOracle()).eval()
+        x = torch.randn(2, 4, 64, 64)
+        ctx = torch.randn(2, 77, 768)
+        t0 = time.perf_counter()
+        unet(x, 741, ctx)
+        t_unet = time.perf_counter() - t0
+    audio = time_reference(1, 1, host_cores)
+    return {"t_unet_cfg_eval_s": t_unet, "t_audio_s": audio["seconds_per_clip"], "threads": threads,
+            "audio_threads": audio["cores"]}
+
+
+def main_clip(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from riffusion import _native, sd15_spec, tc_ops
+    from riffusion.riffusion_pipeline import RiffusionPipeline, VAE_SCALE
+    from riffusion.spectrogram_converter import SpectrogramConverter
+    from riffusion.spectrogram_params import SpectrogramParams
+    from riffusion.unet_b200 import UNetB200
+    from riffusion.vae_b200 import VaeB200
+    from riffusion.util import torch_util
+
+    lib = _native.lib()
+    # frozen weights: created on rank 0 and broadcast once over NCCL (init only; no collective in the step loop)
+    unet_spec, vae_spec = sd15_spec.unet_spec(), sd15_spec.vae_spec()
+    if rank == 0:
+        unet_sd = {k: v.to(dev) for k, v in sd15_spec.random_state_dict(unet_spec, 0).items()}
+        vae_sd = {k: v.to(dev) for k, v in sd15_spec.random_state_dict(vae_spec, 1).items()}
+    else:
+        unet_sd = {k: torch.empty(shp, dtype=torch.float16, device=dev) for k, shp in unet_spec}
+        vae_sd = {k: torch.empty(shp, dtype=torch.float16, device=dev) for k, shp in vae_spec}
+    if dist is not None:
+        for sd in (unet_sd, vae_sd):
+            flat = torch.cat([t.reshape(-1) for t in sd.values()])
+            dist.broadcast(flat, src=0)
+            off = 0
+            for k, t in sd.items():
+                sd[k] = flat[off: off + t.numel()].view(t.shape)
+                off += t.numel()
+    pipe = RiffusionPipeline(vae=VaeB200(vae_sd, device=str(dev)), unet=UNetB200(unet_sd, device=str(dev)), device=str(dev))
+    del unet_sd, vae_sd
+    params = SpectrogramParams()
+    conv = SpectrogramConverter(params, device=str(dev))
+
+    B, n_steps = args.clips, args.evals
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    text = torch.randn((B, 77, 768), generator=g, device=dev, dtype=torch.float16)      # SURVEY 8(d) config 4: N(0,1) embeddings
+    uncond = torch.randn((1, 77, 768), generator=g, device=dev, dtype=torch.float16)
+    seed_rgb = torch.from_numpy(np.load(ROOT / "tests" / "golden" / "og_beat.npz")["rgb"].copy())   # (512,512,3) u8
+    seed_host = seed_rgb.pin_memory()
+    text_host, uncond_host = text.cpu().pin_memory(), uncond.cpu().pin_memory()
+    alphas = torch.linspace(0, 1, B).tolist()
+    img = (seed_rgb.to(dev).permute(2, 0, 1)[None].half() / 255.0) * 2 - 1
+    mean, logvar = pipe.vae.encode_moments(img)                                          # cacheable per seed image
+    std = torch.exp(0.5 * logvar.float().clamp(-30, 20))
+
+    def make_inputs():
+        """per-request tensors the reference draws from its generators: posterior noise + noise_a/noise_b -> slerp"""
+        lat, noises = [], []
+        for i in range(B):
+            ga = torch.Generator(device=dev).manual_seed(i + 1000 * rank)
+            gb = torch.Generator(device=dev).manual_seed(10_000 + i + 1000 * rank)
+            eps = torch.randn(mean.shape, generator=ga, device=dev)
+            lat.append((VAE_SCALE * (mean.float() + std * eps)).half())
+            na = torch.randn(mean.shape, generator=ga, device=dev, dtype=torch.float16)
+            nb = torch.randn(mean.shape, generator=gb, device=dev, dtype=torch.float16)
+            noises.append(torch_util.slerp(alphas[i], na, nb))
+        return torch.cat(lat), torch.cat(noises)
+
+    lat0, noise0 = make_inputs()
+    F = 8821
+    torch.manual_seed(rank)
+    angles = torch.rand((B, F, T_FRAMES), dtype=torch.complex64, device=dev)
+    pcm_host = torch.empty((B, L_WAVE), dtype=torch.int16).pin_memory()
+    img_host = torch.empty((B, 512, 512, 3), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        return pipe.generate_clips(text, uncond, lat0, noise0, 1.0, n_steps, 7.0, conv, init_angles=angles)
+
+    def step_e2e():
+        # host buffers in: seed image + text embeddings; out: uint8 image + int16 pcm
+        rgb = seed_host.to(dev, non_blocking=True)
+        t_emb = text_host.to(dev, non_blocking=True)
+        u_emb = uncond_host.to(dev, non_blocking=True)
+        im = (rgb.permute(2, 0, 1)[None].half() / 255.0) * 2 - 1
+        m_, lv_ = pipe.vae.encode_moments(im)            # the reference re-encodes the seed image on every request
+        lat, nz = make_inputs()
+        out = pipe.generate_clips(t_emb, u_emb, lat, nz, 1.0, n_steps, 7.0, conv)      # random GL phases like the reference
+        w = out["waveform"]
+        pcm = torch.empty((B, L_WAVE), dtype=torch.int16, device=dev)
+        scratch = torch.zeros(1, dtype=torch.float32, device=dev)
+        for i in range(B):                               # per-clip peak normalisation (audio_util.py:24)
+            _native.check(lib.rf_wave_to_int16(w[i].data_ptr(), 1, L_WAVE, 1, pcm[i].data_ptr(), scratch.data_ptr(),
+                                               stream.cuda_stream))
+        pcm_host.copy_(pcm, non_blocking=True)
+        img_host.copy_(out["images"], non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        out = step_device()
+    n_evals = out["n_unet_evals"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # live tensor-core measurement: one eager (non-graph) step with CUDA events around every tcgen05 launch
+    pipe.use_cuda_graph = False
+    step_device()
+    lib.rf_tc_profile_begin()
+    step_device()
+    tc_ms, tc_fl, tc_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_long()
+    lib.rf_tc_profile_end(ctypes.byref(tc_ms), ctypes.byref(tc_fl), ctypes.byref(tc_n))
+    pipe.use_cuda_graph = True
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    clips = B * world
+    value = clips / (ms_step / 1e3)
+    pk = tensor_peaks()
+    achieved = tc_fl.value / (tc_ms.value / 1e3) / 1e12
+    alg_tflop_step = B * (n_evals * 2 * UNET_TFLOP_PER_SAMPLE + VAE_DEC_TFLOP)
+    roofline = {
+        "bound": "tensor", "kernel": "k_tc_gemm (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved,
+        "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "traffic": None,
+        "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+        "kernel_ms_per_step": tc_ms.value, "kernel_launches_per_step": tc_n.value,
+        "kernel_flops_per_step": tc_fl.value, "kernel_share_of_step": tc_ms.value / ms_step,
+        "note": "kernel time and FLOPs (2MNK, true extents, fused-attention MMAs not included) measured live with "
+                "CUDA events around every launch of one eager step; share is vs the CUDA-graph step",
+        "step": {"algorithmic_tflop": alg_tflop_step, "achieved": alg_tflop_step / (ms_step / 1e3),
+                 "frac": alg_tflop_step / (ms_step / 1e3) / pk["sustained"], "unit": "TFLOP/s",
+                 "formula": "B*(n_evals*2*0.803 + 2.515) TFLOP (SURVEY 8d)"},
+    }
+    ms_e2e_step = ms_e2e / args.steps
+    e2e = {"value": clips / (ms_e2e_step / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e_step,
+           "h2d_bytes_per_step": int(seed_host.numel() + text_host.numel() * 2 + uncond_host.numel() * 2),
+           "d2h_bytes_per_step": int(pcm_host.numel() * 2 + img_host.numel()),
+           "api": "VaeB200.encode_moments + RiffusionPipeline.generate_clips + rf_wave_to_int16: pinned host seed image and "
+                  "text embeddings in, uint8 images and int16 PCM out"}
+    # Griffin-Lim sub-benchmark (BASELINE configs[1]) in a child process so that its memory does not add to ours
+    gl = None
+    cpu_baseline = None
+    if world == 1:
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--workload", "gl", "--steps", "5", "--warmup", "3",
+                                "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+            gl_line = json.loads(r.stdout.strip().splitlines()[-1])
+            gl = {"value": gl_line["value"], "unit": gl_line["unit"], "ms_per_step": gl_line["ms_per_step"],
+                  "workload": gl_line["config"]["workload"], "roofline": gl_line["roofline"], "e2e": gl_line["e2e"]}
+        except Exception as exc:  # noqa: BLE001
+            gl = {"error": repr(exc)}
+        if not args.no_cpu_baseline:
+            r = time_reference_clip(cores)
+            per_clip = n_evals * r["t_unet_cfg_eval_s"] * (1 + VAE_DEC_TFLOP / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE)) + r["t_audio_s"]
+            cpu_baseline = {"value": 1.0 / per_clip, "unit": "clips/s", "cores": r["threads"], "kind": "port",
+                            "sample": f"1 CFG UNet evaluation ({r['t_unet_cfg_eval_s']:.1f} s, torch-eager fp32 restatement, "
+                                      f"{r['threads']} threads) extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of "
+                                      f"torchaudio inverse-mel + Griffin-Lim ({r['t_audio_s']:.1f} s, {r['audio_threads']} threads); host has {cores} cores"}
+    config = {"workload": f"full clip: {n_steps}-step img2img (denoising 1.0 -> {n_evals} CFG UNet evaluations, guidance 7, PNDM) + VAE "
+                          f"decode + image->mel + inverse-mel + Griffin-Lim {N_ITER} it, 512x512, {B} clips per GPU per step",
+              "includes_denoise": True, "n_unet_evals": n_evals, "weights": "random-init SD-1.5 (N(0,0.02^2)), broadcast from rank 0 at init",
+              "clips_per_gpu": B, "cuda_graph": True,
+              "l2": "UNet weights 1.7 GB + activations larger than L2; no explicit flush",
+              "sharding": "independent clips per rank; NCCL broadcast of weights at init only"}
+    line = {
+        "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(args.steps * (n_evals * 600 + 400)), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "griffinlim": gl,
     }
     print(json.dumps(line))
     if dist is not None:

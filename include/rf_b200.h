@@ -228,6 +228,10 @@ int rf_concat_channels_f16(const void* a, const void* b, long pixels, int Ca, in
  * (and the latents / 0.18215 of riffusion_pipeline.py:427 folded into in_scale) */
 int rf_conv1x1_small_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int Cout, long HW,
                          float in_scale, void* y_nchw, void* stream);
+/* decoded image -> uint8 RGB: (x/2 + 0.5).clamp(0,1) then (x*255).round() (riffusion_pipeline.py:430-434 + diffusers
+ * numpy_to_pil); x fp16 NCHW (B,3,H,W) -> y uint8 NHWC (B,H,W,3).  Device-side glue between VAE decode and
+ * rf_image_to_mel. */
+int rf_vae_image_to_u8(const void* x_nchw, int B, int H, int W, uint8_t* y_nhwc, void* stream);
 /* conv_in: Conv2d(Cin<=8 -> Cout, 3x3, pad 1) reading NCHW fp16, writing NHWC; w = torch layout [Cout][Cin][3][3] */
 int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int H, int W, int Cout,
                    void* y_nhwc, void* stream);

@@ -390,7 +390,8 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
         int rc = map4(&mk, k, dims, str, box);
         if (rc) return rc;
     }
-    const int NV = (d + 15) / 16 * 16;
+    // must equal the NV template argument of the kernel variant chosen below (the TMA box defines the bytes per stage)
+    const int NV = d <= 48 ? 48 : d <= 64 ? 64 : d <= 80 ? 80 : d <= 128 ? 128 : d <= 160 ? 160 : 192;
     {
         const long dims[4] = {Nk, d, heads, B};
         const long str[4] = {1, vt_pitch, static_cast<long>(d) * vt_pitch, C * vt_pitch};

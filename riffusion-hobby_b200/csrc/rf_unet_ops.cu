@@ -345,6 +345,22 @@ __global__ void k_conv1x1_small(const __half* __restrict__ x, const __half* __re
     }
 }
 
+// VAE output -> PIL-equivalent uint8 image: (x/2 + 0.5).clamp(0,1) * 255, round half to even (numpy .round()),
+// NCHW fp16 (B,3,H,W) -> NHWC uint8 (B,H,W,3)      (riffusion_pipeline.py:430-434 + numpy_to_pil)
+__global__ void k_vae_to_u8(const __half* __restrict__ x, int B, size_t HW, uint8_t* __restrict__ y) {
+    const size_t n = static_cast<size_t>(B) * HW;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t b = i / HW, p = i % HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = __half2float(x[(b * 3 + c) * HW + p]);       // fp16 tensor, upcast like image.float()
+            v = fminf(fmaxf(v / 2.f + 0.5f, 0.f), 1.f);
+            y[i * 3 + c] = static_cast<uint8_t>(rintf(v * 255.f));
+        }
+    }
+}
+
 inline unsigned grid_for(size_t n, int block) {
     size_t g = (n + block - 1) / block;
     return static_cast<unsigned>(g > 148 * 16 ? 148 * 16 : (g ? g : 1));
@@ -444,6 +460,15 @@ extern "C" int rf_conv1x1_small_f16(const void* x_nchw, const void* w, const voi
         static_cast<const __half*>(x_nchw), static_cast<const __half*>(w), static_cast<const __half*>(bias), B, Cin, Cout,
         static_cast<size_t>(HW), in_scale, static_cast<__half*>(y_nchw));
     RF_CUDA_LAUNCH_CHECK("k_conv1x1_small");
+    return RF_OK;
+}
+
+extern "C" int rf_vae_image_to_u8(const void* x_nchw, int B, int H, int W, uint8_t* y_nhwc, void* stream) {
+    if (!x_nchw || !y_nhwc || B <= 0 || H <= 0 || W <= 0) return rf_fail(RF_ERR_INVALID, "rf_vae_image_to_u8: bad argument");
+    const size_t HW = static_cast<size_t>(H) * W;
+    k_vae_to_u8<<<grid_for(static_cast<size_t>(B) * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x_nchw), B, HW, y_nhwc);
+    RF_CUDA_LAUNCH_CHECK("k_vae_to_u8");
     return RF_OK;
 }
 

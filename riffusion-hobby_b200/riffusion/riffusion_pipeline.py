@@ -155,7 +155,7 @@ class RiffusionPipeline:
                             num_images_per_prompt: int = 1, eta: T.Optional[float] = 0.0,
                             output_type: T.Optional[str] = "pil", uncond_embeddings: T.Optional[torch.Tensor] = None,
                             noise_a: T.Optional[torch.Tensor] = None, noise_b: T.Optional[torch.Tensor] = None,
-                            **kwargs) -> T.Dict[str, T.Any]:
+                            noise: T.Optional[torch.Tensor] = None, **kwargs) -> T.Dict[str, T.Any]:
         """riffusion_pipeline.py:289-436.  Extra keyword-only inputs (`uncond_embeddings`, `noise_a`, `noise_b`)
         let callers inject what the reference computes internally (CLIP("") and the generator draws) — used by
         the parity tests and by runs without a text encoder."""
@@ -189,11 +189,13 @@ class RiffusionPipeline:
         init_timestep = min(int(num_inference_steps * strength) + offset, num_inference_steps)    # :361-363
         t_noise = int(self.scheduler.timesteps[-init_timestep])                                   # :365
         init_latents = init_latents.to(device=dev, dtype=latents_dtype).contiguous()
-        if noise_a is None:
-            noise_a = torch.randn(init_latents.shape, generator=generator_a, device=self.device, dtype=latents_dtype)
-        if noise_b is None:
-            noise_b = torch.randn(init_latents.shape, generator=generator_b, device=self.device, dtype=latents_dtype)
-        noise = torch_util.slerp(interpolate_alpha, noise_a.to(dev, latents_dtype), noise_b.to(dev, latents_dtype)).contiguous()
+        if noise is None:
+            if noise_a is None:
+                noise_a = torch.randn(init_latents.shape, generator=generator_a, device=self.device, dtype=latents_dtype)
+            if noise_b is None:
+                noise_b = torch.randn(init_latents.shape, generator=generator_b, device=self.device, dtype=latents_dtype)
+            noise = torch_util.slerp(interpolate_alpha, noise_a.to(dev, latents_dtype), noise_b.to(dev, latents_dtype))
+        noise = noise.to(dev, latents_dtype).contiguous()
         init_latents_orig = init_latents
         latents = self.scheduler.add_noise(init_latents, noise, t_noise)                           # :379
 
@@ -231,6 +233,35 @@ class RiffusionPipeline:
         image = (image.float() / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()             # :430-431
         out["images"] = self.numpy_to_pil(image) if output_type == "pil" else image
         return out
+
+    # ------------------------------------------------------------------------------ batched request -> audio
+    @torch.no_grad()
+    def generate_clips(self, text_embeddings: torch.Tensor, uncond_embeddings: torch.Tensor, init_latents: torch.Tensor,
+                       noise: torch.Tensor, strength: float, num_inference_steps: int, guidance_scale: float,
+                       converter, init_angles: T.Optional[torch.Tensor] = None) -> T.Dict[str, torch.Tensor]:
+        """B independent requests end to end on the device: denoise -> VAE decode -> uint8 image ->
+        mel amplitudes (image_util.spectrogram_from_image semantics, mono = R plane) -> inverse mel + Griffin-Lim.
+        This is what `server.compute_request` does per request (riffuse, then audio_from_spectrogram_image,
+        server.py:145-164) without leaving the GPU in between.  Returns device tensors:
+        images (B,512,512,3) uint8, waveform (B, L) fp32, latents."""
+        from riffusion import _native
+
+        out = self.interpolate_img2img(
+            text_embeddings=text_embeddings, init_latents=init_latents, generator_a=None, generator_b=None,
+            interpolate_alpha=0.0, strength_a=strength, strength_b=strength, num_inference_steps=num_inference_steps,
+            guidance_scale=guidance_scale, uncond_embeddings=uncond_embeddings, noise=noise, output_type="latent")
+        latents = out["latents"]
+        image = self.vae.decode(latents, scale=1.0 / VAE_SCALE).sample
+        u8 = ops.vae_image_to_u8(image)
+        B, H, W, _ = u8.shape
+        mel = torch.empty((B, H, W), dtype=torch.float32, device=u8.device)
+        lib = _native.lib()
+        p = converter.p
+        for i in range(B):
+            _native.check(lib.rf_image_to_mel(u8[i].data_ptr(), H, W, 0, float(p.power_for_image), 30e6, mel[i].data_ptr(),
+                                              _native.stream_ptr(u8.device)))
+        wave = converter.waveform_from_mel_amplitudes(mel, init_angles)
+        return dict(images=u8, waveform=wave, latents=latents, n_unet_evals=out["n_unet_evals"])
 
     @staticmethod
     def numpy_to_pil(images: np.ndarray) -> T.List[Image.Image]:

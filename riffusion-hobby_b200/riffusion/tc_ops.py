@@ -268,3 +268,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, heads: int, nk
         _native.check(_native.lib().rf_attention_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Nq,
                                                      nk, d, vt.shape[-1], float(d) ** -0.5, _stream(q)))
     return out
+
+
+def vae_image_to_u8(x_nchw: torch.Tensor) -> torch.Tensor:
+    """(B, 3, H, W) fp16 in [-1, 1] -> (B, H, W, 3) uint8, the array PIL images are built from."""
+    _f16(x_nchw, "x")
+    B, Cc, H, W = x_nchw.shape
+    assert Cc == 3
+    y = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x_nchw.device)
+    with torch.cuda.device(x_nchw.device):
+        _native.check(_native.lib().rf_vae_image_to_u8(x_nchw.contiguous().data_ptr(), B, H, W, y.data_ptr(), _stream(x_nchw)))
+    return y
