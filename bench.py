@@ -426,16 +426,16 @@ def main_clip(args) -> None:
 
     def make_inputs():
         """per-request tensors the reference draws from its generators: posterior noise + noise_a/noise_b -> slerp"""
-        lat, noises = [], []
+        lat, nas, nbs = [], [], []
         for i in range(B):
             ga = torch.Generator(device=dev).manual_seed(i + 1000 * rank)
             gb = torch.Generator(device=dev).manual_seed(10_000 + i + 1000 * rank)
             eps = torch.randn(mean.shape, generator=ga, device=dev)
             lat.append((VAE_SCALE * (mean.float() + std * eps)).half())
-            na = torch.randn(mean.shape, generator=ga, device=dev, dtype=torch.float16)
-            nb = torch.randn(mean.shape, generator=gb, device=dev, dtype=torch.float16)
-            noises.append(torch_util.slerp(alphas[i], na, nb))
-        return torch.cat(lat), torch.cat(noises)
+            nas.append(torch.randn(mean.shape, generator=ga, device=dev, dtype=torch.float16))
+            nbs.append(torch.randn(mean.shape, generator=gb, device=dev, dtype=torch.float16))
+        noise = tc_ops.slerp(alphas, torch.cat(nas), torch.cat(nbs))       # per-request slerp on the device (rf_slerp_f16)
+        return torch.cat(lat), noise
 
     lat0, noise0 = make_inputs()
     F = 8821

@@ -241,6 +241,10 @@ int rf_conv_out_f16(const void* x_nhwc, const void* w_packed, const void* bias, 
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): t fp32 [B] -> fp16 [B][dim] */
 int rf_timestep_embedding_f16(const float* d_t, int B, int dim, void* out, void* stream);
 int rf_silu_f16(const void* x, long n, void* y, void* stream);
+/* torch_util.slerp (riffusion/util/torch_util.py:21-48) per sample on the device: v0, v1, out fp16 [B][n]; d_alphas fp32
+ * device [B]; d_scratch fp32 device [3*B].  fp32 reductions (the reference reduces in the tensors' dtype on the host). */
+int rf_slerp_f16(const void* v0, const void* v1, int B, long n, const float* d_alphas, float dot_threshold, void* out,
+                 float* d_scratch, void* stream);
 /* classifier-free guidance + PNDM/PLMS multistep update on n = elements of ONE batch half:
  *   eps = eps_u + g (eps_t - eps_u) (riffusion_pipeline.py:411-415); e = c0 eps + c1 h1 + c2 h2 + c3 h3;
  *   prev = ca * sample - cb * e (PNDMScheduler._get_prev_sample).  eps_pair = [uncond | text] (2n). coef4: HOST float[4].

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <string>
 
 #include "rf_common.h"
@@ -33,40 +34,50 @@ __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); 
 //         fixed order (no atomics: repeated runs are bit-identical).
 // pass 2: one warp per (image, group) adds the slab partials in a fixed order -> (mean, rstd).
 // pass 3: y = (x - mean) * rstd * gamma + beta, optional SiLU.
+template <int MAXK>
 __global__ void k_gn_partial(const __half* __restrict__ x, int HW, int C, int G, int slab, int nslabs,
                              float* __restrict__ part /*[B][nslabs][G][2]*/) {
-    extern __shared__ float2 shp[];  // [R][C2]
+    extern __shared__ float2 shp[];  // [nwarps][C2]
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
     const int cpg2 = (C / G) >> 1;  // half2 pairs per group
     const int C2 = C >> 1;
-    const int CW = C2 < static_cast<int>(blockDim.x) ? C2 : static_cast<int>(blockDim.x);
-    const int R = blockDim.x / CW;
-    const int prow = threadIdx.x / CW, lc = threadIdx.x - prow * CW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
-    if (prow < R) {
-        for (int c2 = lc; c2 < C2; c2 += CW) {
-            float s = 0.f, ss = 0.f;
-            for (int p = p0 + prow; p < p1; p += R) {
-                const float2 v = __half22float2(xb[static_cast<size_t>(p) * C2 + c2]);
-                s += v.x + v.y;
-                ss += v.x * v.x + v.y * v.y;
+    // each lane owns the channel pairs lane, lane+32, ... ; each warp walks its pixels: 128-byte coalesced loads
+    float s[MAXK], ss[MAXK];   // MAXK >= ceil(C/64)
+    const int nk = (C2 + 31) / 32;
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) s[k] = ss[k] = 0.f;
+    for (int p = p0 + warp; p < p1; p += nw) {
+        const __half2* row = xb + static_cast<size_t>(p) * C2;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            if (k < nk) {
+                const int c2 = lane + 32 * k;
+                if (c2 < C2) {
+                    const float2 v = __half22float2(row[c2]);
+                    s[k] += v.x + v.y;
+                    ss[k] += v.x * v.x + v.y * v.y;
+                }
             }
-            shp[prow * C2 + c2] = make_float2(s, ss);
         }
     }
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+        if (k < nk && lane + 32 * k < C2) shp[warp * C2 + lane + 32 * k] = make_float2(s[k], ss[k]);
     __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        float s = 0.f, ss = 0.f;
-        for (int r = 0; r < R; ++r)
+        float a = 0.f, q = 0.f;
+        for (int w = 0; w < nw; ++w)
             for (int k = 0; k < cpg2; ++k) {
-                const float2 v = shp[r * C2 + g * cpg2 + k];
-                s += v.x;
-                ss += v.y;
+                const float2 v = shp[w * C2 + g * cpg2 + k];
+                a += v.x;
+                q += v.y;
             }
         float* o = part + ((static_cast<size_t>(b) * nslabs + blockIdx.x) * G + g) * 2;
-        o[0] = s;
-        o[1] = ss;
+        o[0] = a;
+        o[1] = q;
     }
 }
 
@@ -95,28 +106,37 @@ __global__ void k_gn_apply(const __half* __restrict__ x, const float* __restrict
                            const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C,
                            int G, int act, __half* __restrict__ y) {
     const int b = blockIdx.y;
-    const size_t n2 = static_cast<size_t>(HW) * C / 2;
+    const size_t n8 = static_cast<size_t>(HW) * C / 8;   // uint4 = 8 halves (C % 8 == 0)
+    const int C8 = C / 8;
     const int cpg = C / G;
-    const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
-    __half2* yb = reinterpret_cast<__half2*>(y + static_cast<size_t>(b) * HW * C);
-    const __half2* g2 = reinterpret_cast<const __half2*>(gamma);
-    const __half2* b2 = reinterpret_cast<const __half2*>(beta);
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2;
+    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C);
+    uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(b) * HW * C);
+    const float* st = stats + static_cast<size_t>(b) * G * 2;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c2 = static_cast<int>(i % (C / 2));
-        const int g = (2 * c2) / cpg;
-        const float mean = stats[(static_cast<size_t>(b) * G + g) * 2];
-        const float rstd = stats[(static_cast<size_t>(b) * G + g) * 2 + 1];
-        const float2 v = __half22float2(xb[i]);
-        const float2 ga = __half22float2(g2[c2]);
-        const float2 be = __half22float2(b2[c2]);
-        float o0 = (v.x - mean) * rstd * ga.x + be.x;
-        float o1 = (v.y - mean) * rstd * ga.y + be.y;
-        if (act) {
-            o0 = silu(o0);
-            o1 = silu(o1);
+        const int c0 = static_cast<int>(i % C8) * 8;
+        uint4 v = xb[i];
+        const uint4 gv = *reinterpret_cast<const uint4*>(gamma + c0);
+        const uint4 bv = *reinterpret_cast<const uint4*>(beta + c0);
+        __half2* vh = reinterpret_cast<__half2*>(&v);
+        const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g = (c0 + 2 * j) / cpg;           // cpg is even: a half2 never straddles two groups
+            const float mean = st[2 * g], rstd = st[2 * g + 1];
+            const float2 xv = __half22float2(vh[j]);
+            const float2 ga = __half22float2(gh[j]);
+            const float2 be = __half22float2(bh[j]);
+            float o0 = (xv.x - mean) * rstd * ga.x + be.x;
+            float o1 = (xv.y - mean) * rstd * ga.y + be.y;
+            if (act) {
+                o0 = silu(o0);
+                o1 = silu(o1);
+            }
+            vh[j] = __floats2half2_rn(o0, o1);
         }
-        yb[i] = __floats2half2_rn(o0, o1);
+        yb[i] = v;
     }
 }
 
@@ -202,26 +222,38 @@ __global__ void k_upsample2x(const __half* __restrict__ x, int B, int H, int W, 
 
 // ---------------------------------------------------------------- edge convolutions (tiny channel counts)
 // conv_in: NCHW fp16 (B, Cin<=8, H, W) -> NHWC fp16 (B, H, W, Cout), 3x3 pad 1. weights [Cout][Cin][3][3] fp16.
+// CTA = 64 consecutive pixels (8 per warp); the weights are staged once per CTA, transposed to [k][cout] so that
+// lanes (consecutive couts) read conflict-free and write coalesced NHWC rows.
 __global__ void k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                           int B, int Cin, int H, int W, int Cout, __half* __restrict__ y) {
-    extern __shared__ float wsm[];  // [Cout][Cin*9]
+    extern __shared__ float wsm[];  // [Cin*9][Cout]
     const int K = Cin * 9;
-    for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) wsm[i] = __half2float(w[i]);
+    for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {
+        const int co = i / K, k = i - co * K;
+        wsm[k * Cout + co] = __half2float(w[i]);
+    }
     __syncthreads();
-    const size_t pix = static_cast<size_t>(blockIdx.x);  // one pixel per CTA
-    const int xq = static_cast<int>(pix % W), yq = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
-    float in[72];
-    for (int c = 0; c < Cin; ++c)
-        for (int t = 0; t < 9; ++t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t npix = static_cast<size_t>(B) * H * W;
+    for (int j = 0; j < 8; ++j) {
+        const size_t pix = static_cast<size_t>(blockIdx.x) * 64 + warp * 8 + j;
+        if (pix >= npix) break;
+        const int xq = static_cast<int>(pix % W), yq = static_cast<int>((pix / W) % H);
+        const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+        float in[72];
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const int c = k / 9, t = k - c * 9;
             const int yy = yq + t / 3 - 1, xx = xq + t % 3 - 1;
-            in[c * 9 + t] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                                ? __half2float(x[((static_cast<size_t>(b) * Cin + c) * H + yy) * W + xx])
-                                : 0.f;
+            in[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                        ? __half2float(x[((static_cast<size_t>(b) * Cin + c) * H + yy) * W + xx])
+                        : 0.f;
         }
-    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-        float acc = bias ? __half2float(bias[co]) : 0.f;
-        for (int k = 0; k < K; ++k) acc += wsm[co * K + k] * in[k];
-        y[pix * Cout + co] = __float2half_rn(acc);
+        for (int co = lane; co < Cout; co += 32) {
+            float acc = bias ? __half2float(bias[co]) : 0.f;
+            for (int k = 0; k < K; ++k) acc += wsm[k * Cout + co] * in[k];
+            y[pix * Cout + co] = __float2half_rn(acc);
+        }
     }
 }
 
@@ -361,6 +393,68 @@ __global__ void k_vae_to_u8(const __half* __restrict__ x, int B, size_t HW, uint
     }
 }
 
+// ---------------------------------------------------------------- slerp of noise tensors, per sample
+// riffusion/util/torch_util.py:21-48 on the device: dot = <v0,v1>/(|v0||v1|); |dot| > thr -> lerp, else
+// s0 = sin((1-t) th)/sin th, s1 = sin(t th)/sin th.  Reductions in fp32, fixed order (one CTA per sample).
+__global__ void k_slerp_stats(const __half* __restrict__ v0, const __half* __restrict__ v1, size_t n,
+                              float* __restrict__ stats /*[B][3]*/) {
+    __shared__ float sh[3][32];
+    const size_t b = blockIdx.x;
+    const __half* a = v0 + b * n;
+    const __half* c = v1 + b * n;
+    float d = 0.f, aa = 0.f, cc = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = __half2float(a[i]), y = __half2float(c[i]);
+        d += x * y;
+        aa += x * x;
+        cc += y * y;
+    }
+    d = warp_sum(d);
+    aa = warp_sum(aa);
+    cc = warp_sum(cc);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh[0][w] = d;
+        sh[1][w] = aa;
+        sh[2][w] = cc;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        d = l < nw ? sh[0][l] : 0.f;
+        aa = l < nw ? sh[1][l] : 0.f;
+        cc = l < nw ? sh[2][l] : 0.f;
+        d = warp_sum(d);
+        aa = warp_sum(aa);
+        cc = warp_sum(cc);
+        if (l == 0) {
+            stats[b * 3] = d;
+            stats[b * 3 + 1] = aa;
+            stats[b * 3 + 2] = cc;
+        }
+    }
+}
+
+__global__ void k_slerp_apply(const __half* __restrict__ v0, const __half* __restrict__ v1, size_t n,
+                              const float* __restrict__ stats, const float* __restrict__ alphas, float thr,
+                              __half* __restrict__ out) {
+    const size_t b = blockIdx.y;
+    const float t = alphas[b];
+    const float dot = stats[b * 3] / (sqrtf(stats[b * 3 + 1]) * sqrtf(stats[b * 3 + 2]));
+    float s0, s1;
+    if (fabsf(dot) > thr) {
+        s0 = 1.f - t;
+        s1 = t;
+    } else {
+        const float th = acosf(dot), sn = sinf(th);
+        s0 = sinf(th - th * t) / sn;
+        s1 = sinf(th * t) / sn;
+    }
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[b * n + i] = __float2half_rn(s0 * __half2float(v0[b * n + i]) + s1 * __half2float(v1[b * n + i]));
+}
+
 inline unsigned grid_for(size_t n, int block) {
     size_t g = (n + block - 1) / block;
     return static_cast<unsigned>(g > 148 * 16 ? 148 * 16 : (g ? g : 1));
@@ -369,7 +463,7 @@ inline unsigned grid_for(size_t n, int block) {
 }  // namespace
 
 extern "C" size_t rf_group_norm_scratch_floats(int B, int HW, int groups) {
-    const int nslabs = (HW + 63) / 64;
+    const int nslabs = (HW + 31) / 32;
     return static_cast<size_t>(B) * groups * 2 * (static_cast<size_t>(nslabs) + 1);
 }
 
@@ -379,24 +473,32 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
         ((C / groups) & 1))
         return rf_fail(RF_ERR_INVALID, "rf_group_norm_f16: bad argument (channels per group must be even)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int slab = 64;
+    const int slab = 32;
     const int nslabs = (HW + slab - 1) / slab;
     float* stats = d_scratch;                                          // [B][G][2]
     float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
     const int C2 = C / 2;
-    const int CW = C2 < 256 ? C2 : 256;
-    const int R = 256 / CW;
-    const size_t smem = static_cast<size_t>(R) * C2 * sizeof(float2);
-    if (smem > 48 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: too many channels");
+    if (C > 2560 || (C % 8)) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: C must be a multiple of 8, <= 2560");
+    const size_t smem = static_cast<size_t>(8) * C2 * sizeof(float2);
+    static bool attr = false;
+    if (!attr) {
+        RF_CUDA_TRY(cudaFuncSetAttribute(k_gn_partial<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(k_gn_partial<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
     dim3 grid(nslabs, B);
-    k_gn_partial<<<grid, 256, smem, st>>>(static_cast<const __half*>(x), HW, C, groups, slab, nslabs, part);
+    const __half* xh = static_cast<const __half*>(x);
+    if (C <= 320) k_gn_partial<5><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
+    else if (C <= 640) k_gn_partial<10><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
+    else if (C <= 1280) k_gn_partial<20><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
+    else k_gn_partial<40><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
     RF_CUDA_LAUNCH_CHECK("k_gn_partial");
     const int nbg = B * groups;
     if (nbg % 8) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: B*groups must be a multiple of 8");
     k_gn_finalize<<<nbg / 8, 256, 0, st>>>(part, nslabs, groups, 1.f / (static_cast<float>(HW) * (C / groups)), eps, stats);
     RF_CUDA_LAUNCH_CHECK("k_gn_finalize");
-    const size_t n2 = static_cast<size_t>(HW) * C / 2;
-    dim3 grid2(grid_for(n2, 256), B);
+    const size_t n8 = static_cast<size_t>(HW) * C / 8;
+    dim3 grid2(static_cast<unsigned>(std::min<size_t>((n8 + 255) / 256, 4096)), B);
     k_gn_apply<<<grid2, 256, 0, st>>>(static_cast<const __half*>(x), stats, static_cast<const __half*>(gamma),
                                       static_cast<const __half*>(beta), HW, C, groups, act, static_cast<__half*>(y));
     RF_CUDA_LAUNCH_CHECK("k_gn_apply");
@@ -452,6 +554,20 @@ extern "C" int rf_concat_channels_f16(const void* a, const void* b, long pixels,
     return RF_OK;
 }
 
+extern "C" int rf_slerp_f16(const void* v0, const void* v1, int B, long n, const float* d_alphas, float dot_threshold,
+                            void* out, float* d_scratch, void* stream) {
+    if (!v0 || !v1 || !out || !d_alphas || !d_scratch || B <= 0 || n <= 0) return rf_fail(RF_ERR_INVALID, "rf_slerp_f16: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_slerp_stats<<<B, 256, 0, st>>>(static_cast<const __half*>(v0), static_cast<const __half*>(v1), static_cast<size_t>(n),
+                                     d_scratch);
+    RF_CUDA_LAUNCH_CHECK("k_slerp_stats");
+    dim3 grid(grid_for(static_cast<size_t>(n), 256), B);
+    k_slerp_apply<<<grid, 256, 0, st>>>(static_cast<const __half*>(v0), static_cast<const __half*>(v1), static_cast<size_t>(n),
+                                        d_scratch, d_alphas, dot_threshold, static_cast<__half*>(out));
+    RF_CUDA_LAUNCH_CHECK("k_slerp_apply");
+    return RF_OK;
+}
+
 extern "C" int rf_conv1x1_small_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int Cout, long HW,
                                     float in_scale, void* y_nchw, void* stream) {
     if (!x_nchw || !w || !y_nchw || B <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0 || Cout > 8 || HW <= 0)
@@ -482,7 +598,8 @@ extern "C" int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bia
         RF_CUDA_TRY(cudaFuncSetAttribute(k_conv_in, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr = true;
     }
-    k_conv_in<<<static_cast<unsigned>(static_cast<size_t>(B) * H * W), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+    const size_t npix = static_cast<size_t>(B) * H * W;
+    k_conv_in<<<static_cast<unsigned>((npix + 63) / 64), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(x_nchw), static_cast<const __half*>(w), static_cast<const __half*>(bias), B, Cin, H, W,
         Cout, static_cast<__half*>(y_nhwc));
     RF_CUDA_LAUNCH_CHECK("k_conv_in");

@@ -110,6 +110,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "rf_timestep_embedding_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_silu_f16": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]),
+    "rf_slerp_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
     "rf_cfg_pndm_step_f16": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),

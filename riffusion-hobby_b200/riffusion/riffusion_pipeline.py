@@ -44,6 +44,7 @@ class RiffusionPipeline:
         self.text_encoder, self.tokenizer = text_encoder, tokenizer
         self._device = torch.device(device)
         self._moment_cache: T.Dict[int, T.Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.device_slerp = True        # rf_slerp_f16 instead of the reference's host-numpy round trip
         self.use_cuda_graph = True      # replay each CFG UNet evaluation as one CUDA graph
         self._graphs: T.Dict[T.Tuple, T.Any] = {}
 
@@ -194,7 +195,10 @@ class RiffusionPipeline:
                 noise_a = torch.randn(init_latents.shape, generator=generator_a, device=self.device, dtype=latents_dtype)
             if noise_b is None:
                 noise_b = torch.randn(init_latents.shape, generator=generator_b, device=self.device, dtype=latents_dtype)
-            noise = torch_util.slerp(interpolate_alpha, noise_a.to(dev, latents_dtype), noise_b.to(dev, latents_dtype))
+            if self.device_slerp:      # fp32 reductions on the GPU, no device->host->device round trip
+                noise = ops.slerp(interpolate_alpha, noise_a.to(dev, latents_dtype), noise_b.to(dev, latents_dtype))
+            else:                      # the reference's host-numpy slerp in fp16 (bit-compatible)
+                noise = torch_util.slerp(interpolate_alpha, noise_a.to(dev, latents_dtype), noise_b.to(dev, latents_dtype))
         noise = noise.to(dev, latents_dtype).contiguous()
         init_latents_orig = init_latents
         latents = self.scheduler.add_noise(init_latents, noise, t_noise)                           # :379

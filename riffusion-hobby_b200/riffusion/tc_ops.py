@@ -279,3 +279,20 @@ def vae_image_to_u8(x_nchw: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x_nchw.device):
         _native.check(_native.lib().rf_vae_image_to_u8(x_nchw.contiguous().data_ptr(), B, H, W, y.data_ptr(), _stream(x_nchw)))
     return y
+
+
+def slerp(alphas, v0: torch.Tensor, v1: torch.Tensor, dot_threshold: float = 0.9995) -> torch.Tensor:
+    """Per-sample spherical interpolation on the device.  v0, v1: (B, ...) fp16; alphas: float or sequence of B floats."""
+    _f16(v0, "v0"), _f16(v1, "v1")
+    B = v0.shape[0]
+    n = v0.numel() // B
+    if not torch.is_tensor(alphas):
+        alphas = torch.tensor([float(alphas)] * B if not hasattr(alphas, "__len__") else [float(a) for a in alphas],
+                              dtype=torch.float32)
+    al = alphas.to(device=v0.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(v0)
+    scratch = torch.empty(3 * B, dtype=torch.float32, device=v0.device)
+    with torch.cuda.device(v0.device):
+        _native.check(_native.lib().rf_slerp_f16(v0.contiguous().data_ptr(), v1.contiguous().data_ptr(), B, n, al.data_ptr(),
+                                                 float(dot_threshold), out.data_ptr(), scratch.data_ptr(), _stream(v0)))
+    return out

@@ -205,3 +205,21 @@ def test_denoising_loop_matches_oracle_loop(native_lib):
         e = rel_l2(out["latents"], ref)
         print(f"loop steps={steps} strength={strength}: evals {n_ref}, rel_l2 {e:.3e}")
         assert e < 2e-2          # fp16 latents through n_ref guided steps (guidance 7 amplifies eps rounding 7x)
+
+
+def test_device_slerp_matches_reference_numpy(native_lib):
+    """device slerp (fp32 reductions) vs the reference's host-numpy slerp in fp16 (torch_util.py:21-48): within the
+    1e-3 bar; exact lerp fallback for nearly parallel vectors"""
+    from riffusion import tc_ops as ops
+    from riffusion.util import torch_util
+
+    torch.manual_seed(9)
+    a = torch.randn(3, 4, 64, 64, device="cuda").half()
+    b = torch.randn(3, 4, 64, 64, device="cuda").half()
+    alphas = [0.0, 0.25, 0.9]
+    got = ops.slerp(alphas, a, b)
+    for i, al in enumerate(alphas):
+        ref = torch_util.slerp(al, a[i:i + 1], b[i:i + 1])
+        assert rel_l2(got[i:i + 1], ref) < 1e-3
+    par = ops.slerp(0.3, a, (a.float() * 1.0001).half())
+    assert rel_l2(par, 0.7 * a.float() + 0.3 * a.float() * 1.0001) < 1e-3
