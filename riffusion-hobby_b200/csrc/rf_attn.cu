@@ -245,13 +245,18 @@ k_flash_attn(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c0 + i < kmax) ? exp2f(fmaf(__uint_as_float(v[i]), p.c, -mc)) : 0.f;
-                    float p1 = (c0 + i + 1 < kmax) ? exp2f(fmaf(__uint_as_float(v[i + 1]), p.c, -mc)) : 0.f;
-                    const __half2 h = __floats2half2_rn(p0, p1);
+                    // two exponentials per MUFU op (ex2.approx.f16x2): the SFU, not the tensor pipe, bounds small
+                    // head dims.  The argument is formed in fp32 and rounded once to fp16; P is stored as fp16 anyway.
+                    const float a0 = (c0 + i < kmax) ? fmaf(__uint_as_float(v[i]), p.c, -mc) : -INFINITY;
+                    const float a1 = (c0 + i + 1 < kmax) ? fmaf(__uint_as_float(v[i + 1]), p.c, -mc) : -INFINITY;
+                    const __half2 arg = __floats2half2_rn(a0, a1);
+                    uint32_t hbits;
+                    asm("ex2.approx.f16x2 %0, %1;" : "=r"(hbits) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+                    const __half2 h = *reinterpret_cast<const __half2*>(&hbits);
                     // accumulate the row sum from the rounded values the P V product will actually use
                     const float2 hr = __half22float2(h);
                     l += hr.x + hr.y;
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                    pk[i >> 1] = hbits;
                 }
                 // columns c0..c0+31 = 4 chunks of 8 halves; slab = c0 / 64, chunk index within the 128-byte row
                 const int slab = c0 >> 6;

@@ -35,6 +35,7 @@ struct TcParams {
     int M, N, K;            // GEMM mode: per-batch extents. conv mode: N = Cout, K unused
     int batch1, batch2;     // grid.z = batch1 * batch2
     int num_kb;             // K slabs
+    int tiles_m, tiles_n;   // output tiles per batch entry
     int a_m1, a_m2, b_m1, b_m2;  // 0 when the operand is broadcast along that batch dimension (stride 0)
     // conv mode
     int conv;               // 0 = GEMM, 1 = conv
@@ -63,37 +64,40 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// Persistent kernel: grid = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
+//   warp 0: TMA producer — streams the K slabs of all its tiles through one STAGES-deep ring (phases run across tiles)
+//   warp 1: MMA issuer  — accumulates tile i in TMEM buffer i&1, commits tmem_full[i&1]
+//   warps 2-9: epilogue — drain buffer i&1 (tcgen05.ld -> bias/act/residual -> global) while the MMA warp already works
+//              on tile i+1 in the other buffer; arrive tmem_empty[i&1] (256 threads) when done
+// Tile order: n fastest, then m, then batch, so CTAs running at the same time share activation rows in L2.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 3)
+__global__ void __launch_bounds__(320, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int B_TILE_BYTES = BN * BK * 2;
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_TILE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
-    const int b1 = blockIdx.z % p.batch1, b2 = blockIdx.z / p.batch1;
-
-    // conv tile origin
-    int tx = 0, ty = 0, tb = 0;
-    if (p.conv) {
-        tx = m_blk % p.tiles_x;
-        ty = (m_blk / p.tiles_x) % p.tiles_y;
-        tb = m_blk / (p.tiles_x * p.tiles_y);
-    }
+    const int tiles_mn = p.tiles_n * p.tiles_m;
+    const int n_tiles = tiles_mn * p.batch1 * p.batch2;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             tc::mbar_init(&full[i], 1);
             tc::mbar_init(&empty[i], 1);
         }
-        tc::mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tmem_full[i], 1);
+            tc::mbar_init(&tmem_empty[i], 256);
+        }
         tc::fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -101,7 +105,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         tc::tma_prefetch_desc(&mapB);
     }
     if (warp == 1) {
-        tc::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
         tc::tmem_relinquish();
     }
     tc::fence_before_sync();
@@ -111,122 +115,210 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------ TMA producer
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-            const int stage = kb % STAGES;
-            const uint32_t phase = (kb / STAGES) & 1;
-            tc::mbar_wait(&empty[stage], phase ^ 1);
-            tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
-            void* dstA = sA + stage * A_TILE_BYTES;
-            void* dstB = sB + stage * B_TILE_BYTES;
-            if (!p.conv) {
-                tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
-                tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, b1 * p.b_m1, b2 * p.b_m2);
-            } else {
-                const int kct = p.kc1 + p.kc2;
-                const int tap = kb / kct, kc = kb - tap * kct;
-                const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
-                const int x0 = tx * p.bw * p.stride + dx - p.pad;
-                const int y0 = ty * p.bh * p.stride + dy - p.pad;
-                if (kc < p.kc1)
-                    tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
-                else
-                    tc::tma_load_4d(&mapA1, &full[stage], dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
-                tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, 0, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
+            const int m_blk = mn / p.tiles_n, n_blk = mn - m_blk * p.tiles_n;
+            const int b1 = z % p.batch1, b2 = z / p.batch1;
+            int tx = 0, ty = 0, tb = 0;
+            if (p.conv) {
+                tx = m_blk % p.tiles_x;
+                ty = (m_blk / p.tiles_x) % p.tiles_y;
+                tb = m_blk / (p.tiles_x * p.tiles_y);
+            }
+            for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                const int stage = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                tc::mbar_wait(&empty[stage], phase ^ 1);
+                tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
+                void* dstA = sA + stage * A_TILE_BYTES;
+                void* dstB = sB + stage * B_TILE_BYTES;
+                if (!p.conv) {
+                    tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
+                    tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, b1 * p.b_m1, b2 * p.b_m2);
+                } else {
+                    const int kct = p.kc1 + p.kc2;
+                    const int tap = kb / kct, kc = kb - tap * kct;
+                    const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
+                    const int x0 = tx * p.bw * p.stride + dx - p.pad;
+                    const int y0 = ty * p.bh * p.stride + dy - p.pad;
+                    if (kc < p.kc1)
+                        tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
+                    else
+                        tc::tma_load_4d(&mapA1, &full[stage], dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
+                    tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, 0, 0);
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc::make_idesc_f16(BM, BN);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-            const int stage = kb % STAGES;
-            const uint32_t phase = (kb / STAGES) & 1;
-            tc::mbar_wait(&full[stage], phase);
-            tc::fence_after_sync();
-            const uint32_t a_base = tc::smem_u32(sA + stage * A_TILE_BYTES);
-            const uint32_t b_base = tc::smem_u32(sB + stage * B_TILE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-                const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
-                const uint64_t db = tc::make_desc_sw128(b_base + k * 32);
-                tc::mma_f16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+        int it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            if (lt >= 2) {                                   // the epilogue must have drained this accumulator
+                tc::mbar_wait(&tmem_empty[acc], ((lt >> 1) - 1) & 1);
+                tc::fence_after_sync();
             }
-            tc::mma_commit(&empty[stage]);
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                const int stage = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                tc::mbar_wait(&full[stage], phase);
+                tc::fence_after_sync();
+                const uint32_t a_base = tc::smem_u32(sA + stage * A_TILE_BYTES);
+                const uint32_t b_base = tc::smem_u32(sB + stage * B_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
+                    const uint64_t db = tc::make_desc_sw128(b_base + k * 32);
+                    tc::mma_f16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                }
+                tc::mma_commit(&empty[stage]);
+            }
+            tc::mma_commit(&tmem_full[acc]);
         }
-        tc::mma_commit(tmem_full);
     } else if (warp >= 2) {
-        // ------------------------------------------------------------ epilogue
-        tc::mbar_wait(tmem_full, 0);
-        tc::fence_after_sync();
-        const int q = warp & 3;             // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------ epilogue (8 warps)
+        // warp w reads TMEM lanes [32*(w%4), +32) (hardware restriction) and the column half (w-2)/4 of the tile.
+        const int q = warp & 3;
+        const int half_id = (warp - 2) >> 2;
         const int row = q * 32 + lane;      // row of the 128-row tile == TMEM lane
-        // output row address
-        bool row_ok;
-        long out_off, res_off;
-        int img = 0;
-        if (!p.conv) {
-            const int m = m_blk * BM + row;
-            row_ok = m < p.M;
-            out_off = static_cast<long>(b2) * p.so2 + static_cast<long>(b1) * p.so1 + static_cast<long>(m) * p.ldo;
-            res_off = static_cast<long>(b2) * p.sr2 + static_cast<long>(b1) * p.sr1 + static_cast<long>(m) * p.ldr;
-        } else {
-            const int xi = row % p.bw, yi = (row / p.bw) % p.bh, bi = row / (p.bw * p.bh);
-            const int x = tx * p.bw + xi, y = ty * p.bh + yi;
-            img = tb * p.bb + bi;
-            row_ok = (x < p.Wo) && (y < p.Ho) && (img < p.Bn);
-            out_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldo;
-            res_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldr;
-        }
-        const int m_glob = m_blk * BM + row;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-            tc::tmem_wait_ld();
-            const int n0 = n_blk * BN + c0;
-            if (!row_ok || n0 >= p.N) continue;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float acc = __uint_as_float(v[i]) * p.alpha;
-                const int n = n0 + i;
-                if (n < p.N) {
-                    if (p.bias_mode == 1) acc += __half2float(p.bias[n]);
-                    else if (p.bias_mode == 2) acc += __half2float(p.bias[m_glob]);
-                    if (p.bias2) acc += __half2float(p.bias2[static_cast<long>(img) * p.bias2_pitch + n]);
-                    acc = apply_act(acc, p.act);
-                    if (p.residual) acc += __half2float(p.residual[res_off + n]);
-                }
-                f[i] = acc;
-            }
-            if (p.out_f32) {
-                for (int i = 0; i < 32; ++i)
-                    if (n0 + i < p.N) p.out_f32[out_off + n0 + i] = f[i];
-            } else if (n0 + 32 <= p.N && ((out_off + n0) & 7) == 0) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out + out_off + n0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
-                    __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
-                    __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
-                    __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                    dst[i] = pk;
-                }
+        constexpr int COLS_PER_WARP = BN / 2;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
+            const int m_blk = mn / p.tiles_n, n_blk = mn - m_blk * p.tiles_n;
+            const int b1 = z % p.batch1, b2 = z / p.batch1;
+            bool row_ok;
+            long out_off, res_off;
+            int img = 0;
+            if (!p.conv) {
+                const int m = m_blk * BM + row;
+                row_ok = m < p.M;
+                out_off = static_cast<long>(b2) * p.so2 + static_cast<long>(b1) * p.so1 + static_cast<long>(m) * p.ldo;
+                res_off = static_cast<long>(b2) * p.sr2 + static_cast<long>(b1) * p.sr1 + static_cast<long>(m) * p.ldr;
             } else {
-                for (int i = 0; i < 32; ++i)
-                    if (n0 + i < p.N) p.out[out_off + n0 + i] = __float2half_rn(f[i]);
+                const int tx = m_blk % p.tiles_x, ty = (m_blk / p.tiles_x) % p.tiles_y, tb = m_blk / (p.tiles_x * p.tiles_y);
+                const int xi = row % p.bw, yi = (row / p.bw) % p.bh, bi = row / (p.bw * p.bh);
+                const int x = tx * p.bw + xi, y = ty * p.bh + yi;
+                img = tb * p.bb + bi;
+                row_ok = (x < p.Wo) && (y < p.Ho) && (img < p.Bn);
+                out_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldo;
+                res_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldr;
             }
+            const int m_glob = m_blk * BM + row;
+            const float bias_row = (p.bias_mode == 2 && row_ok) ? __half2float(p.bias[m_glob]) : 0.f;
+            tc::mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c0 = half_id * COLS_PER_WARP; c0 < (half_id + 1) * COLS_PER_WARP; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+                tc::tmem_wait_ld();
+                const int n0 = n_blk * BN + c0;
+                if (!row_ok || n0 >= p.N) continue;
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha + bias_row;
+                const bool full = n0 + 32 <= p.N;
+                // per-column bias and per-image bias: 16-byte loads when the 32-column run is complete and aligned
+                if (p.bias_mode == 1) {
+                    if (full && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0)) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 bv = bp[j];
+                            const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 t = __half22float2(bh[e]);
+                                f[8 * j + 2 * e] += t.x;
+                                f[8 * j + 2 * e + 1] += t.y;
+                            }
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < p.N) f[i] += __half2float(p.bias[n0 + i]);
+                    }
+                }
+                if (p.bias2) {
+                    const __half* b2p = p.bias2 + static_cast<long>(img) * p.bias2_pitch + n0;
+                    if (full && ((reinterpret_cast<uintptr_t>(b2p) & 15) == 0)) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(b2p);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 bv = bp[j];
+                            const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 t = __half22float2(bh[e]);
+                                f[8 * j + 2 * e] += t.x;
+                                f[8 * j + 2 * e + 1] += t.y;
+                            }
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < p.N) f[i] += __half2float(b2p[i]);
+                    }
+                }
+                if (p.act) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], p.act);
+                }
+                if (p.residual) {
+                    const __half* rp = p.residual + res_off + n0;
+                    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(rp);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 rv = r4[j];
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 t = __half22float2(rh[e]);
+                                f[8 * j + 2 * e] += t.x;
+                                f[8 * j + 2 * e + 1] += t.y;
+                            }
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < p.N) f[i] += __half2float(rp[i]);
+                    }
+                }
+                if (p.out_f32) {
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + i < p.N) p.out_f32[out_off + n0 + i] = f[i];
+                } else if (full && ((reinterpret_cast<uintptr_t>(p.out + out_off + n0) & 15) == 0)) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + out_off + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
+                        __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
+                        __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
+                        __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        dst[i] = pk;
+                    }
+                } else {
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + i < p.N) p.out[out_off + n0 + i] = __float2half_rn(f[i]);
+                }
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(&tmem_empty[acc]);   // 256 epilogue threads: the accumulator may be overwritten
         }
-        tc::fence_before_sync();
     }
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+        tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }
 }
 
@@ -286,8 +378,16 @@ std::mutex g_prof_mu;
 
 template <int BN, int STAGES>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
-           cudaStream_t st) {
+           cudaStream_t st) {   // `grid` arrives as (tiles_n, tiles_m, batch) and is flattened to a persistent 1-D grid
     const size_t smem = static_cast<size_t>(STAGES) * (A_TILE_BYTES + BN * BK * 2) + 1024;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        RF_CUDA_TRY(cudaGetDevice(&dev));
+        RF_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int n_tiles = static_cast<int>(grid.x * grid.y * grid.z);
+    grid = dim3(static_cast<unsigned>(n_tiles < num_sms ? n_tiles : num_sms));
     static std::once_flag once;
     static cudaError_t aerr = cudaSuccess;
     std::call_once(once, [&] {
@@ -301,7 +401,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         RF_CUDA_TRY(cudaEventCreate(&e1));
         RF_CUDA_TRY(cudaEventRecord(e0, st));
     }
-    k_tc_gemm<BN, STAGES><<<grid, 192, smem, st>>>(a0, a1, b, p);
+    k_tc_gemm<BN, STAGES><<<grid, 320, smem, st>>>(a0, a1, b, p);
     RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
     if (prof) {
         RF_CUDA_TRY(cudaEventRecord(e1, st));
@@ -318,16 +418,16 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
 
 int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, int tiles_m,
              int nbatch, cudaStream_t st) {
-    // Shallow per-CTA rings (2-3 stages, <= 72 KB) so that three CTAs are co-resident per SM: their TMA latency,
-    // MMA main loops and epilogues overlap each other (3 x 128 TMEM columns, 3 x 192 x 96 registers fit).
+    // one persistent CTA per SM: 6-stage (BN=128, 192 KB) / 8-stage (BN=64, 192 KB) TMA ring, 2 TMEM accumulators
+    p.tiles_m = tiles_m;
     if (N > 64) {
-        dim3 grid((N + 127) / 128, tiles_m, nbatch);
-        if (p.num_kb == 1) return launch<128, 1>(a0, a1, b, p, grid, st);
-        return launch<128, 2>(a0, a1, b, p, grid, st);
+        p.tiles_n = (N + 127) / 128;
+        dim3 grid(p.tiles_n, tiles_m, nbatch);
+        return launch<128, 6>(a0, a1, b, p, grid, st);
     }
-    dim3 grid((N + 63) / 64, tiles_m, nbatch);
-    if (p.num_kb == 1) return launch<64, 1>(a0, a1, b, p, grid, st);
-    return launch<64, 3>(a0, a1, b, p, grid, st);
+    p.tiles_n = (N + 63) / 64;
+    dim3 grid(p.tiles_n, tiles_m, nbatch);
+    return launch<64, 8>(a0, a1, b, p, grid, st);
 }
 
 }  // namespace
