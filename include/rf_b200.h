@@ -76,10 +76,15 @@ const char* rf_version(void);
 int rf_plan_create(const rf_plan_desc* desc, const float* window, const float* fb, rf_plan** out);
 void rf_plan_destroy(rf_plan* plan);
 int rf_plan_get_info(const rf_plan* plan, rf_plan_info* info);
+/* Griffin-Lim runs its inner loop on every second waveform sample when the live band allows it (2*k_hi + 800 <=
+ * n_fft/2: aliasing below fp32 rounding; the final reconstruction is always full rate).  enable = 0 forces the
+ * full-rate loop.  Returns 1 if the decimated loop will be used, 0 otherwise (not an error code). */
+int rf_plan_set_decimation(rf_plan* plan, int enable);
 /* Copy a named host table (for tests): "bins" int32[n_live], "pp" uint32[n_live],
  * "wt_fwd"/"wt_inv" float[4][win][2], "window" float[win], "fb" float[n_freq][n_mels],
  * "pinv" float[n_freq][n_mels] (= min-norm inverse-mel operator, dense),
- * "tri" double[3][n_mels] (Gram tridiagonal: sub, diag, super). Returns RF_ERR_INVALID if
+ * "tri" double[3][n_mels] (Gram tridiagonal: sub, diag, super), and for the decimated loop "pp2" uint32[n_live],
+ * "wt2_fwd"/"wt2_inv" float[2][4][win/2][2]. Returns RF_ERR_INVALID if
  * `bytes` does not match the table size. */
 int rf_plan_table(const rf_plan* plan, const char* name, void* dst, size_t bytes);
 

@@ -46,6 +46,11 @@ struct rf_plan {
     int32_t* d_binrow_m = nullptr;
     float* d_binrow_w = nullptr;
     double* d_thomas = nullptr;  // [3][n_mels]: sub, cprime, inv_den
+    rf_c32* d_wt2_fwd = nullptr;  // decimated-loop tables (null when not eligible)
+    rf_c32* d_wt2_inv = nullptr;
+    uint32_t* d_pp2 = nullptr;
+    rf_c32* d_ph_odd = nullptr;
+    bool use_decimation = true;
     std::vector<void*> owned;
 };
 
@@ -95,6 +100,12 @@ static int rf_plan_upload(rf_plan* p) {
         th[2 * h.n_mels + i] = h.thomas[h.n_mels + i];  // inv_den
     }
     RF_CUDA_TRY(upload(p, &p->d_thomas, th.data(), th.size()));
+    if (h.decimate) {
+        RF_CUDA_TRY(upload(p, &p->d_wt2_fwd, h.wt2_fwd.data(), h.wt2_fwd.size() / 2));
+        RF_CUDA_TRY(upload(p, &p->d_wt2_inv, h.wt2_inv.data(), h.wt2_inv.size() / 2));
+        RF_CUDA_TRY(upload(p, &p->d_pp2, h.pp2.data(), h.pp2.size()));
+        RF_CUDA_TRY(upload(p, &p->d_ph_odd, h.ph_odd.data(), h.ph_odd.size() / 2));
+    }
     p->device = dev;
     p->uploaded = true;
     return RF_OK;
@@ -132,6 +143,12 @@ extern "C" int rf_plan_get_info(const rf_plan* p, rf_plan_info* info) {
     return RF_OK;
 }
 
+extern "C" int rf_plan_set_decimation(rf_plan* p, int enable) {
+    if (!p) return rf_fail(RF_ERR_INVALID, "rf_plan_set_decimation: null plan");
+    p->use_decimation = enable != 0;
+    return (p->h.decimate && p->use_decimation) ? 1 : 0;
+}
+
 extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size_t bytes) {
     if (!p || !name || !dst) return rf_fail(RF_ERR_INVALID, "rf_plan_table: null argument");
     const rf_plan_host& h = p->h;
@@ -146,6 +163,9 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
     else if (s == "window") { src = h.window.data(); n = h.window.size() * 4; }
     else if (s == "fb") { src = h.fb.data(); n = h.fb.size() * 4; }
     else if (s == "tri") { src = h.tri.data(); n = h.tri.size() * 8; }
+    else if (s == "pp2") { src = h.pp2.data(); n = h.pp2.size() * 4; }
+    else if (s == "wt2_fwd") { src = h.wt2_fwd.data(); n = h.wt2_fwd.size() * 4; }
+    else if (s == "wt2_inv") { src = h.wt2_inv.data(); n = h.wt2_inv.size() * 4; }
     else if (s == "pinv") {
         // dense min-norm operator P = fb (fb^T fb)^{-1}, built column by column with the
         // same Thomas factors the kernel uses (fp64), for tests
@@ -186,16 +206,17 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
 // ---------------------------------------------------------------------------------------
 
 // ---- iSTFT of one overlap-add chunk (G frames) of one clip, one r-group ------------------
-// grid (nchunks*2, B). Output: part[b][g][chunk][PL] partial overlap-add sums.
-__global__ void __launch_bounds__(RF_NT, 2)
-k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __restrict__ cur,
-              const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL,
-              int nchunks, float* __restrict__ part) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// Output: dst[PL] partial overlap-add sums of the chunk (NA = 10 full rate, NA = 5 odd samples only).
+template <int NA>
+__device__ __forceinline__ void istft_chunk_body(unsigned char* smem_raw, const rf_gl_tables& tb,
+                                                 const float* __restrict__ S, const rf_c32* __restrict__ cur,
+                                                 const rf_c32* __restrict__ prev, int mode, float momentum, int T,
+                                                 int G, int PL, int pair_stride, int b, int g, int chunk,
+                                                 float* __restrict__ dst) {
+    constexpr int W = rf_geom<NA>::W;
     rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
-    float* ola = reinterpret_cast<float*>(smem_raw + 2 * RF_PW * sizeof(rf_c32));
+    float* ola = reinterpret_cast<float*>(smem_raw + 2 * W * sizeof(rf_c32));
     const int tid = threadIdx.x;
-    const int g = blockIdx.x & 1, chunk = blockIdx.x >> 1, b = blockIdx.y;
     const int f0 = chunk * G;
     const int nf = min(G, T - f0);
     const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
@@ -204,7 +225,7 @@ k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __rest
     for (int pr = 0; 2 * pr < nf; ++pr) {
         const int t0 = f0 + 2 * pr;
         const bool has1 = (2 * pr + 1) < nf;
-        rf_istft_zero(tid, RF_NT, V);
+        rf_istft_zero<NA>(tid, RF_NT, V);
         __syncthreads();
         rf_istft_in in;
         const size_t o0 = (static_cast<size_t>(b) * T + t0) * row;
@@ -216,17 +237,48 @@ k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __rest
         in.prev1 = prev ? prev + o0 + row : nullptr;
         in.mode = mode;
         in.momentum = momentum;
-        rf_istft_load(tid, RF_NT, V, tb, j0, j1, in);
+        rf_istft_load<NA>(tid, RF_NT, V, tb, j0, j1, in);
         __syncthreads();
-        rf_pass_c<true>(tid, RF_NT, V);
+        rf_pass_c<true, NA>(tid, RF_NT, V);
         __syncthreads();
-        rf_pass_a<true>(tid, RF_NT, V);
+        rf_pass_a<true, NA>(tid, RF_NT, V);
         __syncthreads();
-        rf_istft_pass_b(tid, RF_NT, V, ola + 2 * pr * tb.hop, tb, g, has1, 2);
+        rf_istft_pass_b<NA>(tid, RF_NT, V, ola + pr * pair_stride, tb, g, has1, 2);
         __syncthreads();
     }
-    float* dst = part + ((static_cast<size_t>(b) * 2 + g) * nchunks + chunk) * PL;
     for (int i = tid; i < PL; i += RF_NT) dst[i] = ola[i];
+}
+
+// full rate: grid (nchunks*2, B), part[b][g][chunk][PL]
+__global__ void __launch_bounds__(RF_NT, 2)
+k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __restrict__ cur,
+              const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL, int nchunks,
+              float* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x & 1, chunk = blockIdx.x >> 1, b = blockIdx.y;
+    istft_chunk_body<10>(smem_raw, tb, S, cur, prev, mode, momentum, T, G, PL, 2 * tb.off1, b, g, chunk,
+                         part + ((static_cast<size_t>(b) * 2 + g) * nchunks + chunk) * PL);
+}
+
+// hybrid decimated loop (rf_gl_dec_geom): grid ((nslots + nchunks)*2, B).  The first nslots*2 CTAs redo the chunks
+// that overlap the edge strips at full rate (heaviest CTAs first), the rest produce half-rate partial sums of every
+// chunk.  part_e[b][g][slot][PL], part_h[b][g][chunk][PLh]
+__global__ void __launch_bounds__(RF_NT, 2)
+k_istft_dec(rf_gl_tables tb, rf_gl_tables tb2, const float* __restrict__ S, const rf_c32* __restrict__ cur,
+            const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL, int PLh, int nchunks,
+            int c_tail, int nslots, float* __restrict__ part_e, float* __restrict__ part_h) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x & 1, b = blockIdx.y;
+    int idx = blockIdx.x >> 1;
+    if (idx < nslots) {
+        const int chunk = idx == 0 ? 0 : c_tail + idx - 1;
+        istft_chunk_body<10>(smem_raw, tb, S, cur, prev, mode, momentum, T, G, PL, 2 * tb.off1, b, g, chunk,
+                             part_e + ((static_cast<size_t>(b) * 2 + g) * nslots + idx) * PL);
+    } else {
+        idx -= nslots;
+        istft_chunk_body<5>(smem_raw, tb2, S, cur, prev, mode, momentum, T, G, PLh, 2 * tb2.off1 - 1, b, g, idx,
+                            part_h + ((static_cast<size_t>(b) * 2 + g) * nchunks + idx) * PLh);
+    }
 }
 
 // ---- overlap-add assembly: x[b][i] = sum(parts) / envelope, kept region only --------------
@@ -246,28 +298,76 @@ __global__ void k_ola_assemble(const float* __restrict__ part, const float* __re
         rf_ola_sample(i, part + static_cast<size_t>(b) * 2 * nchunks * PL, env[i], T, G, PL, nchunks, H, W);
 }
 
+// decimated assembly: xd[b] = [ xo (nxo odd samples 2v+1) | head strip x[0..E) | tail strip x[L-E..L) ]
+__global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float* __restrict__ part_e,
+                                   const float* __restrict__ env, int T, int G, int PL, int PLh, int nchunks,
+                                   int c_tail, int nslots, int H, int W, int L, int nxo, int E,
+                                   float* __restrict__ xd) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (v >= nxo + 2 * E) return;
+    float* dst = xd + static_cast<size_t>(b) * (nxo + 2 * E);
+    if (v < nxo) {
+        dst[v] = rf_ola_sample_d2(v, part_h + static_cast<size_t>(b) * 2 * nchunks * PLh, env[2 * v + 1], G, PLh,
+                                  nchunks, H, W);
+    } else {
+        const int e = v - nxo;
+        const int i = e < E ? e : L - 2 * E + e;
+        dst[v] = rf_ola_sample_edge(i, part_e + static_cast<size_t>(b) * 2 * nslots * PL, env[i], T, G, PL, c_tail,
+                                    nslots, H, W);
+    }
+}
+
 // ---- STFT of one frame pair, one r-group ------------------------------------------------
-// grid (npairs*2, B). x: [B][L] un-padded signal (reflect padding applied on the fly).
-__global__ void __launch_bounds__(RF_NT, 2)
-k_stft_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, rf_c32* __restrict__ R) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// x_full: waveform holding samples [base, ...) (reflect padding applied on the fly); NA = 5: xo odd samples
+template <int NA>
+__device__ __forceinline__ void stft_pair_body(unsigned char* smem_raw, const rf_gl_tables& tb,
+                                               const float* __restrict__ x, int base, int L, int T, int hop, int b,
+                                               int g, int pr, rf_c32* __restrict__ R) {
+    constexpr int W = rf_geom<NA>::W;
     rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
-    float* xs = reinterpret_cast<float*>(smem_raw + 2 * RF_PW * sizeof(rf_c32));
+    float* xs = reinterpret_cast<float*>(smem_raw + 2 * W * sizeof(rf_c32));
     const int tid = threadIdx.x;
-    const int g = blockIdx.x & 1, pr = blockIdx.x >> 1, b = blockIdx.y;
     const int t0 = 2 * pr;
     const bool has1 = t0 + 1 < T;
-    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop);
+    if (NA == 10) rf_stage_x(tid, RF_NT, xs, x, L, t0, hop, base);
+    else rf_stage_x_d2(tid, RF_NT, xs, x, L, t0, hop);
     __syncthreads();
-    rf_stft_pass_b(tid, RF_NT, V, xs, tb, g, has1);
+    rf_stft_pass_b<NA>(tid, RF_NT, V, xs, tb, g, has1);
     __syncthreads();
-    rf_pass_a<false>(tid, RF_NT, V);
+    rf_pass_a<false, NA>(tid, RF_NT, V);
     __syncthreads();
-    rf_pass_c<false>(tid, RF_NT, V);
+    rf_pass_c<false, NA>(tid, RF_NT, V);
     __syncthreads();
     const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
     rf_c32* out0 = R + (static_cast<size_t>(b) * T + t0) * tb.n_live;
-    rf_stft_post(tid, RF_NT, V, tb, j0, j1, out0, has1 ? out0 + tb.n_live : nullptr);
+    rf_stft_post<NA>(tid, RF_NT, V, tb, j0, j1, out0, has1 ? out0 + tb.n_live : nullptr);
+}
+
+// full rate: grid (npairs*2, B). x: [B][L] un-padded signal
+__global__ void __launch_bounds__(RF_NT, 2)
+k_stft_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int hop, rf_c32* __restrict__ R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x & 1, pr = blockIdx.x >> 1, b = blockIdx.y;
+    stft_pair_body<10>(smem_raw, tb, x + static_cast<size_t>(b) * L, 0, L, T, hop, b, g, pr, R);
+}
+
+// hybrid decimated loop: grid (npairs*2, B); the first n_edge_pairs*2 CTAs are the edge pairs (3 head pairs, then
+// the pairs from pr_tail on) at full rate from the strips of xd, the rest read xo at half rate
+__global__ void __launch_bounds__(RF_NT, 2)
+k_stft_dec(rf_gl_tables tb, rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E,
+           int pr_tail, int n_edge_pairs, rf_c32* __restrict__ R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x & 1, b = blockIdx.y;
+    const int idx = blockIdx.x >> 1;
+    const float* xb = xd + static_cast<size_t>(b) * (nxo + 2 * E);
+    if (idx < 3) {
+        stft_pair_body<10>(smem_raw, tb, xb + nxo, 0, L, T, hop, b, g, idx, R);
+    } else if (idx < n_edge_pairs) {
+        stft_pair_body<10>(smem_raw, tb, xb + nxo + E, L - E, L, T, hop, b, g, pr_tail + idx - 3, R);
+    } else {
+        stft_pair_body<5>(smem_raw, tb2, xb, 0, L, T, hop, b, g, 3 + idx - n_edge_pairs, R);
+    }
 }
 
 // ---- STFT + |.| + mel of one frame pair (both groups in one CTA) -------------------------
@@ -278,23 +378,23 @@ k_stft_mel_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
     float* xs = reinterpret_cast<float*>(smem_raw + 2 * RF_PW * sizeof(rf_c32));
-    rf_c32* spec0 = reinterpret_cast<rf_c32*>(xs + RF_PW + tb.hop + ((RF_PW + tb.hop) & 1));
+    rf_c32* spec0 = reinterpret_cast<rf_c32*>(xs + RF_PW + tb.off1 + ((RF_PW + tb.off1) & 1));
     rf_c32* spec1 = spec0 + tb.n_live;
     const int tid = threadIdx.x;
     const int pr = blockIdx.x, b = blockIdx.y;
     const int t0 = 2 * pr;
     const bool has1 = t0 + 1 < T;
-    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.hop);
+    rf_stage_x(tid, RF_NT, xs, x + static_cast<size_t>(b) * L, L, t0, tb.off1);
     __syncthreads();
     for (int g = 0; g < 2; ++g) {
-        rf_stft_pass_b(tid, RF_NT, V, xs, tb, g, has1);
+        rf_stft_pass_b<10>(tid, RF_NT, V, xs, tb, g, has1);
         __syncthreads();
-        rf_pass_a<false>(tid, RF_NT, V);
+        rf_pass_a<false, 10>(tid, RF_NT, V);
         __syncthreads();
-        rf_pass_c<false>(tid, RF_NT, V);
+        rf_pass_c<false, 10>(tid, RF_NT, V);
         __syncthreads();
         const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
-        rf_stft_post(tid, RF_NT, V, tb, j0, j1, spec0, spec1);
+        rf_stft_post<10>(tid, RF_NT, V, tb, j0, j1, spec0, spec1);
         __syncthreads();
     }
     // magnitude in place (spec.x = |X|), torch.abs on complex64
@@ -497,14 +597,23 @@ __global__ void k_wave_to_int16(const float* __restrict__ w, int C, int L, const
 // ---------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------
-static rf_gl_tables make_tables(const rf_plan* p) {
+static rf_gl_tables make_tables(const rf_plan* p, int NA = 10) {
     rf_gl_tables tb;
-    tb.wt_fwd = p->d_wt_fwd;
-    tb.wt_inv = p->d_wt_inv;
-    tb.pp = p->d_pp;
+    if (NA == 10) {
+        tb.wt_fwd = p->d_wt_fwd;
+        tb.wt_inv = p->d_wt_inv;
+        tb.pp = p->d_pp;
+        tb.ph_odd = nullptr;
+        tb.off1 = p->h.H;
+    } else {
+        tb.wt_fwd = p->d_wt2_fwd;
+        tb.wt_inv = p->d_wt2_inv;
+        tb.pp = p->d_pp2;
+        tb.ph_odd = p->d_ph_odd;
+        tb.off1 = (p->h.H + 1) / 2;
+    }
     tb.n_live = p->h.n_live;
     tb.n_even = p->h.n_even;
-    tb.hop = p->h.H;
     return tb;
 }
 
@@ -515,6 +624,8 @@ struct gl_ws {
     rf_c32* R[2];
     float* part;
     float* env;
+    float* part_e;  // decimated loop: full-rate partial sums of the edge chunks [B][2][nslots][PL]
+    float* xd;      // decimated loop: [B][nxo + 2E] odd samples + the two full-rate edge strips
     size_t total;
     int nchunks, PL;
 };
@@ -536,6 +647,14 @@ static gl_ws gl_layout(const rf_plan* p, int B, int T, void* base) {
     off += align256(static_cast<size_t>(B) * 2 * w.nchunks * w.PL * 4);
     w.env = reinterpret_cast<float*>(b + off);
     off += align256(static_cast<size_t>(p->h.H) * (T > 0 ? T - 1 : 0) * 4);
+    w.part_e = w.xd = nullptr;
+    if (p->h.decimate && rf_dec_ok(T, RF_CHUNK)) {
+        const rf_gl_dec_geom d = rf_dec_geom(T, RF_CHUNK, p->h.H, p->h.W);
+        w.part_e = reinterpret_cast<float*>(b + off);
+        off += align256(static_cast<size_t>(B) * 2 * d.nslots * w.PL * 4);
+        w.xd = reinterpret_cast<float*>(b + off);
+        off += align256(static_cast<size_t>(B) * (d.nxo + 2 * d.E) * 4);
+    }
     w.total = off;
     return w;
 }
@@ -561,7 +680,11 @@ static int set_smem_attrs() {
     std::call_once(once, [] {
         err = cudaFuncSetAttribute(k_istft_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(k_istft_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err == cudaSuccess)
             err = cudaFuncSetAttribute(k_stft_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(k_stft_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (err == cudaSuccess)
             err = cudaFuncSetAttribute(k_stft_mel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (err == cudaSuccess)
@@ -598,13 +721,18 @@ struct gl_prof {
 static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float momentum_in, float* d_wave,
                    cudaStream_t st, gl_prof* prof = nullptr) {
     const rf_plan_host& h = p->h;
-    const rf_gl_tables tb = make_tables(p);
+    const rf_gl_tables tb = make_tables(p, 10);
     const int L = h.H * (T - 1);
     // momentum = momentum / (1 + momentum)  (TA/functional/functional.py:300), fp32 like python float->tensor op
     const float m = static_cast<float>(static_cast<double>(momentum_in) / (1.0 + static_cast<double>(momentum_in)));
+    const bool dec = h.decimate && p->use_decimation && p->d_pp2 != nullptr && w.xd != nullptr;
+    const rf_gl_tables tb2 = dec ? make_tables(p, 5) : tb;
+    const rf_gl_dec_geom dg = rf_dec_geom(T, RF_CHUNK, h.H, h.W);
+    const int PLh = ((RF_CHUNK - 1) * h.H + h.W + 1) / 2;
     const size_t smem_i = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(w.PL) * 4;
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
     const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
+    const dim3 grid_i2((w.nchunks + dg.nslots) * 2, B), grid_a2((dg.nxo + 2 * dg.E + 255) / 256, B);
     k_envelope<<<(L + 255) / 256, 256, 0, st>>>(p->d_win2, T, h.H, h.W, L, w.env);
     RF_CUDA_LAUNCH_CHECK("k_envelope");
     for (int it = 0; it <= n_iter; ++it) {
@@ -619,21 +747,34 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
             mode = 1;
             if (it >= 2 && m != 0.f) prev = w.R[it & 1];
         }
+        const bool last = it == n_iter;
+        const bool half = dec && !last;   // the final reconstruction is always full rate
         if (prof) RF_CUDA_TRY(prof->mark(0, 0, st));
-        k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
-                                                     w.part);
+        if (half)
+            k_istft_dec<<<grid_i2, RF_NT, smem_i, st>>>(tb, tb2, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, PLh,
+                                                        w.nchunks, dg.c_tail, dg.nslots, w.part_e, w.part);
+        else
+            k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
+                                                         w.part);
         RF_CUDA_LAUNCH_CHECK("k_istft_chunk");
         if (prof) {
             RF_CUDA_TRY(prof->mark(0, 1, st));
             RF_CUDA_TRY(prof->mark(1, 0, st));
         }
-        k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, w.env, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L,
-                                               d_wave);
+        if (half)
+            k_ola_assemble_dec<<<grid_a2, 256, 0, st>>>(w.part, w.part_e, w.env, T, RF_CHUNK, w.PL, PLh, w.nchunks,
+                                                        dg.c_tail, dg.nslots, h.H, h.W, L, dg.nxo, dg.E, w.xd);
+        else
+            k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, w.env, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L, d_wave);
         RF_CUDA_LAUNCH_CHECK("k_ola_assemble");
         if (prof) RF_CUDA_TRY(prof->mark(1, 1, st));
-        if (it == n_iter) break;
+        if (last) break;
         if (prof) RF_CUDA_TRY(prof->mark(2, 0, st));
-        k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, w.R[it & 1]);
+        if (dec)
+            k_stft_dec<<<grid_f, RF_NT, smem_f, st>>>(tb, tb2, w.xd, L, T, h.H, dg.nxo, dg.E, dg.pr_tail,
+                                                      dg.n_edge_pairs, w.R[it & 1]);
+        else
+            k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, h.H, w.R[it & 1]);
         RF_CUDA_LAUNCH_CHECK("k_stft_pair");
         if (prof) RF_CUDA_TRY(prof->mark(2, 1, st));
     }
@@ -786,7 +927,7 @@ extern "C" int rf_stft(rf_plan* p, const float* d_wave, int B, int L, void* d_sp
     RF_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), n * 8, st));
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
     dim3 grid_f(((T + 1) / 2) * 2, B);
-    k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(make_tables(p), d_wave, L, T, tmp);
+    k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(make_tables(p), d_wave, L, T, h.H, tmp);
     RF_CUDA_LAUNCH_CHECK("k_stft_pair");
     RF_CUDA_TRY(cudaMemsetAsync(d_spec, 0, static_cast<size_t>(B) * h.F * T * 8, st));
     dim3 grid((h.n_live + 31) / 32, (T + 31) / 32, B), blk(32, 32);

@@ -206,6 +206,47 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
                     p.wt_inv[o + 1] = static_cast<float>(-w * std::sin(ang) / p.N);
                 }
 
+    // ---- time-decimated loop tables.  Eligible when every live bin k satisfies 2k + 800 <= N/2: the spectrum of a
+    // windowed frame at distance >= 800 bins from its content is < 4e-8 of the peak (Hann side lobes fall with the
+    // cube of the offset), below fp32 rounding, so sampling the loop signal at every second sample aliases nothing
+    // measurable.  Needs an odd hop (frame parities alternate) and an even chunk size.
+    p.decimate = (p.H % 2 == 1) && (RF_CHUNK % 2 == 0) && (2 * p.k_hi + 800 <= p.N / 2) && (p.W == 4410);
+    if (p.decimate) {
+        const int W2 = 2205, N2 = p.N / 2;
+        p.pp2.resize(p.n_live);
+        p.ph_odd.resize(static_cast<size_t>(p.n_live) * 2);
+        for (int j = 0; j < p.n_live; ++j) {
+            const int k = p.bins[j];
+            const int m = k >> 2;
+            const uint32_t idx = rf_pfa_pos(m % 5, m % RF_NB, m % RF_NC);
+            const int kp = (N2 - k) % N2;
+            const int mp = kp >> 2;
+            const uint32_t idx2 = rf_pfa_pos(mp % 5, mp % RF_NB, mp % RF_NC);
+            p.pp2[j] = static_cast<uint32_t>(k & 3) | (idx << 2) | (idx2 << 15) | (static_cast<uint32_t>(k & 7) << 28);
+            const double ang = -2.0 * M_PI * static_cast<double>(k) / p.N;
+            p.ph_odd[2 * j] = static_cast<float>(std::cos(ang));
+            p.ph_odd[2 * j + 1] = static_cast<float>(std::sin(ang));
+        }
+        p.wt2_fwd.assign(static_cast<size_t>(2) * 4 * W2 * 2, 0.f);
+        p.wt2_inv.assign(static_cast<size_t>(2) * 4 * W2 * 2, 0.f);
+        for (int par = 0; par < 2; ++par)
+            for (int r = 0; r < 4; ++r)
+                for (int a = 0; a < 5; ++a)
+                    for (int b = 0; b < RF_NB; ++b)
+                        for (int c = 0; c < RF_NC; ++c) {
+                            const int u = rf_pfa2_u_of(a, b, c);
+                            const int pos = b * 245 + c * 5 + a;
+                            const long q = (static_cast<long>(r) * u) % N2;
+                            const double ang = -2.0 * M_PI * static_cast<double>(q) / N2;
+                            const double w = p.window[2 * u + par];
+                            const size_t o = ((static_cast<size_t>(par) * 4 + r) * W2 + pos) * 2;
+                            p.wt2_fwd[o] = static_cast<float>(2.0 * w * std::cos(ang));
+                            p.wt2_fwd[o + 1] = static_cast<float>(2.0 * w * std::sin(ang));
+                            p.wt2_inv[o] = static_cast<float>(w * std::cos(ang) / p.N);
+                            p.wt2_inv[o + 1] = static_cast<float>(-w * std::sin(ang) / p.N);
+                        }
+    }
+
     // ---- sparse filterbank
     p.melcol_ptr.assign(p.n_mels + 1, 0);
     p.binrow_ptr.assign(p.n_live + 1, 0);

@@ -25,6 +25,12 @@ struct rf_plan_host {
     std::vector<uint32_t> pp;     // [n_live] r | idx<<2 | idx2<<15 | (k&7)<<28
     std::vector<float> wt_fwd;    // [4][9][49][10][2]  w[n'] * exp(-2 pi i r n'/N), n' = n_of(a,b,c)
     std::vector<float> wt_inv;    // same layout, w[n']/N * exp(+2 pi i r n'/N)
+    // time-decimated Griffin-Lim loop (NA = 5, 2205-point sub-transforms on every second sample); empty if not eligible
+    bool decimate = false;
+    std::vector<uint32_t> pp2;    // [n_live] like pp with positions on the 5 x 9 x 49 grid and partner 8820 - k
+    std::vector<float> wt2_fwd;   // [2 parities][4][9][49][5][2]  2 * w[2u+par] * exp(-2 pi i r u/8820)
+    std::vector<float> wt2_inv;   // same layout,                  w[2u+par]/N * exp(+2 pi i r u/8820)
+    std::vector<float> ph_odd;    // [n_live][2]  exp(-2 pi i k/N)
     // mel filterbank in sparse forms over the private bin order
     std::vector<int32_t> melcol_ptr;  // [n_mels+1]  CSR by mel column: entries (j, w)
     std::vector<int32_t> melcol_j;
@@ -46,3 +52,5 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
 inline int rf_pfa_n_of(int a, int b, int c) { return (441 * a + 490 * b + 90 * c) % RF_W; }
 inline int rf_pfa_m_of(int a, int b, int c) { return (441 * a + 3430 * b + 540 * c) % RF_W; }
 inline int rf_pfa_pos(int a, int b, int c) { return a * 441 + b * 49 + c; }
+// decimated grid 5 x 9 x 49 (2205 points): time-side index u and the same position formula
+inline int rf_pfa2_u_of(int a, int b, int c) { return (441 * a + 245 * b + 45 * c) % 2205; }

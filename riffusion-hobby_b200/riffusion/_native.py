@@ -78,6 +78,7 @@ SIGNATURES = {
     "rf_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "rf_plan_destroy": (None, [C.c_void_p]),
     "rf_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
+    "rf_plan_set_decimation": (C.c_int, [C.c_void_p, C.c_int]),
     "rf_plan_table": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "rf_inverse_mel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_griffinlim_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
@@ -200,6 +201,13 @@ class Plan:
     @property
     def handle(self) -> C.c_void_p:
         return self._h
+
+    def set_decimation(self, enable: bool) -> bool:
+        """Griffin-Lim's half-rate inner loop (include/rf_b200.h: rf_plan_set_decimation); returns whether it is on."""
+        r = lib().rf_plan_set_decimation(self._h, int(bool(enable)))
+        if r < 0:
+            check(r)
+        return bool(r)
 
     def table(self, name: str, dtype, shape) -> np.ndarray:
         out = np.empty(shape, dtype=dtype)

@@ -26,82 +26,144 @@ void phase(F f) {
     for (int tid = 0; tid < NT; ++tid) f(tid);
 }
 
-rf_gl_tables tables(const rf_plan_host& h) {
+rf_gl_tables tables(const rf_plan_host& h, int NA) {
     rf_gl_tables tb;
-    tb.wt_fwd = reinterpret_cast<const rf_c32*>(h.wt_fwd.data());
-    tb.wt_inv = reinterpret_cast<const rf_c32*>(h.wt_inv.data());
-    tb.pp = h.pp.data();
+    if (NA == 10) {
+        tb.wt_fwd = reinterpret_cast<const rf_c32*>(h.wt_fwd.data());
+        tb.wt_inv = reinterpret_cast<const rf_c32*>(h.wt_inv.data());
+        tb.pp = h.pp.data();
+        tb.ph_odd = nullptr;
+        tb.off1 = h.H;
+    } else {
+        tb.wt_fwd = reinterpret_cast<const rf_c32*>(h.wt2_fwd.data());
+        tb.wt_inv = reinterpret_cast<const rf_c32*>(h.wt2_inv.data());
+        tb.pp = h.pp2.data();
+        tb.ph_odd = reinterpret_cast<const rf_c32*>(h.ph_odd.data());
+        tb.off1 = (h.H + 1) / 2;
+    }
     tb.n_live = h.n_live;
     tb.n_even = h.n_even;
-    tb.hop = h.H;
     return tb;
 }
 
-// emulates k_stft_pair over the whole grid for one clip
-void emu_stft_clip(const rf_plan_host& h, const float* x, int L, int T, rf_c32* R) {
-    const rf_gl_tables tb = tables(h);
-    std::vector<rf_c32> V(2 * RF_PW);
-    std::vector<float> xs(RF_PW + h.H);
-    for (int pr = 0; 2 * pr < T; ++pr)
+// emulates stft_pair_body<NA> for the frame pairs [pr_lo, pr_hi) of one clip.  NA = 10: x holds waveform samples
+// [base, ...); NA = 5: x is the odd-sample waveform
+template <int NA>
+void emu_stft_pairs(const rf_plan_host& h, const float* x, int base, int L, int T, int pr_lo, int pr_hi, rf_c32* R) {
+    const rf_gl_tables tb = tables(h, NA);
+    constexpr int W = rf_geom<NA>::W;
+    std::vector<rf_c32> V(2 * W);
+    std::vector<float> xs(W + tb.off1);
+    for (int pr = pr_lo; pr < pr_hi; ++pr)
         for (int g = 0; g < 2; ++g) {
             const int t0 = 2 * pr;
             const bool has1 = t0 + 1 < T;
-            phase([&](int tid) { rf_stage_x(tid, NT, xs.data(), x, L, t0, h.H); });
-            phase([&](int tid) { rf_stft_pass_b(tid, NT, V.data(), xs.data(), tb, g, has1); });
-            phase([&](int tid) { rf_pass_a<false>(tid, NT, V.data()); });
-            phase([&](int tid) { rf_pass_c<false>(tid, NT, V.data()); });
+            if (NA == 10) phase([&](int tid) { rf_stage_x(tid, NT, xs.data(), x, L, t0, h.H, base); });
+            else phase([&](int tid) { rf_stage_x_d2(tid, NT, xs.data(), x, L, t0, h.H); });
+            phase([&](int tid) { rf_stft_pass_b<NA>(tid, NT, V.data(), xs.data(), tb, g, has1); });
+            phase([&](int tid) { rf_pass_a<false, NA>(tid, NT, V.data()); });
+            phase([&](int tid) { rf_pass_c<false, NA>(tid, NT, V.data()); });
             const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
             rf_c32* out0 = R + static_cast<size_t>(t0) * tb.n_live;
             phase([&](int tid) {
-                rf_stft_post(tid, NT, V.data(), tb, j0, j1, out0, has1 ? out0 + tb.n_live : nullptr);
+                rf_stft_post<NA>(tid, NT, V.data(), tb, j0, j1, out0, has1 ? out0 + tb.n_live : nullptr);
             });
         }
 }
 
-// emulates k_istft_chunk (+ k_ola_assemble) for one clip
-void emu_istft_clip(const rf_plan_host& h, const float* S, const rf_c32* cur, const rf_c32* prev, int mode,
-                    float momentum, int T, float* x) {
-    const rf_gl_tables tb = tables(h);
+template <int NA>
+void emu_stft_clip(const rf_plan_host& h, const float* x, int L, int T, rf_c32* R) {
+    emu_stft_pairs<NA>(h, x, 0, L, T, 0, (T + 1) / 2, R);
+}
+
+// emulates istft_chunk_body<NA> for one (chunk, group): dst[PL]
+template <int NA>
+void emu_istft_chunk(const rf_plan_host& h, const float* S, const rf_c32* cur, const rf_c32* prev, int mode,
+                     float momentum, int T, int PL, int g, int chunk, float* dst) {
+    const rf_gl_tables tb = tables(h, NA);
+    constexpr int W = rf_geom<NA>::W;
     const int G = RF_CHUNK;
-    const int nchunks = (T + G - 1) / G;
-    const int PL = (G - 1) * h.H + h.W;
-    std::vector<float> part(static_cast<size_t>(2) * nchunks * PL, 0.f);
-    std::vector<rf_c32> V(2 * RF_PW);
-    std::vector<float> ola(PL);
-    for (int chunk = 0; chunk < nchunks; ++chunk)
-        for (int g = 0; g < 2; ++g) {
-            const int f0 = chunk * G;
-            const int nf = std::min(G, T - f0);
-            const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
-            std::fill(ola.begin(), ola.end(), 0.f);
-            for (int pr = 0; 2 * pr < nf; ++pr) {
-                const int t0 = f0 + 2 * pr;
-                const bool has1 = (2 * pr + 1) < nf;
-                phase([&](int tid) { rf_istft_zero(tid, NT, V.data()); });
-                rf_istft_in in;
-                const size_t o0 = static_cast<size_t>(t0) * tb.n_live;
-                in.S0 = S + o0;
-                in.cur0 = cur + o0;
-                in.prev0 = prev ? prev + o0 : nullptr;
-                in.S1 = has1 ? S + o0 + tb.n_live : nullptr;
-                in.cur1 = cur + o0 + tb.n_live;
-                in.prev1 = prev ? prev + o0 + tb.n_live : nullptr;
-                in.mode = mode;
-                in.momentum = momentum;
-                phase([&](int tid) { rf_istft_load(tid, NT, V.data(), tb, j0, j1, in); });
-                phase([&](int tid) { rf_pass_c<true>(tid, NT, V.data()); });
-                phase([&](int tid) { rf_pass_a<true>(tid, NT, V.data()); });
-                // device: one call with which=2 (barrier between the real- and imaginary-part adds)
-                phase([&](int tid) { rf_istft_pass_b(tid, NT, V.data(), ola.data() + 2 * pr * h.H, tb, g, has1, 0); });
-                phase([&](int tid) { rf_istft_pass_b(tid, NT, V.data(), ola.data() + 2 * pr * h.H, tb, g, has1, 1); });
-            }
-            std::memcpy(&part[(static_cast<size_t>(g) * nchunks + chunk) * PL], ola.data(), PL * sizeof(float));
-        }
+    const int pair_stride = NA == 10 ? 2 * tb.off1 : 2 * tb.off1 - 1;
+    std::vector<rf_c32> V(2 * W);
+    std::vector<float> ola(PL, 0.f);
+    const int f0 = chunk * G;
+    const int nf = std::min(G, T - f0);
+    const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
+    for (int pr = 0; 2 * pr < nf; ++pr) {
+        const int t0 = f0 + 2 * pr;
+        const bool has1 = (2 * pr + 1) < nf;
+        phase([&](int tid) { rf_istft_zero<NA>(tid, NT, V.data()); });
+        rf_istft_in in;
+        const size_t o0 = static_cast<size_t>(t0) * tb.n_live;
+        in.S0 = S + o0;
+        in.cur0 = cur + o0;
+        in.prev0 = prev ? prev + o0 : nullptr;
+        in.S1 = has1 ? S + o0 + tb.n_live : nullptr;
+        in.cur1 = cur + o0 + tb.n_live;
+        in.prev1 = prev ? prev + o0 + tb.n_live : nullptr;
+        in.mode = mode;
+        in.momentum = momentum;
+        phase([&](int tid) { rf_istft_load<NA>(tid, NT, V.data(), tb, j0, j1, in); });
+        phase([&](int tid) { rf_pass_c<true, NA>(tid, NT, V.data()); });
+        phase([&](int tid) { rf_pass_a<true, NA>(tid, NT, V.data()); });
+        // device: one call with which=2 (barrier between the real- and imaginary-part adds)
+        float* o = ola.data() + pr * pair_stride;
+        phase([&](int tid) { rf_istft_pass_b<NA>(tid, NT, V.data(), o, tb, g, has1, 0); });
+        phase([&](int tid) { rf_istft_pass_b<NA>(tid, NT, V.data(), o, tb, g, has1, 1); });
+    }
+    std::memcpy(dst, ola.data(), PL * sizeof(float));
+}
+
+std::vector<float> window_sq(const rf_plan_host& h) {
     std::vector<float> win2(h.W);
     for (int i = 0; i < h.W; ++i) win2[i] = h.window[i] * h.window[i];
+    return win2;
+}
+
+// k_istft_chunk + k_ola_assemble (NA = 10 -> x[L]) or the half-rate part of k_istft_dec + k_ola_assemble_dec
+// (NA = 5 -> x[(L-1)/2] odd samples) for one clip
+template <int NA>
+void emu_istft_clip(const rf_plan_host& h, const float* S, const rf_c32* cur, const rf_c32* prev, int mode,
+                    float momentum, int T, float* x) {
+    const int G = RF_CHUNK;
+    const int nchunks = (T + G - 1) / G;
+    const int PL = NA == 10 ? (G - 1) * h.H + h.W : ((G - 1) * h.H + h.W + 1) / 2;
+    std::vector<float> part(static_cast<size_t>(2) * nchunks * PL, 0.f);
+    for (int chunk = 0; chunk < nchunks; ++chunk)
+        for (int g = 0; g < 2; ++g)
+            emu_istft_chunk<NA>(h, S, cur, prev, mode, momentum, T, PL, g, chunk,
+                                &part[(static_cast<size_t>(g) * nchunks + chunk) * PL]);
+    const std::vector<float> win2 = window_sq(h);
     const int L = h.H * (T - 1);
-    for (int i = 0; i < L; ++i)
-        x[i] = rf_ola_sample(i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PL, nchunks, h.H, h.W);
+    if (NA == 10) {
+        for (int i = 0; i < L; ++i)
+            x[i] = rf_ola_sample(i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PL, nchunks, h.H,
+                                 h.W);
+    } else {
+        for (int v = 0; v < (L - 1) / 2; ++v)
+            x[v] = rf_ola_sample_d2(v, part.data(), rf_envelope(2 * v + 1, win2.data(), T, h.H, h.W), G, PL, nchunks,
+                                    h.H, h.W);
+    }
+}
+
+// the full-rate edge slots of k_istft_dec + the strip part of k_ola_assemble_dec: xe[2E] = head strip | tail strip
+void emu_istft_edges(const rf_plan_host& h, const float* S, const rf_c32* cur, const rf_c32* prev, int mode,
+                     float momentum, int T, float* xe) {
+    const int G = RF_CHUNK;
+    const rf_gl_dec_geom d = rf_dec_geom(T, G, h.H, h.W);
+    const int PL = (G - 1) * h.H + h.W;
+    std::vector<float> part(static_cast<size_t>(2) * d.nslots * PL, 0.f);
+    for (int slot = 0; slot < d.nslots; ++slot)
+        for (int g = 0; g < 2; ++g)
+            emu_istft_chunk<10>(h, S, cur, prev, mode, momentum, T, PL, g, slot == 0 ? 0 : d.c_tail + slot - 1,
+                                &part[(static_cast<size_t>(g) * d.nslots + slot) * PL]);
+    const std::vector<float> win2 = window_sq(h);
+    const int L = h.H * (T - 1);
+    for (int e = 0; e < 2 * d.E; ++e) {
+        const int i = e < d.E ? e : L - 2 * d.E + e;
+        xe[e] = rf_ola_sample_edge(i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PL, d.c_tail,
+                                   d.nslots, h.H, h.W);
+    }
 }
 }  // namespace
 
@@ -131,7 +193,7 @@ void emu_stft(void* p, const float* x, int L, float* spec) {
     auto* h = static_cast<rf_plan_host*>(p);
     const int T = 1 + L / h->H;
     std::vector<rf_c32> R(static_cast<size_t>(T) * h->n_live);
-    emu_stft_clip(*h, x, L, T, R.data());
+    emu_stft_clip<10>(*h, x, L, T, R.data());
     std::memset(spec, 0, static_cast<size_t>(h->F) * T * 8);
     for (int t = 0; t < T; ++t)
         for (int j = 0; j < h->n_live; ++j) {
@@ -141,11 +203,48 @@ void emu_stft(void* p, const float* x, int L, float* spec) {
         }
 }
 
-// Griffin-Lim of one clip, same buffer rotation as gl_loop() in rf_audio.cu.
-// lin[F][T], angles[F][T] complex64 (or null), wave[hop*(T-1)]
-void emu_griffinlim(void* p, const float* lin, const float* angles, int T, int n_iter, float momentum_in,
-                    float* wave) {
+// debug/validation: half-rate STFT of the odd samples of x
+void emu_stft_d2(void* p, const float* x, int L, float* spec) {
     auto* h = static_cast<rf_plan_host*>(p);
+    const int T = 1 + L / h->H;
+    std::vector<rf_c32> R(static_cast<size_t>(T) * h->n_live);
+    std::vector<float> xo((L - 1) / 2 + 1);
+    for (int v = 0; v < (L - 1) / 2; ++v) xo[v] = x[2 * v + 1];
+    emu_stft_clip<5>(*h, xo.data(), L, T, R.data());
+    std::memset(spec, 0, static_cast<size_t>(h->F) * T * 8);
+    for (int t = 0; t < T; ++t)
+        for (int j = 0; j < h->n_live; ++j) {
+            const size_t o = (static_cast<size_t>(h->bins[j]) * T + t) * 2;
+            spec[o] = R[static_cast<size_t>(t) * h->n_live + j].x;
+            spec[o + 1] = R[static_cast<size_t>(t) * h->n_live + j].y;
+        }
+}
+
+// debug/validation: one inverse STFT (mode 0: spec = S * cur) at full (NA=10 -> wave[L]) or half rate (-> wave[(L-1)/2])
+void emu_istft(void* p, const float* lin, const float* angles, int T, int half, float* wave) {
+    auto* h = static_cast<rf_plan_host*>(p);
+    const size_t n = static_cast<size_t>(T) * h->n_live;
+    std::vector<float> S(n);
+    std::vector<rf_c32> R1(n);
+    for (int t = 0; t < T; ++t)
+        for (int j = 0; j < h->n_live; ++j) {
+            const size_t src = static_cast<size_t>(h->bins[j]) * T + t;
+            S[static_cast<size_t>(t) * h->n_live + j] = lin[src];
+            R1[static_cast<size_t>(t) * h->n_live + j] = c_make(angles[2 * src], angles[2 * src + 1]);
+        }
+    if (half) emu_istft_clip<5>(*h, S.data(), R1.data(), nullptr, 0, 0.f, T, wave);
+    else emu_istft_clip<10>(*h, S.data(), R1.data(), nullptr, 0, 0.f, T, wave);
+}
+
+int emu_plan_decimate(void* p) { return static_cast<rf_plan_host*>(p)->decimate ? 1 : 0; }
+
+// Griffin-Lim of one clip, same buffer rotation and decimation rule as gl_loop() in rf_audio.cu.
+// lin[F][T], angles[F][T] complex64 (or null), wave[hop*(T-1)]; decimate != 0 runs the half-rate inner loop
+void emu_griffinlim2(void* p, const float* lin, const float* angles, int T, int n_iter, float momentum_in,
+                     int decimate, float* wave) {
+    auto* h = static_cast<rf_plan_host*>(p);
+    const bool dec = decimate && h->decimate && rf_dec_ok(T, RF_CHUNK);
+    const rf_gl_dec_geom d = rf_dec_geom(T, RF_CHUNK, h->H, h->W);
     const size_t n = static_cast<size_t>(T) * h->n_live;
     std::vector<float> S(n);
     std::vector<rf_c32> R0(n), R1(n);
@@ -159,6 +258,7 @@ void emu_griffinlim(void* p, const float* lin, const float* angles, int T, int n
         }
     const float m = static_cast<float>(static_cast<double>(momentum_in) / (1.0 + static_cast<double>(momentum_in)));
     const int L = h->H * (T - 1);
+    std::vector<float> xo(static_cast<size_t>(L) / 2 + 1), xe(2 * (h->W + h->H));
     for (int it = 0; it <= n_iter; ++it) {
         const rf_c32* cur;
         const rf_c32* prev = nullptr;
@@ -171,9 +271,26 @@ void emu_griffinlim(void* p, const float* lin, const float* angles, int T, int n
             mode = 1;
             if (it >= 2 && m != 0.f) prev = R[it & 1];
         }
-        emu_istft_clip(*h, S.data(), cur, prev, mode, m, T, wave);
-        if (it == n_iter) break;
-        emu_stft_clip(*h, wave, L, T, R[it & 1]);
+        const bool last = it == n_iter;
+        if (dec && !last) {
+            emu_istft_clip<5>(*h, S.data(), cur, prev, mode, m, T, xo.data());
+            emu_istft_edges(*h, S.data(), cur, prev, mode, m, T, xe.data());
+        } else {
+            emu_istft_clip<10>(*h, S.data(), cur, prev, mode, m, T, wave);
+        }
+        if (last) break;
+        if (dec) {   // k_stft_dec
+            emu_stft_pairs<10>(*h, xe.data(), 0, L, T, 0, 3, R[it & 1]);
+            emu_stft_pairs<10>(*h, xe.data() + d.E, L - d.E, L, T, d.pr_tail, (T + 1) / 2, R[it & 1]);
+            emu_stft_pairs<5>(*h, xo.data(), 0, L, T, 3, d.pr_tail, R[it & 1]);
+        } else {
+            emu_stft_clip<10>(*h, wave, L, T, R[it & 1]);
+        }
     }
+}
+
+void emu_griffinlim(void* p, const float* lin, const float* angles, int T, int n_iter, float momentum_in,
+                    float* wave) {
+    emu_griffinlim2(p, lin, angles, T, n_iter, momentum_in, 0, wave);
 }
 }

@@ -199,6 +199,46 @@ def test_griffinlim_og_beat_32_iters_vs_torchaudio(conv, ta, golden):
     assert abs(got.shape[1] / 44100 - 5.11) < 0.01
 
 
+@pytest.mark.parametrize("T_,n_iter,B", [(64, 4, 1), (131, 6, 2), (512, 8, 1)])
+def test_griffinlim_decimated_loop_vs_full_rate(conv, ta, T_, n_iter, B):
+    """The half-rate inner loop (odd samples + full-rate edge strips) is a re-association of the same
+    arithmetic: against the full-rate loop of the same library, the fp64 oracle and torchaudio."""
+    from oracle import audio_oracle as ao
+    from riffusion.spectrogram_converter import SpectrogramConverter, get_plan
+    from riffusion.spectrogram_params import SpectrogramParams
+
+    torch.manual_seed(7 * T_ + n_iter)
+    mel = (torch.rand(B, 512, T_) ** 4) * 3e7
+    ang = torch.rand(B, F, T_, dtype=torch.complex64)
+    prm = SpectrogramParams(num_griffin_lim_iters=n_iter)
+    c = SpectrogramConverter(prm, device="cuda")
+    plan = get_plan(prm, full_band=False)
+    try:
+        assert plan.set_decimation(False) is False
+        full = c.waveform_from_mel_amplitudes(mel.cuda(), ang.cuda()).cpu()
+        assert plan.set_decimation(True) is True
+        dec = c.waveform_from_mel_amplitudes(mel.cuda(), ang.cuda()).cpu()
+    finally:
+        plan.set_decimation(True)
+    assert not torch.equal(full, dec)
+    import torchaudio
+
+    from oracle.torchaudio_ref import griffinlim_with_angles
+
+    lin = ta.inverse_mel_scaler(mel)
+    gl = torchaudio.transforms.GriffinLim(n_fft=N, n_iter=n_iter, win_length=W, hop_length=H, power=1.0,
+                                          momentum=0.99, rand_init=True)
+    ref = griffinlim_with_angles(gl, lin, ang)
+    o64 = torch.from_numpy(ao.griffinlim(lin.numpy(), N, H, ao.hann_window(W).double().numpy(), n_iter, 0.99,
+                                         ang.numpy())).float()
+    err_ta, err_full, err_dec = _norm_rms(ref, o64), _norm_rms(full, o64), _norm_rms(dec, o64)
+    print(f"T={T_} iters={n_iter}: normalised RMS vs fp64 - torchaudio {err_ta:.2e}, full-rate {err_full:.2e}, "
+          f"decimated {err_dec:.2e}; decimated vs full-rate {_norm_rms(dec, full):.2e}")
+    assert err_full <= max(2 * err_ta, 2e-5)
+    assert err_dec <= max(3 * err_ta, 2e-5)
+    assert _norm_rms(dec, ref) < 1e-4
+
+
 def test_griffinlim_full_size_properties(conv):
     """size-independent properties at BASELINE's full size (batch 16 x 512 frames): batch
     independence (clip b of a batch == the same clip alone, bit-exact), determinism, finiteness,

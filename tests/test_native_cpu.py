@@ -168,3 +168,52 @@ def test_emulated_griffinlim_matches_torchaudio(hostemu, full_band, T_, n_iter):
     if err_ta < 5e-6:
         assert ((got - ref).norm() / ref.norm()).item() < 1e-5
     hostemu.emu_plan_destroy(p)
+
+
+@pytest.mark.parametrize("T_,n_iter", [(64, 3), (75, 4), (97, 8)])
+def test_emulated_decimated_griffinlim(hostemu, T_, n_iter):
+    """The half-rate inner loop (odd samples + two full-rate edge strips) against the full-rate loop,
+    the fp64 oracle and torchaudio.  T_=64 is the smallest eligible clip (c_tail = 2), 75 / 97 have odd frame counts
+    and ragged last chunks."""
+    import torchaudio
+
+    from oracle import audio_oracle as ao
+    from oracle.torchaudio_ref import griffinlim_with_angles
+
+    p, fb = _emu_plan(hostemu, False)
+    assert hostemu.emu_plan_decimate(p) == 1
+    torch.manual_seed(T_ + n_iter)
+    mag = torch.rand(F, T_) * 100 * torch.from_numpy((fb != 0).any(axis=1))[:, None]
+    ang = torch.rand(F, T_, dtype=torch.complex64)
+    gl = torchaudio.transforms.GriffinLim(n_fft=N, n_iter=n_iter, win_length=W, hop_length=H, power=1.0,
+                                          momentum=0.99, rand_init=True)
+    ref = griffinlim_with_angles(gl, mag[None], ang[None])[0].numpy()
+    o64 = ao.griffinlim(mag[None].numpy(), N, H, torch.hann_window(W).double().numpy(), n_iter, 0.99,
+                        ang[None].numpy())[0]
+    out = {}
+    for dec in (0, 1):
+        wave = np.zeros(H * (T_ - 1), np.float32)
+        hostemu.emu_griffinlim2(p, mag.numpy().ctypes.data, torch.view_as_real(ang).numpy().ctypes.data, T_, n_iter,
+                                ctypes.c_float(0.99), dec, wave.ctypes.data)
+        out[dec] = wave
+    nrm = np.linalg.norm(o64)
+    err_ta = np.linalg.norm(ref - o64) / nrm
+    err_full = np.linalg.norm(out[0] - o64) / nrm
+    err_dec = np.linalg.norm(out[1] - o64) / nrm
+    assert not np.array_equal(out[0], out[1])            # the decimated path really ran
+    assert err_full < max(5e-6, err_ta)
+    assert err_dec < max(1e-5, 3 * err_ta)                # aliasing stays at the fp32 rounding level
+    hostemu.emu_plan_destroy(p)
+
+
+def test_decimation_eligibility(hostemu):
+    """full-band plans (k_hi = n_fft/2) and wide mel bands must not decimate"""
+    p, _ = _emu_plan(hostemu, True)
+    assert hostemu.emu_plan_decimate(p) == 0
+    hostemu.emu_plan_destroy(p)
+    p, _ = _emu_plan(hostemu, False, 0.0, 12000.0)
+    assert hostemu.emu_plan_decimate(p) == 0
+    hostemu.emu_plan_destroy(p)
+    p, _ = _emu_plan(hostemu, False, 0.0, 10000.0)
+    assert hostemu.emu_plan_decimate(p) == 1
+    hostemu.emu_plan_destroy(p)
