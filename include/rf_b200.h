@@ -170,7 +170,8 @@ typedef struct rf_gemm_desc {
     const void* residual;      /* fp16, indexed like D with ldr/sr1/sr2, or NULL */
     int64_t ldr, sr1, sr2;
     float alpha;               /* 0 is treated as 1 */
-    int32_t act;               /* 0 none, 1 SiLU */
+    int32_t act;               /* 0 none, 1 SiLU, 2 GEGLU: B rows come in runs of [16 value | 16 gate] rows of the
+                                  same 16 outputs, D has N/2 columns, D[m][16 r + j] = v_j * gelu(g_j) (exact erf) */
     int32_t out_f32;           /* 1: D is fp32 */
 } rf_gemm_desc;
 int rf_gemm_f16(const rf_gemm_desc* desc, void* stream);

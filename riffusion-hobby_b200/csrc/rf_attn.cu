@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -315,6 +316,291 @@ k_flash_attn(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
     }
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-pass variant (head dims up to 112): every key tile is visited once.
+//   * The two softmax groups still take alternate key tiles of the same 128 queries, but each group keeps its OWN
+//     reference maximum and its OWN accumulator O_g in TMEM, so the groups never exchange anything inside the loop;
+//     the epilogue merges  O = (O_A 2^(mA-m) + O_B 2^(mB-m)) / (l_A 2^(mA-m) + l_B 2^(mB-m)).
+//   * The reference maximum is only raised when a tile exceeds it by more than 2^RESCALE_LOG2 (probabilities stay
+//     <= 2^RESCALE_LOG2, safe in fp16); raising it rescales O_g in TMEM (tcgen05.ld -> multiply -> tcgen05.st), which
+//     happens a handful of times per row instead of once per tile.
+//   * Row sums come out of the tensor core: the V^T tiles carry 16 extra rows of ones below the head dim, so column NV
+//     of O_g is sum_j P_ij of exactly the fp16 values the P V product used.
+//   * A group pulls its whole 128-score row into registers and frees the S buffer before it evaluates the
+//     exponentials, so the next Q K^T overlaps the softmax arithmetic.
+// TMEM: S0 | S1 | O_A (NV+16 columns) | O_B (NV+16 columns).
+constexpr float RESCALE_LOG2 = 4.f;
+
+template <int DPAD, int NV, int NS>
+__global__ void __launch_bounds__(320, 1)
+k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+              const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NSLAB = DPAD / 64;
+    constexpr int NVP = NV + 16;                                  // head dim columns + the row-sum column block
+    static_assert(256 + 2 * NVP <= 512, "TMEM budget");
+    constexpr int Q_BYTES = NSLAB * TQ * 128;
+    constexpr int K_BYTES = NSLAB * TK * 128;
+    constexpr int V_SLAB = ((NVP * 128 + 1023) / 1024) * 1024;
+    constexpr int V_BYTES = 2 * V_SLAB;
+    constexpr int P_BYTES = 2 * TQ * 128;
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + Q_BYTES;
+    uint8_t* sV = sK + NS * K_BYTES;
+    uint8_t* sP = sV + NS * V_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + NS;
+    uint64_t* s_full = kv_empty + NS;
+    uint64_t* s_empty = s_full + 2;
+    uint64_t* p_full = s_empty + 2;
+    uint64_t* p_empty = p_full + 2;
+    uint64_t* o_full = p_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    float* xchg = reinterpret_cast<float*>(tmem_slot + 2);       // [2][128] reference maxima of the two groups
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int T = p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(q_full, 1);
+        for (int i = 0; i < NS; ++i) {
+            tc::mbar_init(&kv_full[i], 1);
+            tc::mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s_full[i], 1);
+            tc::mbar_init(&s_empty[i], 128);
+            tc::mbar_init(&p_full[i], 128);
+            tc::mbar_init(&p_empty[i], 1);
+        }
+        tc::mbar_init(o_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    // rows NV .. NV+15 of every V^T slab = 1.0 (never touched by the TMA boxes, which are NV rows tall)
+    for (int i = threadIdx.x; i < NS * 2 * 16 * 8; i += blockDim.x) {
+        const int ch = i & 7, r = (i >> 3) & 15, sl = (i >> 7) & 1, st = i >> 8;
+        *reinterpret_cast<uint4*>(sV + st * V_BYTES + sl * V_SLAB + (NV + r) * 128 + ch * 16) =
+            make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    }
+    fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_O = tmem_base + 256;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        tc::mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+        for (int s = 0; s < NSLAB; ++s) tc::tma_load_4d(&mapQ, q_full, sQ + s * TQ * 128, s * 64, q_blk * TQ, head, b);
+        for (int j = 0; j < T; ++j) {
+            const int st = j % NS;
+            tc::mbar_wait(&kv_empty[st], ((j / NS) & 1) ^ 1);
+            tc::mbar_expect_tx(&kv_full[st], K_BYTES + 2 * NV * 128);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+                tc::tma_load_4d(&mapK, &kv_full[st], sK + st * K_BYTES + s * TK * 128, s * 64, j * TK, head, b);
+            tc::tma_load_4d(&mapVt, &kv_full[st], sV + st * V_BYTES, j * TK, 0, head, b);
+            tc::tma_load_4d(&mapVt, &kv_full[st], sV + st * V_BYTES + V_SLAB, j * TK + 64, 0, head, b);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_qk = tc::make_idesc_f16(TQ, TK);
+        constexpr uint32_t idesc_pv = tc::make_idesc_f16(TQ, NVP);
+        tc::mbar_wait(q_full, 0);
+        tc::fence_after_sync();
+        const uint32_t q_base = tc::smem_u32(sQ);
+        int se_cnt[2] = {0, 0}, pe_cnt[2] = {0, 0};
+        auto qk = [&](int j) {                   // S_{j&1} = Q K_j^T
+            const int i = j & 1, st = j % NS;
+            if (se_cnt[i] > 0) {
+                tc::mbar_wait(&s_empty[i], (se_cnt[i] - 1) & 1);
+                tc::fence_after_sync();
+            }
+            tc::mbar_wait(&kv_full[st], (j / NS) & 1);
+            tc::fence_after_sync();
+            const uint32_t k_base = tc::smem_u32(sK + st * K_BYTES);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16(tmem_base + i * 128, tc::make_desc_sw128(q_base + s * TQ * 128 + k * 32),
+                                tc::make_desc_sw128(k_base + s * TK * 128 + k * 32), idesc_qk, (s | k) ? 1u : 0u);
+            tc::mma_commit(&s_full[i]);
+            ++se_cnt[i];
+        };
+        constexpr int LA = NS >= 2 ? 2 : 1;
+        for (int j = 0; j < LA && j < T; ++j) qk(j);
+        for (int j = 0; j < T; ++j) {
+            const int i = j & 1, st = j % NS;
+            tc::mbar_wait(&p_full[i], pe_cnt[i] & 1);
+            tc::fence_after_sync();
+            const uint32_t p_base = tc::smem_u32(sP + i * P_BYTES);
+            const uint32_t v_base = tc::smem_u32(sV + st * V_BYTES);
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16(tmem_O + i * NVP, tc::make_desc_sw128(p_base + s * TQ * 128 + k * 32),
+                                tc::make_desc_sw128(v_base + s * V_SLAB + k * 32), idesc_pv, ((j >> 1) | s | k) ? 1u : 0u);
+            tc::mma_commit(&p_empty[i]);
+            tc::mma_commit(&kv_empty[st]);
+            ++pe_cnt[i];
+            if (j + LA < T) qk(j + LA);
+        }
+        tc::mma_commit(o_full);
+    } else if (warp >= 2) {
+        // ------------------------------------------------------------------ softmax groups
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t t_Og = t_row + 256 + g * NVP;
+        const float c = p.c;
+        int sf_phase = 0, pe_phase = 0, n_mine = 0;
+        float m_ref = -INFINITY;                 // reference maximum (raw score units) of this group
+        uint8_t* myP = sP + g * P_BYTES;
+        for (int j = g; j < T; j += 2, ++n_mine) {
+            tc::mbar_wait(&s_full[g], sf_phase);
+            sf_phase ^= 1;
+            tc::fence_after_sync();
+            uint32_t v[128];
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) tc::tmem_ld_32x32(t_row + g * 128 + c0, v + c0);
+            tc::tmem_wait_ld();
+            tc::fence_before_sync();
+            tc::mbar_arrive(&s_empty[g]);        // the scores are in registers: the next Q K^T may overwrite S
+            const int kmax = p.Nk - j * TK;
+            const bool ragged = kmax < TK;
+            if (ragged) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= kmax) v[i] = 0xff800000u;   // -inf
+            }
+            float mt = __uint_as_float(v[0]);
+#pragma unroll
+            for (int i = 1; i < 128; i += 2) {
+                const float e = i + 1 < 128 ? __uint_as_float(v[i + 1]) : -INFINITY;
+                mt = fmaxf(mt, fmaxf(__uint_as_float(v[i]), e));
+            }
+            const bool grow = (mt - m_ref) * c > RESCALE_LOG2;   // always true on the first tile (m_ref = -inf)
+            float fac = 1.f;
+            if (grow) {
+                fac = exp2f((m_ref - mt) * c);                   // 0 on the first tile
+                m_ref = mt;
+            }
+            if (n_mine > 0) {
+                tc::mbar_wait(&p_empty[g], pe_phase);            // previous P V of this group done: P buffer free, O_g quiet
+                pe_phase ^= 1;
+                tc::fence_after_sync();
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < NVP; c0 += 16) {
+                        uint32_t o[16];
+                        tmem_ld16(t_Og + c0, o);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * fac);
+                        tmem_st16(t_Og + c0, o);
+                    }
+                    tmem_wait_st();
+                }
+            }
+            const float mc = m_ref * c;
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    // two exponentials per MUFU op; the argument (<= RESCALE_LOG2) is formed in fp32, rounded once
+                    const float a0 = fmaf(__uint_as_float(v[c0 + i]), c, -mc);
+                    const float a1 = fmaf(__uint_as_float(v[c0 + i + 1]), c, -mc);
+                    const __half2 arg = __floats2half2_rn(a0, a1);
+                    asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i >> 1]) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+                }
+                const int slab = c0 >> 6, chunk = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4*>(myP + slab * TQ * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_async_smem();                  // P stores -> async proxy
+            tc::fence_before_sync();             // orders the tcgen05.st of a rescale before the P V issued after p_full
+            tc::mbar_arrive(&p_full[g]);
+        }
+        // ---- epilogue: merge the two groups' accumulators
+        xchg[g * 128 + row] = m_ref;
+        named_bar_sync(1, 256);
+        const bool haveB = T > 1;
+        const float mA = xchg[row], mB = haveB ? xchg[128 + row] : -INFINITY;
+        const float mm = fmaxf(mA, mB);
+        const float fA = exp2f((mA - mm) * c), fB = haveB ? exp2f((mB - mm) * c) : 0.f;
+        tc::mbar_wait(o_full, 0);
+        tc::fence_after_sync();
+        float inv;
+        {
+            uint32_t la[16], lb[16];
+            tmem_ld16(t_row + 256 + NV, la);
+            if (haveB) tmem_ld16(t_row + 256 + NVP + NV, lb);
+            tc::tmem_wait_ld();
+            inv = 1.f / (__uint_as_float(la[0]) * fA + (haveB ? __uint_as_float(lb[0]) * fB : 0.f));
+        }
+        const int qi = q_blk * TQ + row;
+        __half* dst = p.out + (static_cast<long>(b) * p.Nq + qi) * p.out_pitch + head * p.d;
+        const float wA = fA * inv, wB = fB * inv;
+#pragma unroll 1
+        for (int c0 = g * 16; c0 < NV; c0 += 32) {   // the groups take alternate 16-column chunks
+            uint32_t oa[16], ob[16];
+            tmem_ld16(t_row + 256 + c0, oa);
+            if (haveB) tmem_ld16(t_row + 256 + NVP + c0, ob);
+            tc::tmem_wait_ld();
+            if (qi < p.Nq) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int col = c0 + 8 * ch;
+                    if (col < p.d) {             // d is a multiple of 8
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float x0 = __uint_as_float(oa[8 * ch + 2 * e]) * wA, x1 = __uint_as_float(oa[8 * ch + 2 * e + 1]) * wA;
+                            if (haveB) {
+                                x0 = fmaf(__uint_as_float(ob[8 * ch + 2 * e]), wB, x0);
+                                x1 = fmaf(__uint_as_float(ob[8 * ch + 2 * e + 1]), wB, x1);
+                            }
+                            const __half2 h = __floats2half2_rn(x0, x1);
+                            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(dst + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -370,6 +656,24 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     return RF_OK;
 }
 
+template <int DPAD, int NV, int NS>
+int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, dim3 grid,
+                 cudaStream_t st) {
+    constexpr int NSLAB = DPAD / 64;
+    constexpr int V_SLAB = (((NV + 16) * 128 + 1023) / 1024) * 1024;
+    const size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NS) * (NSLAB * TK * 128 + 2 * V_SLAB) +
+                        2 * (2 * TQ * 128) + 256 + 2 * 128 * 4 + 1024;
+    static std::once_flag once;
+    static cudaError_t aerr = cudaSuccess;
+    std::call_once(once, [&] {
+        aerr = cudaFuncSetAttribute(k_flash_attn1<DPAD, NV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    });
+    if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn1): ") + cudaGetErrorString(aerr));
+    k_flash_attn1<DPAD, NV, NS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
+    RF_CUDA_LAUNCH_CHECK("k_flash_attn1");
+    return RF_OK;
+}
+
 }  // namespace
 
 // q: [B][Nq][heads*d], k: [B][Nk][heads*d], vt: [B][heads*d][vt_pitch] (V transposed), out: [B][Nq][heads*d]; fp16.
@@ -396,7 +700,7 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
         if (rc) return rc;
     }
     // must equal the NV template argument of the kernel variant chosen below (the TMA box defines the bytes per stage)
-    const int NV = d <= 48 ? 48 : d <= 64 ? 64 : d <= 80 ? 80 : d <= 128 ? 128 : d <= 160 ? 160 : 192;
+    const int NV = d <= 48 ? 48 : d <= 64 ? 64 : d <= 80 ? 80 : d <= 96 ? 96 : d <= 112 ? 112 : d <= 128 ? 128 : d <= 160 ? 160 : 192;
     {
         const long dims[4] = {Nk, d, heads, B};
         const long str[4] = {1, vt_pitch, static_cast<long>(d) * vt_pitch, C * vt_pitch};
@@ -412,9 +716,19 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     p.out_pitch = C;
     dim3 grid((Nq + TQ - 1) / TQ, heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool two_pass = getenv("RF_ATTN_TWO_PASS") != nullptr;   // A/B switch for the older kernel
+    if (!two_pass) {
+        if (d <= 48) return launch_attn1<64, 48, 3>(mq, mk, mv, p, grid, st);
+        if (d <= 64) return launch_attn1<64, 64, 3>(mq, mk, mv, p, grid, st);
+        if (d <= 80) return launch_attn1<128, 80, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 96) return launch_attn1<128, 96, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 112) return launch_attn1<128, 112, 2>(mq, mk, mv, p, grid, st);
+    }
     if (d <= 48) return launch_attn<64, 48, 3>(mq, mk, mv, p, grid, st);
     if (d <= 64) return launch_attn<64, 64, 3>(mq, mk, mv, p, grid, st);
     if (d <= 80) return launch_attn<128, 80, 2>(mq, mk, mv, p, grid, st);
+    if (d <= 96) return launch_attn<128, 96, 2>(mq, mk, mv, p, grid, st);
+    if (d <= 112) return launch_attn<128, 112, 2>(mq, mk, mv, p, grid, st);
     if (d <= 128) return launch_attn<128, 128, 2>(mq, mk, mv, p, grid, st);
     if (d <= 160) return launch_attn<192, 160, 1>(mq, mk, mv, p, grid, st);
     return launch_attn<192, 192, 1>(mq, mk, mv, p, grid, st);

@@ -263,6 +263,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                             if (n0 + i < p.N) f[i] += __half2float(b2p[i]);
                     }
                 }
+                if (p.act == 2) {
+                    // GEGLU: the 32-column run is [16 value | 16 gate] columns of the same 16 outputs (weight rows
+                    // interleaved by the caller); D has N/2 columns: out[n0/2 + j] = value_j * gelu(gate_j)
+                    __half* dst = p.out + out_off + (n0 >> 1);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float g0 = f[16 + 2 * j], g1 = f[17 + 2 * j];
+                        const float y0 = f[2 * j] * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f)));
+                        const float y1 = f[2 * j + 1] * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f)));
+                        const __half2 h = __floats2half2_rn(y0, y1);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    continue;
+                }
                 if (p.act) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], p.act);
@@ -474,6 +491,10 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
     p.ldr = d->ldr; p.sr1 = d->sr1; p.sr2 = d->sr2;
     p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.act = d->act;
+    if (d->act == 2 && ((d->N % 32) || d->residual || d->out_f32 || (d->ldd % 8) || (d->sd1 % 8) || (d->sd2 % 8) ||
+                        (reinterpret_cast<uintptr_t>(d->D) & 15)))
+        return rf_fail(RF_ERR_UNSUPPORTED, "rf_gemm_f16: GEGLU epilogue needs N % 32 == 0, fp16 output with 16-byte "
+                                           "aligned rows and no residual");
     return dispatch(d->N, ma, ma, mb, p, (d->M + BM - 1) / BM, b1 * b2, static_cast<cudaStream_t>(stream));
 }
 

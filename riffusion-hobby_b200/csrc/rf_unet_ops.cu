@@ -224,7 +224,7 @@ __global__ void k_upsample2x(const __half* __restrict__ x, int B, int H, int W, 
 // conv_in: NCHW fp16 (B, Cin<=8, H, W) -> NHWC fp16 (B, H, W, Cout), 3x3 pad 1. weights [Cout][Cin][3][3] fp16.
 // CTA = 64 consecutive pixels (8 per warp); the weights are staged once per CTA, transposed to [k][cout] so that
 // lanes (consecutive couts) read conflict-free and write coalesced NHWC rows.
-__global__ void k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+__global__ void k_conv_in_generic(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                           int B, int Cin, int H, int W, int Cout, __half* __restrict__ y) {
     extern __shared__ float wsm[];  // [Cin*9][Cout]
     const int K = Cin * 9;
@@ -259,7 +259,7 @@ __global__ void k_conv_in(const __half* __restrict__ x, const __half* __restrict
 
 // conv_out: NHWC fp16 (B, H, W, Cin) -> NCHW fp16/fp32 (B, Cout<=8, H, W), 3x3 pad 1. weights packed [Cout][3][3][Cin].
 // One warp per output pixel; lanes split the channels.
-__global__ void k_conv_out(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+__global__ void k_conv_out_generic(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                            int B, int H, int W, int Cin, int Cout, __half* __restrict__ y) {
     const size_t pix = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -281,6 +281,149 @@ __global__ void k_conv_out(const __half* __restrict__ x, const __half* __restric
         const float s = warp_sum(acc[o]);
         if (lane == 0)
             y[((static_cast<size_t>(b) * Cout + o) * H + yq) * W + xq] = __float2half_rn(s + (bias ? __half2float(bias[o]) : 0.f));
+    }
+}
+
+// conv_in, register-blocked: a warp computes 4 horizontally adjacent pixels x all Cout.  Lane owns the cout pairs
+// {2 lane + 64 i}, i < NCO2 (half2 stores: one 128-byte row segment per warp store), weights fp32 [k][Cout] in shared
+// memory (LDS.64, conflict-free), the 3 x 6 x Cin input patch of the group staged per warp and read by broadcast.
+// Persistent grid: every CTA stages the weights once and its warps stride over the pixel groups.  Needs W % 4 == 0.
+template <int NCO2>
+__global__ void __launch_bounds__(256)
+k_conv_in_blk(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias, int B, int Cin,
+              int H, int W, __half* __restrict__ y) {
+    constexpr int Cout = 64 * NCO2;
+    extern __shared__ float wsm[];                 // [Cin*9][Cout], then 8 warps x 18*Cin patch floats
+    const int K = Cin * 9;
+    for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {
+        const int co = i / K, k = i - co * K;      // torch layout [Cout][Cin][3][3] -> k = c*9 + dy*3 + dx
+        wsm[k * Cout + co] = __half2float(w[i]);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* patch = wsm + K * Cout + warp * (18 * 8);   // [c][dy][col 6]
+    __syncthreads();
+    float2 bz[NCO2];
+#pragma unroll
+    for (int i = 0; i < NCO2; ++i)
+        bz[i] = bias ? __half22float2(*reinterpret_cast<const __half2*>(bias + 2 * lane + 64 * i)) : make_float2(0.f, 0.f);
+    const int gpr = W / 4;                          // groups per row
+    const long ngroups = static_cast<long>(B) * H * gpr;
+    for (long g = static_cast<long>(blockIdx.x) * 8 + warp; g < ngroups; g += static_cast<long>(gridDim.x) * 8) {
+        const int x0 = static_cast<int>(g % gpr) * 4, yq = static_cast<int>((g / gpr) % H);
+        const int b = static_cast<int>(g / (static_cast<long>(gpr) * H));
+        __syncwarp();
+        for (int e = lane; e < 18 * Cin; e += 32) {
+            const int c = e / 18, r = e - c * 18, dy = r / 6, col = r - dy * 6;
+            const int yy = yq + dy - 1, xx = x0 + col - 1;
+            patch[e] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                           ? __half2float(x[((static_cast<size_t>(b) * Cin + c) * H + yy) * W + xx])
+                           : 0.f;
+        }
+        __syncwarp();
+        float2 acc[4][NCO2];
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+            for (int i = 0; i < NCO2; ++i) acc[p_][i] = bz[i];
+        for (int c = 0; c < Cin; ++c)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3, dx = t % 3;
+                const float* pr = patch + c * 18 + dy * 6 + dx;
+                const float i0 = pr[0], i1 = pr[1], i2 = pr[2], i3 = pr[3];
+                const float2* wr = reinterpret_cast<const float2*>(wsm + (c * 9 + t) * Cout) + lane;
+#pragma unroll
+                for (int i = 0; i < NCO2; ++i) {
+                    const float2 wv = wr[32 * i];
+                    acc[0][i].x += wv.x * i0; acc[0][i].y += wv.y * i0;
+                    acc[1][i].x += wv.x * i1; acc[1][i].y += wv.y * i1;
+                    acc[2][i].x += wv.x * i2; acc[2][i].y += wv.y * i2;
+                    acc[3][i].x += wv.x * i3; acc[3][i].y += wv.y * i3;
+                }
+            }
+        __half* yp = y + ((static_cast<size_t>(b) * H + yq) * W + x0) * Cout + 2 * lane;
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+            for (int i = 0; i < NCO2; ++i)
+                *reinterpret_cast<__half2*>(yp + static_cast<size_t>(p_) * Cout + 64 * i) =
+                    __floats2half2_rn(acc[p_][i].x, acc[p_][i].y);
+    }
+}
+
+// conv_out, register-blocked: a warp computes 4 horizontally adjacent pixels x Cout (<= 4) outputs.  Lane owns the
+// channel pairs {2 lane + 64 s}, s < NSTEP (coalesced 128-byte loads), weights fp32 in shared memory as
+// [tap][s][2 halves of the cout quad][lane][4] (LDS.128, conflict-free).  The 6 input columns of a kernel row are
+// loaded once and shared by the 3 horizontal taps of the 4 pixels.  Persistent grid.  Needs W % 4 == 0.
+template <int NSTEP>
+__global__ void __launch_bounds__(256)
+k_conv_out_blk(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias, int B, int H,
+               int W, int Cout, __half* __restrict__ y) {
+    constexpr int Cin = 64 * NSTEP;
+    extern __shared__ float wsm[];                 // [9][NSTEP][2][32][4]
+    for (int i = threadIdx.x; i < 9 * NSTEP * 256; i += blockDim.x) {
+        const int e = i & 3, ln = (i >> 2) & 31, hf = (i >> 7) & 1, s_ = (i >> 8) % NSTEP, t = i / (256 * NSTEP);
+        const int o = 2 * hf + (e >> 1), c = 2 * ln + 64 * s_ + (e & 1);
+        wsm[i] = o < Cout ? __half2float(w[(static_cast<size_t>(o) * 9 + t) * Cin + c]) : 0.f;   // packed [Cout][3][3][Cin]
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gpr = W / 4;
+    const long ngroups = static_cast<long>(B) * H * gpr;
+    for (long g = static_cast<long>(blockIdx.x) * 8 + warp; g < ngroups; g += static_cast<long>(gridDim.x) * 8) {
+        const int x0 = static_cast<int>(g % gpr) * 4, yq = static_cast<int>((g / gpr) % H);
+        const int b = static_cast<int>(g / (static_cast<long>(gpr) * H));
+        float acc[4][4];
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[p_][o] = 0.f;
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = yq + dy - 1;
+            if (yy < 0 || yy >= H) continue;
+            float2 in[6][NSTEP];
+            const __half* row = x + ((static_cast<size_t>(b) * H + yy) * W) * Cin + 2 * lane;
+#pragma unroll
+            for (int col = 0; col < 6; ++col) {
+                const int xx = x0 + col - 1;
+                const bool ok = xx >= 0 && xx < W;
+#pragma unroll
+                for (int s_ = 0; s_ < NSTEP; ++s_)
+                    in[col][s_] = ok ? __half22float2(*reinterpret_cast<const __half2*>(row + static_cast<size_t>(xx) * Cin + 64 * s_))
+                                     : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int s_ = 0; s_ < NSTEP; ++s_) {
+                    const float4* wq = reinterpret_cast<const float4*>(wsm) + (((dy * 3 + dx) * NSTEP + s_) * 2) * 32 + lane;
+                    const float4 w01 = wq[0], w23 = wq[32];   // (o0c0, o0c1, o1c0, o1c1), (o2c0, o2c1, o3c0, o3c1)
+#pragma unroll
+                    for (int p_ = 0; p_ < 4; ++p_) {
+                        const float2 v = in[p_ + dx][s_];
+                        acc[p_][0] += v.x * w01.x + v.y * w01.y;
+                        acc[p_][1] += v.x * w01.z + v.y * w01.w;
+                        acc[p_][2] += v.x * w23.x + v.y * w23.y;
+                        acc[p_][3] += v.x * w23.z + v.y * w23.w;
+                    }
+                }
+        }
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[p_][o] = warp_sum(acc[p_][o]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (lane == o && o < Cout) {
+                const float bo = bias ? __half2float(bias[o]) : 0.f;
+                const __half2 h01 = __floats2half2_rn(acc[0][o] + bo, acc[1][o] + bo);
+                const __half2 h23 = __floats2half2_rn(acc[2][o] + bo, acc[3][o] + bo);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(y + ((static_cast<size_t>(b) * Cout + o) * H + yq) * W + x0) = pk;
+            }
     }
 }
 
@@ -588,29 +731,68 @@ extern "C" int rf_vae_image_to_u8(const void* x_nchw, int B, int H, int W, uint8
     return RF_OK;
 }
 
+template <int NCO2>
+static int launch_conv_in_blk(const void* x, const void* w, const void* bias, int B, int Cin, int H, int W, void* y,
+                              cudaStream_t st) {
+    const size_t smem = (static_cast<size_t>(64 * NCO2) * Cin * 9 + 8 * 18 * 8) * sizeof(float);
+    RF_CUDA_TRY(cudaFuncSetAttribute(k_conv_in_blk<NCO2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    const long ngroups = static_cast<long>(B) * H * (W / 4);
+    const unsigned grid = static_cast<unsigned>(std::min<long>((ngroups + 7) / 8, 2 * 148));
+    k_conv_in_blk<NCO2><<<grid, 256, smem, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(w),
+                                                 static_cast<const __half*>(bias), B, Cin, H, W, static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_conv_in_blk");
+    return RF_OK;
+}
+
 extern "C" int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bias, int B, int Cin, int H, int W,
                               int Cout, void* y_nhwc, void* stream) {
     if (!x_nchw || !w || !y_nhwc || B <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0) return rf_fail(RF_ERR_INVALID, "rf_conv_in_f16: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W % 4 == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 3) == 0) &&
+        (reinterpret_cast<uintptr_t>(y_nhwc) & 3) == 0) {
+        if (Cout == 320) return launch_conv_in_blk<5>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);
+        if (Cout == 128) return launch_conv_in_blk<2>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);
+        if (Cout == 64) return launch_conv_in_blk<1>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);
+    }
     const size_t smem = static_cast<size_t>(Cout) * Cin * 9 * sizeof(float);
     if (smem > 96 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv_in_f16: weights too large");
     static bool attr = false;
     if (!attr) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(k_conv_in, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(k_conv_in_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr = true;
     }
     const size_t npix = static_cast<size_t>(B) * H * W;
-    k_conv_in<<<static_cast<unsigned>((npix + 63) / 64), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    k_conv_in_generic<<<static_cast<unsigned>((npix + 63) / 64), 256, smem, st>>>(
         static_cast<const __half*>(x_nchw), static_cast<const __half*>(w), static_cast<const __half*>(bias), B, Cin, H, W,
         Cout, static_cast<__half*>(y_nhwc));
     RF_CUDA_LAUNCH_CHECK("k_conv_in");
     return RF_OK;
 }
 
+template <int NSTEP>
+static int launch_conv_out_blk(const void* x, const void* w, const void* bias, int B, int H, int W, int Cout, void* y,
+                               cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(9) * NSTEP * 256 * sizeof(float);
+    RF_CUDA_TRY(cudaFuncSetAttribute(k_conv_out_blk<NSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    const long ngroups = static_cast<long>(B) * H * (W / 4);
+    const unsigned grid = static_cast<unsigned>(std::min<long>((ngroups + 7) / 8, 2 * 148));
+    k_conv_out_blk<NSTEP><<<grid, 256, smem, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(w),
+                                                   static_cast<const __half*>(bias), B, H, W, Cout, static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_conv_out_blk");
+    return RF_OK;
+}
+
 extern "C" int rf_conv_out_f16(const void* x_nhwc, const void* w_packed, const void* bias, int B, int H, int W, int Cin,
                                int Cout, void* y_nchw, void* stream) {
     if (!x_nhwc || !w_packed || !y_nchw || B <= 0 || Cout <= 0 || Cout > 8) return rf_fail(RF_ERR_INVALID, "rf_conv_out_f16: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W % 4 == 0 && Cout <= 4 && (reinterpret_cast<uintptr_t>(y_nchw) & 7) == 0) {
+        if (Cin == 320) return launch_conv_out_blk<5>(x_nhwc, w_packed, bias, B, H, W, Cout, y_nchw, st);
+        if (Cin == 128) return launch_conv_out_blk<2>(x_nhwc, w_packed, bias, B, H, W, Cout, y_nchw, st);
+        if (Cin == 64) return launch_conv_out_blk<1>(x_nhwc, w_packed, bias, B, H, W, Cout, y_nchw, st);
+    }
     const size_t pix = static_cast<size_t>(B) * H * W;
-    k_conv_out<<<static_cast<unsigned>((pix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    k_conv_out_generic<<<static_cast<unsigned>((pix + 7) / 8), 256, 0, st>>>(
         static_cast<const __half*>(x_nhwc), static_cast<const __half*>(w_packed), static_cast<const __half*>(bias), B, H,
         W, Cin, Cout, static_cast<__half*>(y_nchw));
     RF_CUDA_LAUNCH_CHECK("k_conv_out");

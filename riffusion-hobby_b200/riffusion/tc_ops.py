@@ -12,7 +12,7 @@ import torch
 
 from riffusion import _native
 
-ACT_NONE, ACT_SILU = 0, 1
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 
 
 def _f16(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -45,12 +45,13 @@ def gemm(
     a = a.expand(B2, B1, M, K)          # broadcast batch dims get stride 0 (handled in the C-ABI)
     b = b.expand(B2, B1, N, K)
     assert b.shape[3] == K and a.stride(3) == 1 and b.stride(3) == 1
+    n_out = N // 2 if act == ACT_GEGLU else N       # GEGLU epilogue: b packed with interleave_geglu()
     if out is None:
-        out = torch.empty((B2, B1, M, N), dtype=out_dtype, device=a.device)
+        out = torch.empty((B2, B1, M, n_out), dtype=out_dtype, device=a.device)
     o4 = out
     while o4.dim() < 4:
         o4 = o4.unsqueeze(0)
-    assert o4.shape == (B2, B1, M, N) and o4.stride(3) == 1
+    assert o4.shape == (B2, B1, M, n_out) and o4.stride(3) == 1
     d = _native.GemmDesc()
     d.M, d.N, d.K, d.batch1, d.batch2 = M, N, K, B1, B2
     d.A, d.lda, d.sa1, d.sa2 = a.data_ptr(), a.stride(2), a.stride(1), a.stride(0)
@@ -68,6 +69,17 @@ def gemm(
     with torch.cuda.device(a.device):
         _native.check(_native.lib().rf_gemm_f16(C.byref(d), _stream(a)))
     return out
+
+
+def interleave_geglu(t: torch.Tensor) -> torch.Tensor:
+    """Row order the GEGLU epilogue of rf_gemm_f16 expects.  t: (2*inner, ...) = diffusers GEGLU.proj weight or bias,
+    rows [0, inner) the value half and [inner, 2*inner) the gate half (models/activations.py GEGLU.forward: chunk(2));
+    result: runs of [16 value rows | 16 gate rows] of the same 16 outputs."""
+    inner = t.shape[0] // 2
+    assert t.shape[0] == 2 * inner and inner % 16 == 0
+    v = t[:inner].reshape(inner // 16, 16, *t.shape[1:])
+    g = t[inner:].reshape(inner // 16, 16, *t.shape[1:])
+    return torch.stack((v, g), dim=1).reshape(t.shape).contiguous()
 
 
 def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:

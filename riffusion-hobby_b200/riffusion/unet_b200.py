@@ -50,6 +50,8 @@ class UNetB200:
                 self.w[name] = ops.pack_conv_weight(p.to(dev))               # (Cout, 3, 3, Cin)
             elif p.dim() == 4 and p.shape[2] == 1:
                 self.w[name] = _h(p.reshape(p.shape[0], p.shape[1]), dev)    # 1x1 conv == linear over pixels
+            elif ".ff.net.0.proj." in name:
+                self.w[name] = ops.interleave_geglu(_h(p, dev))              # value/gate rows paired for the epilogue
             else:
                 self.w[name] = _h(p, dev)
         # all resnets' time_emb_proj (Linear 1280 -> cout) stacked into one GEMM per forward
@@ -146,8 +148,8 @@ class UNetB200:
                      residual=h).reshape(rows, C)
         # GEGLU feed-forward
         n3 = ops.layer_norm(h, w[t + "norm3.weight"], w[t + "norm3.bias"])
-        ff = ops.gemm(n3, w[t + "ff.net.0.proj.weight"], bias=w[t + "ff.net.0.proj.bias"]).reshape(rows, 8 * C)
-        g = ops.geglu(ff)
+        g = ops.gemm(n3, w[t + "ff.net.0.proj.weight"], bias=w[t + "ff.net.0.proj.bias"],
+                     act=ops.ACT_GEGLU).reshape(rows, 4 * C)                 # proj + GEGLU in the GEMM epilogue
         h = ops.gemm(g, w[t + "ff.net.2.weight"], bias=w[t + "ff.net.2.bias"], residual=h).reshape(rows, C)
         out = ops.gemm(h, w[pfx + "proj_out.weight"], bias=w[pfx + "proj_out.bias"], residual=x.reshape(rows, C))
         return out.reshape(B, H, W, C)

@@ -33,6 +33,26 @@ def test_gemm_matches_torch(native_lib, M, N, K):
     _close(f32, ref, tol=2e-5)
 
 
+@pytest.mark.parametrize("M,C", [(300, 320), (4096, 640), (77, 1280)])
+def test_gemm_geglu_epilogue(native_lib, M, C):
+    """ff.net.0.proj + GEGLU fused (diffusers GEGLU: hidden, gate = proj(x).chunk(2); hidden * gelu(gate))"""
+    import torch.nn.functional as F
+
+    from riffusion import tc_ops as ops
+
+    torch.manual_seed(M + C)
+    x = torch.randn(M, C, device="cuda").half()
+    w = (torch.randn(8 * C, C, device="cuda") / C ** 0.5).half()
+    b = (0.1 * torch.randn(8 * C, device="cuda")).half()
+    h, gate = (x.float() @ w.float().t() + b.float()).chunk(2, dim=-1)
+    ref = h * F.gelu(gate)
+    got = ops.gemm(x, ops.interleave_geglu(w), bias=ops.interleave_geglu(b), act=ops.ACT_GEGLU)
+    assert got.shape[-2:] == (M, 4 * C)
+    assert (got.float().reshape(M, 4 * C) - ref).abs().max() < 2e-2
+    unfused = ops.geglu(ops.gemm(x, w, bias=b).reshape(M, 8 * C))
+    assert (got.float().reshape(M, 4 * C) - unfused.float()).abs().max() < 1e-2
+
+
 def test_gemm_batched_strided_heads(native_lib):
     """attention-shaped operands: Q/K views (B, heads, tokens, d) of a (B, tokens, heads*d) tensor, d = 40
     (K tail zero-filled by TMA), per-row bias, fp32 and fp16 outputs"""
@@ -90,7 +110,7 @@ def test_conv_matches_torch(native_lib, B, H, W, C1, C2, Cout, k, stride):
                                              (3, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (1, 8, 1024, 77, 80),
                                              (2, 8, 256, 77, 160), (1, 4, 200, 300, 16), (1, 2, 128, 129, 64)])
 def test_fused_attention_matches_torch(native_lib, B, heads, Nq, Nk, d):
-    """fused QK^T -> softmax -> PV (tcgen05, two-pass) vs fp32 torch attention on the same fp16 inputs;
+    """fused QK^T -> softmax -> PV (tcgen05) vs fp32 torch attention on the same fp16 inputs;
     UNet self-/cross-attention shapes plus ragged sizes (query / key tails, single and odd tile counts)"""
     from riffusion import tc_ops
 
@@ -109,3 +129,30 @@ def test_fused_attention_matches_torch(native_lib, B, heads, Nq, Nk, d):
     assert got.shape == ref.shape and torch.isfinite(got).all()
     _close(got, ref, tol=4e-3)
     assert float((got.float() - ref).norm() / ref.norm()) < 2e-3
+
+
+@pytest.mark.parametrize("Nk,d", [(1024, 40), (700, 40), (512, 80), (384, 64), (300, 96)])
+def test_fused_attention_growing_scores(native_lib, Nk, d):
+    """single-pass kernel: the keys are ordered so that the row maximum keeps growing along the key axis (forces the
+    TMEM rescale of the running accumulators several times per row) with peaked softmax rows (large logits)"""
+    from riffusion import tc_ops
+
+    torch.manual_seed(Nk + d)
+    B, heads, Nq = 1, 2, 200
+    C = heads * d
+    a = 0.5 + torch.rand(B, Nq, 1, device="cuda")
+    q = (a + 0.5 * torch.randn(B, Nq, C, device="cuda")).half()            # q_i ~ a_i * ones + noise
+    ramp = torch.linspace(0.0, 6.0, Nk, device="cuda")[None, :, None]
+    k = (ramp + 0.5 * torch.randn(B, Nk, C, device="cuda")).half()          # logits ~ a_i * ramp_j * sqrt(d)
+    v = torch.randn(B, Nk, C, device="cuda").half()
+    pitch = (Nk + 7) // 8 * 8
+    vt = torch.zeros(B, C, pitch, dtype=torch.float16, device="cuda")
+    vt[..., :Nk] = v.transpose(1, 2)
+    qh, kh, vh = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    logits = qh @ kh.transpose(-1, -2) * d ** -0.5
+    assert float(logits.max() - logits.min()) > 30          # the test is only meaningful with a wide logit range
+    ref = (torch.softmax(logits, dim=-1) @ vh).transpose(1, 2).reshape(B, Nq, C)
+    got = tc_ops.attention(q, k, vt, heads, Nk)
+    assert torch.isfinite(got).all()
+    _close(got, ref, tol=6e-3)
+    assert float((got.float() - ref).norm() / ref.norm()) < 3e-3

@@ -46,17 +46,21 @@ def test_elementwise_ops_match_torch(native_lib):
     assert torch.equal(ops.upsample2x(x), F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1))
     a, bb = torch.randn(2, 3, 3, 128, device="cuda").half(), torch.randn(2, 3, 3, 64, device="cuda").half()
     assert torch.equal(ops.concat_channels(a, bb), torch.cat([a, bb], dim=-1))
-    # edge convolutions
-    x = torch.randn(2, 4, 12, 12, device="cuda").half()
-    w = (torch.randn(320, 4, 3, 3, device="cuda") * 0.1).half()
-    bias = torch.randn(320, device="cuda").half()
-    ref = F.conv2d(x.float(), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
-    assert (ops.conv_in(x, w, bias).float() - ref).abs().max() < 5e-3
-    x = torch.randn(2, 12, 12, 320, device="cuda").half()
-    w = (torch.randn(4, 320, 3, 3, device="cuda") * 0.02).half()
-    bias = torch.randn(4, device="cuda").half()
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)
-    assert (ops.conv_out(x, ops.pack_conv_weight(w), bias).float() - ref).abs().max() < 5e-3
+    # edge convolutions: register-blocked kernels (W % 4 == 0, Cout/Cin in {64, 128, 320}) and the generic fallback
+    for (B, Cin, H, W, Cout) in ((2, 4, 12, 12, 320), (1, 3, 8, 20, 128), (3, 4, 5, 8, 64), (2, 4, 6, 7, 320),
+                                 (1, 4, 9, 12, 96)):
+        x = torch.randn(B, Cin, H, W, device="cuda").half()
+        w = (torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.1).half()
+        bias = torch.randn(Cout, device="cuda").half()
+        ref = F.conv2d(x.float(), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+        assert (ops.conv_in(x, w, bias).float() - ref).abs().max() < 5e-3, (B, Cin, H, W, Cout)
+    for (B, H, W, Cin, Cout) in ((2, 12, 12, 320, 4), (1, 8, 20, 128, 3), (3, 5, 8, 64, 4), (2, 6, 7, 320, 4),
+                                 (1, 9, 12, 96, 4)):
+        x = torch.randn(B, H, W, Cin, device="cuda").half()
+        w = (torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.02).half()
+        bias = torch.randn(Cout, device="cuda").half()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1)
+        assert (ops.conv_out(x, ops.pack_conv_weight(w), bias).float() - ref).abs().max() < 5e-3, (B, H, W, Cin, Cout)
     # sinusoidal embedding
     from oracle.unet_oracle import timestep_sinusoid
 
