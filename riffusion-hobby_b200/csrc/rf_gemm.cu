@@ -57,6 +57,12 @@ struct TcParams {
     float alpha;
     int act;                // 0 none, 1 SiLU
     float* out_f32;         // optional fp32 output instead of fp16 (same indexing)
+    // split-K (non-batched problems with few output tiles): work unit u = tile * splits + sp covers K slabs
+    // [sp * kb_per_split, ...); every unit stores its raw fp32 accumulator to ws[sp][row][N] and k_splitk_reduce applies
+    // the epilogue.  splits == 1: the normal fused epilogue.
+    int splits, kb_per_split;
+    float* ws;
+    long ws_split_stride;   // rows * N
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -76,7 +82,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int B_TILE_BYTES = BN * BK * 2;
-    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM allocations are powers of two
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_TILE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
@@ -87,7 +93,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_mn = p.tiles_n * p.tiles_m;
-    const int n_tiles = tiles_mn * p.batch1 * p.batch2;
+    const int n_tiles = tiles_mn * p.batch1 * p.batch2 * p.splits;   // work units (== tiles when splits == 1)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -116,7 +122,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------ TMA producer
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
+            const int tile = unit / p.splits, sp = unit - tile * p.splits;
+            const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
             const int m_blk = mn / p.tiles_n, n_blk = mn - m_blk * p.tiles_n;
             const int b1 = z % p.batch1, b2 = z / p.batch1;
@@ -126,7 +134,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 ty = (m_blk / p.tiles_x) % p.tiles_y;
                 tb = m_blk / (p.tiles_x * p.tiles_y);
             }
-            for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t phase = (it / STAGES) & 1;
                 tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -154,14 +162,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc::make_idesc_f16(BM, BN);
         int it = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++lt) {
+            const int sp = unit % p.splits;
+            const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int acc = lt & 1;
             if (lt >= 2) {                                   // the epilogue must have drained this accumulator
                 tc::mbar_wait(&tmem_empty[acc], ((lt >> 1) - 1) & 1);
                 tc::fence_after_sync();
             }
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t phase = (it / STAGES) & 1;
                 tc::mbar_wait(&full[stage], phase);
@@ -172,7 +182,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
                     const uint64_t db = tc::make_desc_sw128(b_base + k * 32);
-                    tc::mma_f16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                    tc::mma_f16(d_tmem, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
                 }
                 tc::mma_commit(&empty[stage]);
             }
@@ -184,9 +194,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const int q = warp & 3;
         const int half_id = (warp - 2) >> 2;
         const int row = q * 32 + lane;      // row of the 128-row tile == TMEM lane
-        constexpr int COLS_PER_WARP = BN / 2;
         int lt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++lt) {
+            const int tile = unit / p.splits, sp = unit - tile * p.splits;
             const int acc = lt & 1;
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
             const int m_blk = mn / p.tiles_n, n_blk = mn - m_blk * p.tiles_n;
@@ -213,12 +223,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             tc::mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int c0 = half_id * COLS_PER_WARP; c0 < (half_id + 1) * COLS_PER_WARP; c0 += 32) {
+            for (int c0 = half_id * 32; c0 < BN; c0 += 64) {   // the two warp sets take alternate 32-column runs
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
                 tc::tmem_wait_ld();
                 const int n0 = n_blk * BN + c0;
                 if (!row_ok || n0 >= p.N) continue;
+                if (p.splits > 1) {   // raw partial sums; ws rows are dense with pitch N in output-row order
+                    float* wp = p.ws + sp * p.ws_split_stride + (out_off / p.ldo) * p.N + n0;
+                    if (n0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            reinterpret_cast<uint4*>(wp)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < p.N) wp[i] = __uint_as_float(v[i]);
+                    }
+                    continue;
+                }
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha + bias_row;
@@ -387,7 +409,7 @@ struct TcProfile {
     std::vector<cudaEvent_t> ev;   // begin/end pairs
     double flops = 0.0;
     long launches = 0;
-    struct Rec { int conv, M, N, K, batch; };
+    struct Rec { int conv, M, N, K, batch, splits; };
     std::vector<Rec> recs;
 };
 TcProfile g_prof;
@@ -428,23 +450,153 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         g_prof.launches += 1;
         const double m = p.conv ? static_cast<double>(p.Bn) * p.Ho * p.Wo : static_cast<double>(p.M) * p.batch1 * p.batch2;
         g_prof.flops += 2.0 * m * p.N * p.K;
-        g_prof.recs.push_back({p.conv, p.conv ? p.Bn * p.Ho * p.Wo : p.M, p.N, p.K, p.batch1 * p.batch2});
+        g_prof.recs.push_back({p.conv, p.conv ? p.Bn * p.Ho * p.Wo : p.M, p.N, p.K, p.batch1 * p.batch2, p.splits});
     }
     return RF_OK;
 }
 
+// ---- split-K second stage: out = act(alpha * sum_s ws[s] + bias + bias2[img]) + residual, 8 columns per thread
+__global__ void k_splitk_reduce(const float* __restrict__ ws, int splits, long split_stride, long rows, int N, long ldo,
+                                long ldr, int rows_per_image, float alpha, const __half* __restrict__ bias, int bias_mode,
+                                const __half* __restrict__ bias2, int bias2_pitch, int act,
+                                const __half* __restrict__ residual, __half* __restrict__ out, float* __restrict__ out_f32) {
+    const int n8 = N / 8;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * n8;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long r = i / n8;
+        const int n0 = static_cast<int>(i - r * n8) * 8;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        for (int sidx = 0; sidx < splits; ++sidx) {
+            const float4* wp = reinterpret_cast<const float4*>(ws + sidx * split_stride + r * N + n0);
+            const float4 a = wp[0], b = wp[1];
+            f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+            f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+        }
+        const float brow = bias_mode == 2 ? __half2float(bias[r]) : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = f[e] * alpha + brow;
+            if (bias_mode == 1) v += __half2float(bias[n0 + e]);
+            if (bias2) v += __half2float(bias2[(r / rows_per_image) * bias2_pitch + n0 + e]);
+            if (act == 1) v = apply_act(v, 1);
+            if (residual) v += __half2float(residual[r * ldr + n0 + e]);
+            f[e] = v;
+        }
+        if (out_f32) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) out_f32[r * ldo + n0 + e] = f[e];
+        } else {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(out + r * ldo + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// Split-K workspace: one lazily grown device buffer per process (allocated outside stream capture: the eager warm-up
+// evaluation that precedes every graph capture sizes it).
+struct SplitWs {
+    float* ptr = nullptr;
+    size_t bytes = 0;
+};
+SplitWs g_ws;
+constexpr size_t SPLIT_WS_MAX = static_cast<size_t>(192) << 20;
+
+// Number of K splits: a problem with fewer tiles than SMs leaves SMs idle AND streams its weights through too few
+// TMA rings to cover HBM latency.  Cost model in microseconds: ceil(units / SMs) waves of (slabs per unit) x t_slab,
+// plus for S > 1 the second-stage launch and its fp32 round trip (mostly L2 resident).
+int pick_splits(long rows, int N, int tiles, int num_kb, int num_sms, bool allowed) {
+    static const char* env = getenv("RF_GEMM_SPLITK");   // "0" disables, "N" forces N where legal (A/B measurements)
+    if (!allowed || (env && env[0] == '0')) return 1;
+    const double t_slab = 0.2, t_launch = 3.0, ws_bw = 8.0e6;   // us, us, bytes/us
+    int best = 1;
+    double best_t = 1e30;
+    for (int S = 1; S <= 8; ++S) {
+        if (S > 1 && (num_kb / S < 6 || static_cast<size_t>(S) * rows * N * 4 > SPLIT_WS_MAX)) break;
+        const int kbs = (num_kb + S - 1) / S;
+        if (S > 1 && (S - 1) * kbs >= num_kb) continue;   // the last split would be empty
+        const int waves = (tiles * S + num_sms - 1) / num_sms;
+        double t = waves * kbs * t_slab;
+        if (S > 1) t += t_launch + 2.0 * S * rows * N * 4 / ws_bw;
+        if (env && atoi(env) == S) return S;
+        if (t < best_t * (S > 1 ? 0.9 : 1.0)) {   // a split must win by 10%
+            best_t = t;
+            best = S;
+        }
+    }
+    return best;
+}
+
+// output-tile width: 64 for narrow outputs, 160 when it divides N and 128 does not, else 128
+int pick_bn(int N) {
+    if (N <= 64) return 64;
+    if (N % 160 == 0 && N % 128 != 0) return 160;
+    return 128;
+}
+
+int num_sms_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            n = 148;
+    }
+    return n;
+}
+
 int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, int tiles_m,
              int nbatch, cudaStream_t st) {
-    // one persistent CTA per SM: 6-stage (BN=128, 192 KB) / 8-stage (BN=64, 192 KB) TMA ring, 2 TMEM accumulators
+    // one persistent CTA per SM: 6-stage (BN=128/160) / 8-stage (BN=64) TMA ring, 2 TMEM accumulators
     p.tiles_m = tiles_m;
-    if (N > 64) {
-        p.tiles_n = (N + 127) / 128;
-        dim3 grid(p.tiles_n, tiles_m, nbatch);
-        return launch<128, 6>(a0, a1, b, p, grid, st);
+    const int bn = pick_bn(N);
+    p.tiles_n = (N + bn - 1) / bn;
+    // split-K: non-batched, plain or SiLU epilogue, 16-byte aligned fp16/fp32 rows
+    const long rows = p.conv ? static_cast<long>(p.Bn) * p.Ho * p.Wo : p.M;
+    const bool can_split = nbatch == 1 && p.act != 2 && (N % 8) == 0 && (p.ldo % 8) == 0 &&
+                           (!p.residual || (p.ldr % 8) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.out ? static_cast<void*>(p.out) : static_cast<void*>(p.out_f32)) & 15) == 0);
+    p.splits = pick_splits(rows, N, p.tiles_n * tiles_m, p.num_kb, num_sms_cached(), can_split);
+    p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
+    p.ws = nullptr;
+    p.ws_split_stride = rows * N;
+    if (p.splits > 1) {
+        const size_t need = static_cast<size_t>(p.splits) * rows * N * sizeof(float);
+        if (g_ws.bytes < need) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cs);
+            if (cs != cudaStreamCaptureStatusNone)
+                return rf_fail(RF_ERR_CUDA, "split-K workspace must be sized by an eager run before stream capture");
+            if (g_ws.ptr) RF_CUDA_TRY(cudaFree(g_ws.ptr));
+            g_ws.ptr = nullptr;
+            g_ws.bytes = 0;
+            RF_CUDA_TRY(cudaMalloc(&g_ws.ptr, need));
+            g_ws.bytes = need;
+        }
+        p.ws = g_ws.ptr;
     }
-    p.tiles_n = (N + 63) / 64;
-    dim3 grid(p.tiles_n, tiles_m, nbatch);
-    return launch<64, 8>(a0, a1, b, p, grid, st);
+    dim3 grid(p.tiles_n * p.splits, tiles_m, nbatch);
+    int rc;
+    if (bn == 160) rc = launch<160, 6>(a0, a1, b, p, grid, st);   // N = 320-type layers: two exact 160-column tiles
+    else if (bn == 128) rc = launch<128, 6>(a0, a1, b, p, grid, st);
+    else rc = launch<64, 8>(a0, a1, b, p, grid, st);
+    if (rc || p.splits == 1) return rc;
+    const long work = rows * (N / 8);
+    const unsigned blocks = static_cast<unsigned>(std::min<long>((work + 255) / 256, 8L * num_sms_cached()));
+    k_splitk_reduce<<<blocks, 256, 0, st>>>(p.ws, p.splits, p.ws_split_stride, rows, N, p.ldo, p.ldr,
+                                            p.conv ? p.Ho * p.Wo : 1, p.alpha, p.bias, p.bias_mode, p.bias2, p.bias2_pitch,
+                                            p.act, p.residual, p.out, p.out_f32);
+    RF_CUDA_LAUNCH_CHECK("k_splitk_reduce");
+    if (g_prof.on) {   // the measured interval of this launch ends after the second stage
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (!g_prof.ev.empty()) RF_CUDA_TRY(cudaEventRecord(g_prof.ev.back(), st));
+    }
+    return RF_OK;
 }
 
 }  // namespace
@@ -466,7 +618,7 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
         int rc = make_map(&ma, d->A, dims, str, box, es);
         if (rc) return rc;
     }
-    const int BN = d->N > 64 ? 128 : 64;
+    const int BN = pick_bn(d->N);
     {
         const long dims[4] = {d->K, d->N, b_m1 ? b1 : 1, b_m2 ? b2 : 1};
         const long str[4] = {1, d->ldb, b_m1 ? d->sb1 : d->ldb, b_m2 ? d->sb2 : d->ldb};
@@ -539,7 +691,7 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     }
     const int taps = d->ksize * d->ksize;
     const long Ktot = static_cast<long>(taps) * (d->C1 + C2);
-    const int BN = d->Cout > 64 ? 128 : 64;
+    const int BN = pick_bn(d->Cout);
     {
         const long dims[4] = {Ktot, d->Cout, 1, 1};
         const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
@@ -592,14 +744,14 @@ extern "C" int rf_tc_profile_end(double* ms_out, double* flops_out, long* launch
     cudaError_t err = cudaDeviceSynchronize();
     FILE* dump = nullptr;
     if (const char* path = getenv("RF_TC_PROFILE_DUMP")) dump = fopen(path, "w");   // per-launch csv for profiles/
-    if (dump) fprintf(dump, "conv,M,N,K,batch,ms\n");
+    if (dump) fprintf(dump, "conv,M,N,K,batch,splits,ms\n");
     for (size_t i = 0; i + 1 < g_prof.ev.size() && err == cudaSuccess; i += 2) {
         float t = 0.f;
         err = cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
         ms += t;
         if (dump && i / 2 < g_prof.recs.size()) {
             const TcProfile::Rec& r = g_prof.recs[i / 2];
-            fprintf(dump, "%d,%d,%d,%d,%d,%.4f\n", r.conv, r.M, r.N, r.K, r.batch, t);
+            fprintf(dump, "%d,%d,%d,%d,%d,%d,%.4f\n", r.conv, r.M, r.N, r.K, r.batch, r.splits, t);
         }
     }
     if (dump) fclose(dump);
