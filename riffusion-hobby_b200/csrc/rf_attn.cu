@@ -342,7 +342,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // TMEM: S0 | S1 | O_A (NV+16 columns) | O_B (NV+16 columns).
 constexpr float RESCALE_LOG2 = 4.f;
 
-template <int DPAD, int NV, int NS>
+template <int DPAD, int NV, int NKS, int NVS>
 __global__ void __launch_bounds__(320, 1)
 k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
@@ -356,14 +356,16 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     constexpr int V_BYTES = 2 * V_SLAB;
     constexpr int P_BYTES = 2 * TQ * 128;
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + Q_BYTES;
-    uint8_t* sV = sK + NS * K_BYTES;
-    uint8_t* sP = sV + NS * V_BYTES;
+    uint8_t* sK = sQ + Q_BYTES;                 // [NKS][K_BYTES]  K tiles are released by their Q K^T (early)
+    uint8_t* sV = sK + NKS * K_BYTES;           // [NVS][V_BYTES]  V^T tiles by their P V (late): separate rings
+    uint8_t* sP = sV + NVS * V_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = kv_full + NS;
-    uint64_t* s_full = kv_empty + NS;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + NKS;
+    uint64_t* v_full = k_empty + NKS;
+    uint64_t* v_empty = v_full + NVS;
+    uint64_t* s_full = v_empty + NVS;
     uint64_t* s_empty = s_full + 2;
     uint64_t* p_full = s_empty + 2;
     uint64_t* p_empty = p_full + 2;
@@ -377,9 +379,13 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         tc::mbar_init(q_full, 1);
-        for (int i = 0; i < NS; ++i) {
-            tc::mbar_init(&kv_full[i], 1);
-            tc::mbar_init(&kv_empty[i], 1);
+        for (int i = 0; i < NKS; ++i) {
+            tc::mbar_init(&k_full[i], 1);
+            tc::mbar_init(&k_empty[i], 1);
+        }
+        for (int i = 0; i < NVS; ++i) {
+            tc::mbar_init(&v_full[i], 1);
+            tc::mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1);
@@ -395,7 +401,7 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         tc::tmem_relinquish();
     }
     // rows NV .. NV+15 of every V^T slab = 1.0 (never touched by the TMA boxes, which are NV rows tall)
-    for (int i = threadIdx.x; i < NS * 2 * 16 * 8; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NVS * 2 * 16 * 8; i += blockDim.x) {
         const int ch = i & 7, r = (i >> 3) & 15, sl = (i >> 7) & 1, st = i >> 8;
         *reinterpret_cast<uint4*>(sV + st * V_BYTES + sl * V_SLAB + (NV + r) * 128 + ch * 16) =
             make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
@@ -412,15 +418,23 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         tc::mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
         for (int s = 0; s < NSLAB; ++s) tc::tma_load_4d(&mapQ, q_full, sQ + s * TQ * 128, s * 64, q_blk * TQ, head, b);
-        for (int j = 0; j < T; ++j) {
-            const int st = j % NS;
-            tc::mbar_wait(&kv_empty[st], ((j / NS) & 1) ^ 1);
-            tc::mbar_expect_tx(&kv_full[st], K_BYTES + 2 * NV * 128);
+        // K runs two tiles ahead of V^T: Q K_{j+2}^T is issued while the softmax of tile j is still running
+        auto load_k = [&](int j) {
+            const int st = j % NKS;
+            tc::mbar_wait(&k_empty[st], ((j / NKS) & 1) ^ 1);
+            tc::mbar_expect_tx(&k_full[st], K_BYTES);
 #pragma unroll
             for (int s = 0; s < NSLAB; ++s)
-                tc::tma_load_4d(&mapK, &kv_full[st], sK + st * K_BYTES + s * TK * 128, s * 64, j * TK, head, b);
-            tc::tma_load_4d(&mapVt, &kv_full[st], sV + st * V_BYTES, j * TK, 0, head, b);
-            tc::tma_load_4d(&mapVt, &kv_full[st], sV + st * V_BYTES + V_SLAB, j * TK + 64, 0, head, b);
+                tc::tma_load_4d(&mapK, &k_full[st], sK + st * K_BYTES + s * TK * 128, s * 64, j * TK, head, b);
+        };
+        for (int j = 0; j < 2 && j < T; ++j) load_k(j);
+        for (int j = 0; j < T; ++j) {
+            if (j + 2 < T) load_k(j + 2);
+            const int st = j % NVS;
+            tc::mbar_wait(&v_empty[st], ((j / NVS) & 1) ^ 1);
+            tc::mbar_expect_tx(&v_full[st], 2 * NV * 128);
+            tc::tma_load_4d(&mapVt, &v_full[st], sV + st * V_BYTES, j * TK, 0, head, b);
+            tc::tma_load_4d(&mapVt, &v_full[st], sV + st * V_BYTES + V_SLAB, j * TK + 64, 0, head, b);
         }
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
@@ -429,14 +443,17 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         tc::mbar_wait(q_full, 0);
         tc::fence_after_sync();
         const uint32_t q_base = tc::smem_u32(sQ);
+        // Event-driven issue: the two softmax groups run independently, so the issuer polls, per group, "scores buffer
+        // released + K tile landed" (next Q K^T of that group) and "P written + V^T tile landed" (next P V of that
+        // group) and issues whatever is ready; neither group ever waits for the other's exponentials.
+        int qk_next[2] = {0, 1}, pv_next[2] = {0, 1};     // next tile of each group needing Q K^T / P V
         int se_cnt[2] = {0, 0}, pe_cnt[2] = {0, 0};
-        auto qk = [&](int j) {                   // S_{j&1} = Q K_j^T
-            const int i = j & 1, st = j % NS;
-            if (se_cnt[i] > 0) {
-                tc::mbar_wait(&s_empty[i], (se_cnt[i] - 1) & 1);
-                tc::fence_after_sync();
-            }
-            tc::mbar_wait(&kv_full[st], (j / NS) & 1);
+        auto try_qk = [&](int i) -> bool {
+            const int j = qk_next[i];
+            if (j >= T) return false;
+            const int st = j % NKS;
+            if (se_cnt[i] > 0 && !tc::mbar_test(&s_empty[i], (se_cnt[i] - 1) & 1)) return false;
+            if (!tc::mbar_test(&k_full[st], (j / NKS) & 1)) return false;
             tc::fence_after_sync();
             const uint32_t k_base = tc::smem_u32(sK + st * K_BYTES);
 #pragma unroll
@@ -446,13 +463,17 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     tc::mma_f16(tmem_base + i * 128, tc::make_desc_sw128(q_base + s * TQ * 128 + k * 32),
                                 tc::make_desc_sw128(k_base + s * TK * 128 + k * 32), idesc_qk, (s | k) ? 1u : 0u);
             tc::mma_commit(&s_full[i]);
+            tc::mma_commit(&k_empty[st]);
             ++se_cnt[i];
+            qk_next[i] = j + 2;
+            return true;
         };
-        constexpr int LA = NS >= 2 ? 2 : 1;
-        for (int j = 0; j < LA && j < T; ++j) qk(j);
-        for (int j = 0; j < T; ++j) {
-            const int i = j & 1, st = j % NS;
-            tc::mbar_wait(&p_full[i], pe_cnt[i] & 1);
+        auto try_pv = [&](int i) -> bool {
+            const int j = pv_next[i];
+            if (j >= T) return false;
+            const int st = j % NVS;
+            if (!tc::mbar_test(&p_full[i], pe_cnt[i] & 1)) return false;
+            if (!tc::mbar_test(&v_full[st], (j / NVS) & 1)) return false;
             tc::fence_after_sync();
             const uint32_t p_base = tc::smem_u32(sP + i * P_BYTES);
             const uint32_t v_base = tc::smem_u32(sV + st * V_BYTES);
@@ -463,9 +484,20 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     tc::mma_f16(tmem_O + i * NVP, tc::make_desc_sw128(p_base + s * TQ * 128 + k * 32),
                                 tc::make_desc_sw128(v_base + s * V_SLAB + k * 32), idesc_pv, ((j >> 1) | s | k) ? 1u : 0u);
             tc::mma_commit(&p_empty[i]);
-            tc::mma_commit(&kv_empty[st]);
+            tc::mma_commit(&v_empty[st]);
             ++pe_cnt[i];
-            if (j + LA < T) qk(j + LA);
+            pv_next[i] = j + 2;
+            return true;
+        };
+        // K and V^T tiles arrive in tile order through shared rings, so a group can run ahead of the other only by the
+        // ring depth; the tile-order guard keeps the rings deadlock-free (a slot is always freed by the oldest tile)
+        while (pv_next[0] < T || pv_next[1] < T) {
+            bool any = false;
+            for (int i = 0; i < 2; ++i) {
+                if (qk_next[i] < T && qk_next[i] - qk_next[i ^ 1] < NKS) any |= try_qk(i);
+                if (pv_next[i] < T && pv_next[i] - pv_next[i ^ 1] < NVS) any |= try_pv(i);
+            }
+            if (!any) __nanosleep(20);
         }
         tc::mma_commit(o_full);
     } else if (warp >= 2) {
@@ -496,12 +528,15 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 for (int i = 0; i < 128; ++i)
                     if (i >= kmax) v[i] = 0xff800000u;   // -inf
             }
-            float mt = __uint_as_float(v[0]);
+            float mx[8];                          // eight independent chains: the maximum is latency, not issue, bound
 #pragma unroll
-            for (int i = 1; i < 128; i += 2) {
-                const float e = i + 1 < 128 ? __uint_as_float(v[i + 1]) : -INFINITY;
-                mt = fmaxf(mt, fmaxf(__uint_as_float(v[i]), e));
-            }
+            for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(v[i]);
+#pragma unroll
+            for (int i = 8; i < 128; i += 16)
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v[i + e]), i + 8 + e < 128 ? __uint_as_float(v[i + 8 + e]) : -INFINITY));
+            const float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
             const bool grow = (mt - m_ref) * c > RESCALE_LOG2;   // always true on the first tile (m_ref = -inf)
             float fac = 1.f;
             if (grow) {
@@ -656,20 +691,24 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     return RF_OK;
 }
 
-template <int DPAD, int NV, int NS>
+template <int DPAD, int NV, int NKS, int NVS>
 int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, dim3 grid,
                  cudaStream_t st) {
     constexpr int NSLAB = DPAD / 64;
     constexpr int V_SLAB = (((NV + 16) * 128 + 1023) / 1024) * 1024;
-    const size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NS) * (NSLAB * TK * 128 + 2 * V_SLAB) +
-                        2 * (2 * TQ * 128) + 256 + 2 * 128 * 4 + 1024;
+    const size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NKS) * NSLAB * TK * 128 +
+                        static_cast<size_t>(NVS) * 2 * V_SLAB + 2 * (2 * TQ * 128) + 256 + 2 * 128 * 4 + 1024;
+    static_assert(static_cast<size_t>(DPAD / 64) * TQ * 128 + static_cast<size_t>(NKS) * (DPAD / 64) * TK * 128 +
+                          static_cast<size_t>(NVS) * 2 * ((((NV + 16) * 128 + 1023) / 1024) * 1024) + 4 * TQ * 128 + 2304 <=
+                      232448,
+                  "shared memory budget");
     static std::once_flag once;
     static cudaError_t aerr = cudaSuccess;
     std::call_once(once, [&] {
-        aerr = cudaFuncSetAttribute(k_flash_attn1<DPAD, NV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        aerr = cudaFuncSetAttribute(k_flash_attn1<DPAD, NV, NKS, NVS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     });
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn1): ") + cudaGetErrorString(aerr));
-    k_flash_attn1<DPAD, NV, NS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
+    k_flash_attn1<DPAD, NV, NKS, NVS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
     RF_CUDA_LAUNCH_CHECK("k_flash_attn1");
     return RF_OK;
 }
@@ -718,11 +757,12 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool two_pass = getenv("RF_ATTN_TWO_PASS") != nullptr;   // A/B switch for the older kernel
     if (!two_pass) {
-        if (d <= 48) return launch_attn1<64, 48, 3>(mq, mk, mv, p, grid, st);
-        if (d <= 64) return launch_attn1<64, 64, 3>(mq, mk, mv, p, grid, st);
-        if (d <= 80) return launch_attn1<128, 80, 2>(mq, mk, mv, p, grid, st);
-        if (d <= 96) return launch_attn1<128, 96, 2>(mq, mk, mv, p, grid, st);
-        if (d <= 112) return launch_attn1<128, 112, 2>(mq, mk, mv, p, grid, st);
+        // K ring / V^T ring depths chosen to fill the 227 KB of shared memory next to Q and the two P tiles
+        if (d <= 48) return launch_attn1<64, 48, 4, 3>(mq, mk, mv, p, grid, st);
+        if (d <= 64) return launch_attn1<64, 64, 4, 3>(mq, mk, mv, p, grid, st);
+        if (d <= 80) return launch_attn1<128, 80, 2, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 96) return launch_attn1<128, 96, 2, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 112) return launch_attn1<128, 112, 2, 2>(mq, mk, mv, p, grid, st);
     }
     if (d <= 48) return launch_attn<64, 48, 3>(mq, mk, mv, p, grid, st);
     if (d <= 64) return launch_attn<64, 64, 3>(mq, mk, mv, p, grid, st);

@@ -29,47 +29,45 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
 // ---------------------------------------------------------------- GroupNorm (NHWC), deterministic
-// pass 1: per (image, slab of 64 pixels, group) partial sum and sum of squares.  Threads read coalesced
-//         half2 channel pairs, park their partials in shared memory, and one thread per group adds them in a
-//         fixed order (no atomics: repeated runs are bit-identical).
+// pass 1: per (image, slab of pixels, group) partial sum and sum of squares.  Threads read 16-byte channel octets,
+//         park their partials in shared memory, and one thread per group adds them in a fixed order (no atomics:
+//         repeated runs are bit-identical).
 // pass 2: one warp per (image, group) adds the slab partials in a fixed order -> (mean, rstd).
 // pass 3: y = (x - mean) * rstd * gamma + beta, optional SiLU.
-template <int MAXK>
-__global__ void k_gn_partial(const __half* __restrict__ x, int HW, int C, int G, int slab, int nslabs,
-                             float* __restrict__ part /*[B][nslabs][G][2]*/) {
-    extern __shared__ float2 shp[];  // [nwarps][C2]
+// Vectorised pass 1 (C % 8 == 0, C <= 2560): blockDim = PPI * C/8 threads; a thread owns 8 fixed channels (one 16-byte
+// load per pixel) and walks every PPI-th pixel of the slab, four loads in flight.  Same deterministic two-level sum.
+__global__ void k_gn_partial_v(const __half* __restrict__ x, int HW, int C, int G, int slab, int nslabs,
+                               float* __restrict__ part /*[B][nslabs][G][2]*/) {
+    extern __shared__ float2 shp[];  // [PPI][C/2]
     const int b = blockIdx.y;
+    const int C8 = C >> 3, C2 = C >> 1;
+    const int c8 = threadIdx.x % C8, pp = threadIdx.x / C8, PPI = blockDim.x / C8;
     const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
-    const int cpg2 = (C / G) >> 1;  // half2 pairs per group
-    const int C2 = C >> 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const __half2* xb = reinterpret_cast<const __half2*>(x + static_cast<size_t>(b) * HW * C);
-    // each lane owns the channel pairs lane, lane+32, ... ; each warp walks its pixels: 128-byte coalesced loads
-    float s[MAXK], ss[MAXK];   // MAXK >= ceil(C/64)
-    const int nk = (C2 + 31) / 32;
+    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C) + c8;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    auto acc = [&](const uint4& v) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k) s[k] = ss[k] = 0.f;
-    for (int p = p0 + warp; p < p1; p += nw) {
-        const __half2* row = xb + static_cast<size_t>(p) * C2;
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) {
-            if (k < nk) {
-                const int c2 = lane + 32 * k;
-                if (c2 < C2) {
-                    const float2 v = __half22float2(row[c2]);
-                    s[k] += v.x + v.y;
-                    ss[k] += v.x * v.x + v.y * v.y;
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            s[j] += f.x + f.y;
+            ss[j] = fmaf(f.x, f.x, fmaf(f.y, f.y, ss[j]));
         }
+    };
+    int p = p0 + pp;
+    for (; p + 3 * PPI < p1; p += 4 * PPI) {
+        const uint4 v0 = xb[static_cast<size_t>(p) * C8], v1 = xb[static_cast<size_t>(p + PPI) * C8];
+        const uint4 v2 = xb[static_cast<size_t>(p + 2 * PPI) * C8], v3 = xb[static_cast<size_t>(p + 3 * PPI) * C8];
+        acc(v0); acc(v1); acc(v2); acc(v3);
     }
+    for (; p < p1; p += PPI) acc(xb[static_cast<size_t>(p) * C8]);
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k)
-        if (k < nk && lane + 32 * k < C2) shp[warp * C2 + lane + 32 * k] = make_float2(s[k], ss[k]);
+    for (int j = 0; j < 4; ++j) shp[pp * C2 + c8 * 4 + j] = make_float2(s[j], ss[j]);
     __syncthreads();
+    const int cpg2 = (C / G) >> 1;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float a = 0.f, q = 0.f;
-        for (int w = 0; w < nw; ++w)
+        for (int w = 0; w < PPI; ++w)
             for (int k = 0; k < cpg2; ++k) {
                 const float2 v = shp[w * C2 + g * cpg2 + k];
                 a += v.x;
@@ -79,6 +77,67 @@ __global__ void k_gn_partial(const __half* __restrict__ x, int HW, int C, int G,
         o[0] = a;
         o[1] = q;
     }
+}
+
+// silu(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU op (tanh.approx, 2^-11 relative) instead of ex2 + rcp
+__device__ __forceinline__ float silu_tanh(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+// Vectorised pass 3, same thread -> channel mapping: the affine form y = x * sc + sh (sc = rstd * gamma,
+// sh = beta - mean * sc) of the thread's 8 channels lives in registers for the whole slab.
+__global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restrict__ stats,
+                             const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int G,
+                             int act, int slab, __half* __restrict__ y) {
+    const int b = blockIdx.y;
+    const int C8 = C >> 3;
+    const int c8 = threadIdx.x % C8, pp = threadIdx.x / C8, PPI = blockDim.x / C8;
+    const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
+    const int cpg = C / G;
+    float sc[8], sh[8];
+    {
+        const uint4 gv = *reinterpret_cast<const uint4*>(gamma + c8 * 8);
+        const uint4 bv = *reinterpret_cast<const uint4*>(beta + c8 * 8);
+        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        const __half* bh = reinterpret_cast<const __half*>(&bv);
+        const float* st = stats + static_cast<size_t>(b) * G * 2;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (c8 * 8 + e) / cpg;
+            const float mean = st[2 * g], rstd = st[2 * g + 1];
+            sc[e] = rstd * __half2float(gh[e]);
+            sh[e] = fmaf(-mean, sc[e], __half2float(bh[e]));
+        }
+    }
+    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C) + c8;
+    uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(b) * HW * C) + c8;
+    auto xf = [&](uint4 v) -> uint4 {
+        __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            float o0 = fmaf(f.x, sc[2 * j], sh[2 * j]), o1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+            if (act) {
+                o0 = silu_tanh(o0);
+                o1 = silu_tanh(o1);
+            }
+            h[j] = __floats2half2_rn(o0, o1);
+        }
+        return v;
+    };
+    int p = p0 + pp;
+    for (; p + 3 * PPI < p1; p += 4 * PPI) {
+        const uint4 v0 = xb[static_cast<size_t>(p) * C8], v1 = xb[static_cast<size_t>(p + PPI) * C8];
+        const uint4 v2 = xb[static_cast<size_t>(p + 2 * PPI) * C8], v3 = xb[static_cast<size_t>(p + 3 * PPI) * C8];
+        yb[static_cast<size_t>(p) * C8] = xf(v0);
+        yb[static_cast<size_t>(p + PPI) * C8] = xf(v1);
+        yb[static_cast<size_t>(p + 2 * PPI) * C8] = xf(v2);
+        yb[static_cast<size_t>(p + 3 * PPI) * C8] = xf(v3);
+    }
+    for (; p < p1; p += PPI) yb[static_cast<size_t>(p) * C8] = xf(xb[static_cast<size_t>(p) * C8]);
 }
 
 __global__ void k_gn_finalize(const float* __restrict__ part, int nslabs, int G, float inv_n, float eps,
@@ -99,44 +158,6 @@ __global__ void k_gn_finalize(const float* __restrict__ part, int nslabs, int G,
         const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
         stats[static_cast<size_t>(bg) * 2] = mean;
         stats[static_cast<size_t>(bg) * 2 + 1] = rsqrtf(var + eps);
-    }
-}
-
-__global__ void k_gn_apply(const __half* __restrict__ x, const float* __restrict__ stats,
-                           const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C,
-                           int G, int act, __half* __restrict__ y) {
-    const int b = blockIdx.y;
-    const size_t n8 = static_cast<size_t>(HW) * C / 8;   // uint4 = 8 halves (C % 8 == 0)
-    const int C8 = C / 8;
-    const int cpg = C / G;
-    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C);
-    uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(b) * HW * C);
-    const float* st = stats + static_cast<size_t>(b) * G * 2;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % C8) * 8;
-        uint4 v = xb[i];
-        const uint4 gv = *reinterpret_cast<const uint4*>(gamma + c0);
-        const uint4 bv = *reinterpret_cast<const uint4*>(beta + c0);
-        __half2* vh = reinterpret_cast<__half2*>(&v);
-        const __half2* gh = reinterpret_cast<const __half2*>(&gv);
-        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int g = (c0 + 2 * j) / cpg;           // cpg is even: a half2 never straddles two groups
-            const float mean = st[2 * g], rstd = st[2 * g + 1];
-            const float2 xv = __half22float2(vh[j]);
-            const float2 ga = __half22float2(gh[j]);
-            const float2 be = __half22float2(bh[j]);
-            float o0 = (xv.x - mean) * rstd * ga.x + be.x;
-            float o1 = (xv.y - mean) * rstd * ga.y + be.y;
-            if (act) {
-                o0 = silu(o0);
-                o1 = silu(o1);
-            }
-            vh[j] = __floats2half2_rn(o0, o1);
-        }
-        yb[i] = v;
     }
 }
 
@@ -616,35 +637,29 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
         ((C / groups) & 1))
         return rf_fail(RF_ERR_INVALID, "rf_group_norm_f16: bad argument (channels per group must be even)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int slab = 32;
+    if (C > 2560 || (C % 8)) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: C must be a multiple of 8, <= 2560");
+    const int nbg = B * groups;
+    if (nbg % 8) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: B*groups must be a multiple of 8");
+    // thread -> (pixel phase, 8-channel column): blockDim = PPI * C/8 (<= 320 threads)
+    const int C8 = C / 8;
+    const int PPI = C8 >= 256 ? 1 : 256 / C8;
+    const int threads = PPI * C8;
+    // slab: >= 32 pixels (the scratch is sized for HW/32 slabs); large images take longer slabs (still >= 4 waves)
+    int slab = 32;
+    while (slab < 256 && static_cast<long>(B) * (HW / (2 * slab)) >= 4 * 148) slab *= 2;
     const int nslabs = (HW + slab - 1) / slab;
     float* stats = d_scratch;                                          // [B][G][2]
     float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
-    const int C2 = C / 2;
-    if (C > 2560 || (C % 8)) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: C must be a multiple of 8, <= 2560");
-    const size_t smem = static_cast<size_t>(8) * C2 * sizeof(float2);
-    static bool attr = false;
-    if (!attr) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(k_gn_partial<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        RF_CUDA_TRY(cudaFuncSetAttribute(k_gn_partial<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
-    }
+    const size_t smem = static_cast<size_t>(PPI) * (C / 2) * sizeof(float2);
     dim3 grid(nslabs, B);
-    const __half* xh = static_cast<const __half*>(x);
-    if (C <= 320) k_gn_partial<5><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
-    else if (C <= 640) k_gn_partial<10><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
-    else if (C <= 1280) k_gn_partial<20><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
-    else k_gn_partial<40><<<grid, 256, smem, st>>>(xh, HW, C, groups, slab, nslabs, part);
-    RF_CUDA_LAUNCH_CHECK("k_gn_partial");
-    const int nbg = B * groups;
-    if (nbg % 8) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: B*groups must be a multiple of 8");
+    k_gn_partial_v<<<grid, threads, smem, st>>>(static_cast<const __half*>(x), HW, C, groups, slab, nslabs, part);
+    RF_CUDA_LAUNCH_CHECK("k_gn_partial_v");
     k_gn_finalize<<<nbg / 8, 256, 0, st>>>(part, nslabs, groups, 1.f / (static_cast<float>(HW) * (C / groups)), eps, stats);
     RF_CUDA_LAUNCH_CHECK("k_gn_finalize");
-    const size_t n8 = static_cast<size_t>(HW) * C / 8;
-    dim3 grid2(static_cast<unsigned>(std::min<size_t>((n8 + 255) / 256, 4096)), B);
-    k_gn_apply<<<grid2, 256, 0, st>>>(static_cast<const __half*>(x), stats, static_cast<const __half*>(gamma),
-                                      static_cast<const __half*>(beta), HW, C, groups, act, static_cast<__half*>(y));
-    RF_CUDA_LAUNCH_CHECK("k_gn_apply");
+    k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), stats, static_cast<const __half*>(gamma),
+                                           static_cast<const __half*>(beta), HW, C, groups, act, slab,
+                                           static_cast<__half*>(y));
+    RF_CUDA_LAUNCH_CHECK("k_gn_apply_v");
     return RF_OK;
 }
 
