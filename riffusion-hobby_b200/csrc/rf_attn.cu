@@ -342,36 +342,43 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // TMEM: S0 | S1 | O_A (NV+16 columns) | O_B (NV+16 columns).
 constexpr float RESCALE_LOG2 = 4.f;
 
-template <int DPAD, int NV, int NKS, int NVS>
-__global__ void __launch_bounds__(320, 1)
+// NG softmax groups (2 or 4) take the key tiles round-robin; a tile is TKT = 256/NG keys, so the NG score buffers always
+// fill TMEM columns [0, 256) and O_g sits at 256 + g*(NV+16).  NG = 4 (head dim <= 48) puts four independent warps on
+// every SM sub-partition: while one waits for its scores or drains TMEM (tcgen05.ld, 64 B/clk per SM), the others keep
+// the MUFU pipe busy — with NG = 2 each sub-partition has only two warps and the phases of a warp run back to back.
+template <int DPAD, int NV, int NKS, int NVS, int NG>
+__global__ void __launch_bounds__(96 + 128 * NG, 1)
 k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int TKT = 256 / NG;                                 // keys per tile
+    constexpr int KSL = TKT / 64;                                 // 64-key slabs per tile (P and V^T)
     constexpr int NSLAB = DPAD / 64;
     constexpr int NVP = NV + 16;                                  // head dim columns + the row-sum column block
-    static_assert(256 + 2 * NVP <= 512, "TMEM budget");
+    static_assert(NG == 2 || NG == 4, "two or four softmax groups");
+    static_assert(256 + NG * NVP <= 512, "TMEM budget");
     constexpr int Q_BYTES = NSLAB * TQ * 128;
-    constexpr int K_BYTES = NSLAB * TK * 128;
+    constexpr int K_BYTES = NSLAB * TKT * 128;
     constexpr int V_SLAB = ((NVP * 128 + 1023) / 1024) * 1024;
-    constexpr int V_BYTES = 2 * V_SLAB;
-    constexpr int P_BYTES = 2 * TQ * 128;
+    constexpr int V_BYTES = KSL * V_SLAB;
+    constexpr int P_BYTES = KSL * TQ * 128;
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + Q_BYTES;                 // [NKS][K_BYTES]  K tiles are released by their Q K^T (early)
     uint8_t* sV = sK + NKS * K_BYTES;           // [NVS][V_BYTES]  V^T tiles by their P V (late): separate rings
-    uint8_t* sP = sV + NVS * V_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint8_t* sP = sV + NVS * V_BYTES;           // [NG][P_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NG * P_BYTES);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = k_full + NKS;
     uint64_t* v_full = k_empty + NKS;
     uint64_t* v_empty = v_full + NVS;
     uint64_t* s_full = v_empty + NVS;
-    uint64_t* s_empty = s_full + 2;
-    uint64_t* p_full = s_empty + 2;
-    uint64_t* p_empty = p_full + 2;
-    uint64_t* o_full = p_empty + 2;
+    uint64_t* s_empty = s_full + NG;
+    uint64_t* p_full = s_empty + NG;
+    uint64_t* p_empty = p_full + NG;
+    uint64_t* o_full = p_empty + NG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-    float* xchg = reinterpret_cast<float*>(tmem_slot + 2);       // [2][128] reference maxima of the two groups
+    float* xchg = reinterpret_cast<float*>(tmem_slot + 2);       // [NG][128] reference maxima of the groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -387,7 +394,7 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             tc::mbar_init(&v_full[i], 1);
             tc::mbar_init(&v_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NG; ++i) {
             tc::mbar_init(&s_full[i], 1);
             tc::mbar_init(&s_empty[i], 128);
             tc::mbar_init(&p_full[i], 128);
@@ -401,8 +408,8 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         tc::tmem_relinquish();
     }
     // rows NV .. NV+15 of every V^T slab = 1.0 (never touched by the TMA boxes, which are NV rows tall)
-    for (int i = threadIdx.x; i < NVS * 2 * 16 * 8; i += blockDim.x) {
-        const int ch = i & 7, r = (i >> 3) & 15, sl = (i >> 7) & 1, st = i >> 8;
+    for (int i = threadIdx.x; i < NVS * KSL * 16 * 8; i += blockDim.x) {
+        const int ch = i & 7, r = (i >> 3) & 15, sl = (i >> 7) % KSL, st = (i >> 7) / KSL;
         *reinterpret_cast<uint4*>(sV + st * V_BYTES + sl * V_SLAB + (NV + r) * 128 + ch * 16) =
             make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
     }
@@ -418,89 +425,113 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         tc::mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
         for (int s = 0; s < NSLAB; ++s) tc::tma_load_4d(&mapQ, q_full, sQ + s * TQ * 128, s * 64, q_blk * TQ, head, b);
-        // K runs two tiles ahead of V^T: Q K_{j+2}^T is issued while the softmax of tile j is still running
+        // K runs NG tiles ahead of V^T: the next Q K^T of a group is issued while its softmax is still running
         auto load_k = [&](int j) {
             const int st = j % NKS;
             tc::mbar_wait(&k_empty[st], ((j / NKS) & 1) ^ 1);
             tc::mbar_expect_tx(&k_full[st], K_BYTES);
 #pragma unroll
             for (int s = 0; s < NSLAB; ++s)
-                tc::tma_load_4d(&mapK, &k_full[st], sK + st * K_BYTES + s * TK * 128, s * 64, j * TK, head, b);
+                tc::tma_load_4d(&mapK, &k_full[st], sK + st * K_BYTES + s * TKT * 128, s * 64, j * TKT, head, b);
         };
-        for (int j = 0; j < 2 && j < T; ++j) load_k(j);
+        for (int j = 0; j < NG && j < T; ++j) load_k(j);
         for (int j = 0; j < T; ++j) {
-            if (j + 2 < T) load_k(j + 2);
+            if (j + NG < T) load_k(j + NG);
             const int st = j % NVS;
             tc::mbar_wait(&v_empty[st], ((j / NVS) & 1) ^ 1);
-            tc::mbar_expect_tx(&v_full[st], 2 * NV * 128);
-            tc::tma_load_4d(&mapVt, &v_full[st], sV + st * V_BYTES, j * TK, 0, head, b);
-            tc::tma_load_4d(&mapVt, &v_full[st], sV + st * V_BYTES + V_SLAB, j * TK + 64, 0, head, b);
+            tc::mbar_expect_tx(&v_full[st], KSL * NV * 128);
+#pragma unroll
+            for (int s = 0; s < KSL; ++s)
+                tc::tma_load_4d(&mapVt, &v_full[st], sV + st * V_BYTES + s * V_SLAB, j * TKT + 64 * s, 0, head, b);
         }
     } else if (warp == 1 && lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc_qk = tc::make_idesc_f16(TQ, TK);
-        constexpr uint32_t idesc_pv = tc::make_idesc_f16(TQ, NVP);
+        // ------------------------------------------------------------------ Q K^T issuer
+        // Two issuing threads (this one and the P V issuer in the last warp): a single thread spends ~1000 cycles per
+        // 128-key tile on descriptors, polling and commits for the 12 MMAs, which is the whole MUFU budget of the tile.
+        // Both are event driven: they poll, per softmax group, whether that group's next MMA can go and issue whatever
+        // is ready, so no group ever waits for another group's exponentials.
+        constexpr uint32_t idesc_qk = tc::make_idesc_f16(TQ, TKT);
         tc::mbar_wait(q_full, 0);
         tc::fence_after_sync();
-        const uint32_t q_base = tc::smem_u32(sQ);
-        // Event-driven issue: the two softmax groups run independently, so the issuer polls, per group, "scores buffer
-        // released + K tile landed" (next Q K^T of that group) and "P written + V^T tile landed" (next P V of that
-        // group) and issues whatever is ready; neither group ever waits for the other's exponentials.
-        int qk_next[2] = {0, 1}, pv_next[2] = {0, 1};     // next tile of each group needing Q K^T / P V
-        int se_cnt[2] = {0, 0}, pe_cnt[2] = {0, 0};
-        auto try_qk = [&](int i) -> bool {
-            const int j = qk_next[i];
-            if (j >= T) return false;
-            const int st = j % NKS;
-            if (se_cnt[i] > 0 && !tc::mbar_test(&s_empty[i], (se_cnt[i] - 1) & 1)) return false;
-            if (!tc::mbar_test(&k_full[st], (j / NKS) & 1)) return false;
-            tc::fence_after_sync();
-            const uint32_t k_base = tc::smem_u32(sK + st * K_BYTES);
+        const uint32_t q_lo = tc::desc_lo_sw128(tc::smem_u32(sQ));
+        int qk_next[NG], se_cnt[NG];
 #pragma unroll
-            for (int s = 0; s < NSLAB; ++s)
+        for (int i = 0; i < NG; ++i) {
+            qk_next[i] = i;
+            se_cnt[i] = 0;
+        }
+        // K tiles arrive in tile order through a ring: a tile may only be issued while it is less than a ring depth
+        // ahead of the oldest tile not yet issued (whose completion frees the next slot)
+        for (;;) {
+            int qk_min = T;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc::mma_f16(tmem_base + i * 128, tc::make_desc_sw128(q_base + s * TQ * 128 + k * 32),
-                                tc::make_desc_sw128(k_base + s * TK * 128 + k * 32), idesc_qk, (s | k) ? 1u : 0u);
-            tc::mma_commit(&s_full[i]);
-            tc::mma_commit(&k_empty[st]);
-            ++se_cnt[i];
-            qk_next[i] = j + 2;
-            return true;
-        };
-        auto try_pv = [&](int i) -> bool {
-            const int j = pv_next[i];
-            if (j >= T) return false;
-            const int st = j % NVS;
-            if (!tc::mbar_test(&p_full[i], pe_cnt[i] & 1)) return false;
-            if (!tc::mbar_test(&v_full[st], (j / NVS) & 1)) return false;
-            tc::fence_after_sync();
-            const uint32_t p_base = tc::smem_u32(sP + i * P_BYTES);
-            const uint32_t v_base = tc::smem_u32(sV + st * V_BYTES);
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc::mma_f16(tmem_O + i * NVP, tc::make_desc_sw128(p_base + s * TQ * 128 + k * 32),
-                                tc::make_desc_sw128(v_base + s * V_SLAB + k * 32), idesc_pv, ((j >> 1) | s | k) ? 1u : 0u);
-            tc::mma_commit(&p_empty[i]);
-            tc::mma_commit(&v_empty[st]);
-            ++pe_cnt[i];
-            pv_next[i] = j + 2;
-            return true;
-        };
-        // K and V^T tiles arrive in tile order through shared rings, so a group can run ahead of the other only by the
-        // ring depth; the tile-order guard keeps the rings deadlock-free (a slot is always freed by the oldest tile)
-        while (pv_next[0] < T || pv_next[1] < T) {
+            for (int i = 0; i < NG; ++i) qk_min = min(qk_min, qk_next[i]);
+            if (qk_min >= T) break;
             bool any = false;
-            for (int i = 0; i < 2; ++i) {
-                if (qk_next[i] < T && qk_next[i] - qk_next[i ^ 1] < NKS) any |= try_qk(i);
-                if (pv_next[i] < T && pv_next[i] - pv_next[i ^ 1] < NVS) any |= try_pv(i);
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                const int j = qk_next[i];
+                if (j >= T || j - qk_min >= NKS) continue;
+                const int st = j % NKS;
+                if (se_cnt[i] > 0 && !tc::mbar_test(&s_empty[i], (se_cnt[i] - 1) & 1)) continue;   // scores still being read
+                if (!tc::mbar_test(&k_full[st], (j / NKS) & 1)) continue;
+                tc::fence_after_sync();
+                const uint32_t k_lo = tc::desc_lo_sw128(tc::smem_u32(sK + st * K_BYTES));
+#pragma unroll
+                for (int s = 0; s < NSLAB; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_f16_lo(tmem_base + i * TKT, q_lo + ((s * TQ * 128 + k * 32) >> 4),
+                                       k_lo + ((s * TKT * 128 + k * 32) >> 4), idesc_qk, (s | k) ? 1u : 0u);
+                tc::mma_commit(&s_full[i]);
+                tc::mma_commit(&k_empty[st]);
+                ++se_cnt[i];
+                qk_next[i] = j + NG;
+                any = true;
+            }
+            if (!any) __nanosleep(20);
+        }
+    } else if (warp == 2 + 4 * NG && lane == 0) {
+        // ------------------------------------------------------------------ P V issuer
+        constexpr uint32_t idesc_pv = tc::make_idesc_f16(TQ, NVP);
+        int pv_next[NG], pe_cnt[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            pv_next[i] = i;
+            pe_cnt[i] = 0;
+        }
+        for (;;) {
+            int pv_min = T;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) pv_min = min(pv_min, pv_next[i]);
+            if (pv_min >= T) break;
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                const int j = pv_next[i];
+                if (j >= T || j - pv_min >= NVS) continue;
+                const int st = j % NVS;
+                if (!tc::mbar_test(&p_full[i], pe_cnt[i] & 1)) continue;
+                if (!tc::mbar_test(&v_full[st], (j / NVS) & 1)) continue;
+                tc::fence_after_sync();
+                const uint32_t p_lo = tc::desc_lo_sw128(tc::smem_u32(sP + i * P_BYTES));
+                const uint32_t v_lo = tc::desc_lo_sw128(tc::smem_u32(sV + st * V_BYTES));
+#pragma unroll
+                for (int s = 0; s < KSL; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_f16_lo(tmem_O + i * NVP, p_lo + ((s * TQ * 128 + k * 32) >> 4),
+                                       v_lo + ((s * V_SLAB + k * 32) >> 4), idesc_pv, ((j >= NG) | s | k) ? 1u : 0u);
+                tc::mma_commit(&p_empty[i]);
+                tc::mma_commit(&v_empty[st]);
+                ++pe_cnt[i];
+                pv_next[i] = j + NG;
+                any = true;
             }
             if (!any) __nanosleep(20);
         }
         tc::mma_commit(o_full);
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 2 + 4 * NG) {
         // ------------------------------------------------------------------ softmax groups
         const int g = (warp - 2) >> 2;
         const int q = warp & 3;
@@ -511,31 +542,30 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         int sf_phase = 0, pe_phase = 0, n_mine = 0;
         float m_ref = -INFINITY;                 // reference maximum (raw score units) of this group
         uint8_t* myP = sP + g * P_BYTES;
-        for (int j = g; j < T; j += 2, ++n_mine) {
+        for (int j = g; j < T; j += NG, ++n_mine) {
             tc::mbar_wait(&s_full[g], sf_phase);
             sf_phase ^= 1;
             tc::fence_after_sync();
-            uint32_t v[128];
+            uint32_t v[TKT];
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) tc::tmem_ld_32x32(t_row + g * 128 + c0, v + c0);
+            for (int c0 = 0; c0 < TKT; c0 += 32) tc::tmem_ld_32x32(t_row + g * TKT + c0, v + c0);
             tc::tmem_wait_ld();
             tc::fence_before_sync();
             tc::mbar_arrive(&s_empty[g]);        // the scores are in registers: the next Q K^T may overwrite S
-            const int kmax = p.Nk - j * TK;
-            const bool ragged = kmax < TK;
-            if (ragged) {
+            const int kmax = p.Nk - j * TKT;
+            if (kmax < TKT) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
+                for (int i = 0; i < TKT; ++i)
                     if (i >= kmax) v[i] = 0xff800000u;   // -inf
             }
             float mx[8];                          // eight independent chains: the maximum is latency, not issue, bound
 #pragma unroll
             for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(v[i]);
 #pragma unroll
-            for (int i = 8; i < 128; i += 16)
+            for (int i = 8; i < TKT; i += 16)
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                    mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v[i + e]), i + 8 + e < 128 ? __uint_as_float(v[i + 8 + e]) : -INFINITY));
+                    mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v[i + e]), i + 8 + e < TKT ? __uint_as_float(v[i + 8 + e]) : -INFINITY));
             const float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
             const bool grow = (mt - m_ref) * c > RESCALE_LOG2;   // always true on the first tile (m_ref = -inf)
             float fac = 1.f;
@@ -562,15 +592,23 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             }
             const float mc = m_ref * c;
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 8) {
+            for (int c0 = 0; c0 < TKT; c0 += 8) {
                 uint32_t pk[4];
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
-                    // two exponentials per MUFU op; the argument (<= RESCALE_LOG2) is formed in fp32, rounded once
+                    // the argument (<= RESCALE_LOG2) is formed in fp32 and rounded once to fp16; P is fp16 anyway
                     const float a0 = fmaf(__uint_as_float(v[c0 + i]), c, -mc);
                     const float a1 = fmaf(__uint_as_float(v[c0 + i + 1]), c, -mc);
+#ifdef RF_ATTN_EXP_F16X2
                     const __half2 arg = __floats2half2_rn(a0, a1);
                     asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i >> 1]) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+#else
+                    float e0, e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+                    const __half2 h = __floats2half2_rn(e0, e1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+#endif
                 }
                 const int slab = c0 >> 6, chunk = (c0 & 63) >> 3;
                 *reinterpret_cast<uint4*>(myP + slab * TQ * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) =
@@ -580,32 +618,49 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             tc::fence_before_sync();             // orders the tcgen05.st of a rescale before the P V issued after p_full
             tc::mbar_arrive(&p_full[g]);
         }
-        // ---- epilogue: merge the two groups' accumulators
-        xchg[g * 128 + row] = m_ref;
-        named_bar_sync(1, 256);
-        const bool haveB = T > 1;
-        const float mA = xchg[row], mB = haveB ? xchg[128 + row] : -INFINITY;
-        const float mm = fmaxf(mA, mB);
-        const float fA = exp2f((mA - mm) * c), fB = haveB ? exp2f((mB - mm) * c) : 0.f;
+        // ---- epilogue: merge the groups' accumulators
+        xchg[g * 128 + row] = m_ref;             // -inf for a group that saw no tile
+        named_bar_sync(1, 128 * NG);
+        float mg[NG], fg[NG];
+        float mm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            mg[i] = i < T ? xchg[i * 128 + row] : -INFINITY;
+            mm = fmaxf(mm, mg[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NG; ++i) fg[i] = i < T ? exp2f((mg[i] - mm) * c) : 0.f;
         tc::mbar_wait(o_full, 0);
         tc::fence_after_sync();
-        float inv;
-        {
-            uint32_t la[16], lb[16];
-            tmem_ld16(t_row + 256 + NV, la);
-            if (haveB) tmem_ld16(t_row + 256 + NVP + NV, lb);
-            tc::tmem_wait_ld();
-            inv = 1.f / (__uint_as_float(la[0]) * fA + (haveB ? __uint_as_float(lb[0]) * fB : 0.f));
+        float lsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            if (i < T) {                          // accumulators of groups without a tile were never written
+                uint32_t l16[16];
+                tmem_ld16(t_row + 256 + i * NVP + NV, l16);
+                tc::tmem_wait_ld();
+                lsum = fmaf(__uint_as_float(l16[0]), fg[i], lsum);
+            }
         }
+        const float inv = 1.f / lsum;
         const int qi = q_blk * TQ + row;
         __half* dst = p.out + (static_cast<long>(b) * p.Nq + qi) * p.out_pitch + head * p.d;
-        const float wA = fA * inv, wB = fB * inv;
 #pragma unroll 1
-        for (int c0 = g * 16; c0 < NV; c0 += 32) {   // the groups take alternate 16-column chunks
-            uint32_t oa[16], ob[16];
-            tmem_ld16(t_row + 256 + c0, oa);
-            if (haveB) tmem_ld16(t_row + 256 + NVP + c0, ob);
-            tc::tmem_wait_ld();
+        for (int c0 = g * 16; c0 < NV; c0 += 16 * NG) {   // the groups take the 16-column chunks round-robin
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                if (i < T) {
+                    uint32_t o[16];
+                    tmem_ld16(t_row + 256 + i * NVP + c0, o);
+                    tc::tmem_wait_ld();
+                    const float w = fg[i] * inv;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] = fmaf(__uint_as_float(o[e]), w, acc[e]);
+                }
+            }
             if (qi < p.Nq) {
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
@@ -614,12 +669,7 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            float x0 = __uint_as_float(oa[8 * ch + 2 * e]) * wA, x1 = __uint_as_float(oa[8 * ch + 2 * e + 1]) * wA;
-                            if (haveB) {
-                                x0 = fmaf(__uint_as_float(ob[8 * ch + 2 * e]), wB, x0);
-                                x1 = fmaf(__uint_as_float(ob[8 * ch + 2 * e + 1]), wB, x1);
-                            }
-                            const __half2 h = __floats2half2_rn(x0, x1);
+                            const __half2 h = __floats2half2_rn(acc[8 * ch + 2 * e], acc[8 * ch + 2 * e + 1]);
                             pk[e] = *reinterpret_cast<const uint32_t*>(&h);
                         }
                         *reinterpret_cast<uint4*>(dst + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -691,24 +741,22 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     return RF_OK;
 }
 
-template <int DPAD, int NV, int NKS, int NVS>
+template <int DPAD, int NV, int NKS, int NVS, int NG>
 int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, dim3 grid,
                  cudaStream_t st) {
-    constexpr int NSLAB = DPAD / 64;
+    constexpr int NSLAB = DPAD / 64, TKT = 256 / NG, KSL = TKT / 64;
     constexpr int V_SLAB = (((NV + 16) * 128 + 1023) / 1024) * 1024;
-    const size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NKS) * NSLAB * TK * 128 +
-                        static_cast<size_t>(NVS) * 2 * V_SLAB + 2 * (2 * TQ * 128) + 256 + 2 * 128 * 4 + 1024;
-    static_assert(static_cast<size_t>(DPAD / 64) * TQ * 128 + static_cast<size_t>(NKS) * (DPAD / 64) * TK * 128 +
-                          static_cast<size_t>(NVS) * 2 * ((((NV + 16) * 128 + 1023) / 1024) * 1024) + 4 * TQ * 128 + 2304 <=
-                      232448,
-                  "shared memory budget");
+    constexpr size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NKS) * NSLAB * TKT * 128 +
+                            static_cast<size_t>(NVS) * KSL * V_SLAB + static_cast<size_t>(NG) * KSL * TQ * 128 + 512 +
+                            NG * 128 * 4 + 1024;
+    static_assert(smem <= 232448, "shared memory budget");
     static std::once_flag once;
     static cudaError_t aerr = cudaSuccess;
     std::call_once(once, [&] {
-        aerr = cudaFuncSetAttribute(k_flash_attn1<DPAD, NV, NKS, NVS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        aerr = cudaFuncSetAttribute(k_flash_attn1<DPAD, NV, NKS, NVS, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     });
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn1): ") + cudaGetErrorString(aerr));
-    k_flash_attn1<DPAD, NV, NKS, NVS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
+    k_flash_attn1<DPAD, NV, NKS, NVS, NG><<<grid, 96 + 128 * NG, smem, st>>>(mq, mk, mv, p);
     RF_CUDA_LAUNCH_CHECK("k_flash_attn1");
     return RF_OK;
 }
@@ -723,6 +771,11 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
         return rf_fail(RF_ERR_INVALID, "rf_attention_f16: bad argument");
     if (d > 192) return rf_fail(RF_ERR_UNSUPPORTED, "rf_attention_f16: head dim > 192 (use the GEMM + softmax path)");
     const long C = static_cast<long>(heads) * d;
+    static const bool two_pass = getenv("RF_ATTN_TWO_PASS") != nullptr;   // A/B switch for the older kernel
+    static const bool two_groups = getenv("RF_ATTN_TWO_GROUPS") != nullptr;     // A/B switch (four groups: 766 vs 830 us)
+    const bool one_pass = !two_pass && d <= 112;
+    const int ng = (one_pass && d <= 48 && !two_groups) ? 4 : 2;         // softmax groups; key tile = 256 / ng keys
+    const int tkt = one_pass ? 256 / ng : TK;
     CUtensorMap mq, mk, mv;
     {
         const long dims[4] = {d, Nq, heads, B};
@@ -734,7 +787,7 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     {
         const long dims[4] = {d, Nk, heads, B};
         const long str[4] = {1, C, d, static_cast<long>(Nk) * C};
-        const int box[4] = {64, TK, 1, 1};
+        const int box[4] = {64, tkt, 1, 1};
         int rc = map4(&mk, k, dims, str, box);
         if (rc) return rc;
     }
@@ -749,20 +802,20 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     }
     AttnParams p;
     p.Nq = Nq; p.Nk = Nk; p.d = d; p.heads = heads;
-    p.n_tiles = (Nk + TK - 1) / TK;
+    p.n_tiles = (Nk + tkt - 1) / tkt;
     p.c = scale * 1.4426950408889634f;
     p.out = static_cast<__half*>(out);
     p.out_pitch = C;
     dim3 grid((Nq + TQ - 1) / TQ, heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const bool two_pass = getenv("RF_ATTN_TWO_PASS") != nullptr;   // A/B switch for the older kernel
-    if (!two_pass) {
-        // K ring / V^T ring depths chosen to fill the 227 KB of shared memory next to Q and the two P tiles
-        if (d <= 48) return launch_attn1<64, 48, 4, 3>(mq, mk, mv, p, grid, st);
-        if (d <= 64) return launch_attn1<64, 64, 4, 3>(mq, mk, mv, p, grid, st);
-        if (d <= 80) return launch_attn1<128, 80, 2, 2>(mq, mk, mv, p, grid, st);
-        if (d <= 96) return launch_attn1<128, 96, 2, 2>(mq, mk, mv, p, grid, st);
-        if (d <= 112) return launch_attn1<128, 112, 2, 2>(mq, mk, mv, p, grid, st);
+    if (one_pass) {
+        // ring depths fill the 227 KB of shared memory next to Q and the P tiles
+        if (ng == 4) return launch_attn1<64, 48, 8, 6, 4>(mq, mk, mv, p, grid, st);
+        if (d <= 48) return launch_attn1<64, 48, 4, 3, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 64) return launch_attn1<64, 64, 4, 3, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 80) return launch_attn1<128, 80, 2, 2, 2>(mq, mk, mv, p, grid, st);
+        if (d <= 96) return launch_attn1<128, 96, 2, 2, 2>(mq, mk, mv, p, grid, st);
+        return launch_attn1<128, 112, 2, 2, 2>(mq, mk, mv, p, grid, st);
     }
     if (d <= 48) return launch_attn<64, 48, 3>(mq, mk, mv, p, grid, st);
     if (d <= 64) return launch_attn<64, 64, 3>(mq, mk, mv, p, grid, st);

@@ -194,6 +194,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const int q = warp & 3;
         const int half_id = (warp - 2) >> 2;
         const int row = q * 32 + lane;      // row of the 128-row tile == TMEM lane
+        // 64 bytes (one 32-column run of fp16 side input): two 256-bit loads when 32-byte aligned, else four 128-bit
+        auto ld64 = [](const __half* src, uint4* q4) {
+            if ((reinterpret_cast<uintptr_t>(src) & 31) == 0) {
+                tc::ld_global_256(src, q4[0], q4[1]);
+                tc::ld_global_256(src + 16, q4[2], q4[3]);
+            } else {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q4[j] = s4[j];
+            }
+        };
         int lt = 0;
         for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++lt) {
             const int tile = unit / p.splits, sp = unit - tile * p.splits;
@@ -248,10 +259,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 // per-column bias and per-image bias: 16-byte loads when the 32-column run is complete and aligned
                 if (p.bias_mode == 1) {
                     if (full && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0)) {
-                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+                        uint4 q4[4];
+                        ld64(p.bias + n0, q4);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 bv = bp[j];
+                            const uint4 bv = q4[j];
                             const __half2* bh = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -268,10 +280,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 if (p.bias2) {
                     const __half* b2p = p.bias2 + static_cast<long>(img) * p.bias2_pitch + n0;
                     if (full && ((reinterpret_cast<uintptr_t>(b2p) & 15) == 0)) {
-                        const uint4* bp = reinterpret_cast<const uint4*>(b2p);
+                        uint4 q4[4];
+                        ld64(b2p, q4);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 bv = bp[j];
+                            const uint4 bv = q4[j];
                             const __half2* bh = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -298,8 +311,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                         const __half2 h = __floats2half2_rn(y0, y1);
                         pk[j] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+                        tc::st_global_256(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                    } else {
+                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
                     continue;
                 }
                 if (p.act) {
@@ -309,10 +326,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 if (p.residual) {
                     const __half* rp = p.residual + res_off + n0;
                     if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-                        const uint4* r4 = reinterpret_cast<const uint4*>(rp);
+                        uint4 q4[4];
+                        ld64(rp, q4);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 rv = r4[j];
+                            const uint4 rv = q4[j];
                             const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -331,18 +349,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                         if (n0 + i < p.N) p.out_f32[out_off + n0 + i] = f[i];
                 } else if (full && ((reinterpret_cast<uintptr_t>(p.out + out_off + n0) & 15) == 0)) {
                     uint4* dst = reinterpret_cast<uint4*>(p.out + out_off + n0);
+                    uint4 pk[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
                         __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
                         __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
                         __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        dst[i] = pk;
+                        pk[i].x = *reinterpret_cast<uint32_t*>(&h0);
+                        pk[i].y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk[i].z = *reinterpret_cast<uint32_t*>(&h2);
+                        pk[i].w = *reinterpret_cast<uint32_t*>(&h3);
+                    }
+                    if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {   // whole 32-byte sectors per store
+                        tc::st_global_256(dst, pk[0], pk[1]);
+                        tc::st_global_256(dst + 2, pk[2], pk[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = pk[i];
                     }
                 } else {
                     for (int i = 0; i < 32; ++i)

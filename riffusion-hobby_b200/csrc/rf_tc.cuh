@@ -128,6 +128,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread per instruction.  Row-per-
+// thread epilogues write 64-byte runs; with 128-bit stores every sector is written twice as two partial 16-byte halves.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(ptr));
+}
+
 // ------------------------------------------------------------------ descriptors
 // K-major operand tile, rows of 64 fp16 (128 B) with 128-byte swizzle: 8-row atoms of 1024 B.
 //   start address >> 4 | LBO (unused for swizzled K-major, 1) << 16 | SBO (1024 B >> 4) << 32 |
@@ -141,6 +154,26 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// low word of that descriptor; +2 per 32 bytes of start address (the high word is the constant DESC_SW128_HI)
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+constexpr uint32_t DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+// same MMA with the descriptors given by their low words: the single issuing thread spends ~3 instructions per MMA
+// on operands instead of rebuilding two 64-bit descriptors (matters when one thread feeds 12+ MMAs per key tile)
+__device__ __forceinline__ void mma_f16_lo(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(DESC_SW128_HI)
+        : "memory");
+}
+
 // kind::f16, fp16 A/B (format 0), fp32 accumulate (c_format 1), both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
