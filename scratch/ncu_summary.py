@@ -1,0 +1,29 @@
+"""Key counters of every kernel in an .ncu-rep (ncu --set full) -> JSON for profiles/.
+usage: python scratch/ncu_summary.py rep.ncu-rep "command that produced it" > profiles/xxx.json"""
+import csv, io, json, subprocess, sys
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "lts__t_sector_hit_rate.pct",
+]
+rep, cmd = sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else ""
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+out = {"command": cmd, "kernels": []}
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    k = {"Kernel Name": d.get("Kernel Name", "")}
+    for key in KEYS:
+        if key in d:
+            k[key] = d[key] + (" " + units[hdr.index(key)] if units[hdr.index(key)] else "")
+    out["kernels"].append(k)
+print(json.dumps(out, indent=1))
