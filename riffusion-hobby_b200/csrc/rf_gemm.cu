@@ -557,11 +557,17 @@ int pick_splits(long rows, int N, int tiles, int num_kb, int num_sms, bool allow
     return best;
 }
 
-// output-tile width: 64 for narrow outputs, 160 when it divides N and 128 does not, else 128
-int pick_bn(int N) {
+// Output-tile width: 64 for narrow outputs; otherwise 128, or 160 when it divides N and is not slower by the wave
+// count: relative time = ceil(tiles / SMs) waves x tile width.  160 always wins when 128 does not divide N (N = 320:
+// two exact tiles instead of three with 17 % padding) and often when both do (M = 4096, N = 1280: 256 tiles = 2 waves
+// instead of 320 tiles = 3 waves); it also moves 12 % fewer operand bytes per FLOP from L2.
+int pick_bn(int N, long tiles_m) {
     if (N <= 64) return 64;
-    if (N % 160 == 0 && N % 128 != 0) return 160;
-    return 128;
+    if (N % 160) return 128;
+    const long sms = 148;
+    const long t128 = tiles_m * ((N + 127) / 128), t160 = tiles_m * (N / 160);
+    const long c128 = ((t128 + sms - 1) / sms) * 128, c160 = ((t160 + sms - 1) / sms) * 160;
+    return c160 * 100 <= c128 * 102 ? 160 : 128;
 }
 
 int num_sms_cached() {
@@ -578,7 +584,7 @@ int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
              int nbatch, cudaStream_t st) {
     // one persistent CTA per SM: 6-stage (BN=128/160) / 8-stage (BN=64) TMA ring, 2 TMEM accumulators
     p.tiles_m = tiles_m;
-    const int bn = pick_bn(N);
+    const int bn = pick_bn(N, static_cast<long>(tiles_m) * nbatch);
     p.tiles_n = (N + bn - 1) / bn;
     // split-K: non-batched, plain or SiLU epilogue, 16-byte aligned fp16/fp32 rows
     const long rows = p.conv ? static_cast<long>(p.Bn) * p.Ho * p.Wo : p.M;
@@ -642,7 +648,7 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
         int rc = make_map(&ma, d->A, dims, str, box, es);
         if (rc) return rc;
     }
-    const int BN = pick_bn(d->N);
+    const int BN = pick_bn(d->N, static_cast<long>((d->M + BM - 1) / BM) * b1 * b2);
     {
         const long dims[4] = {d->K, d->N, b_m1 ? b1 : 1, b_m2 ? b2 : 1};
         const long str[4] = {1, d->ldb, b_m1 ? d->sb1 : d->ldb, b_m2 ? d->sb2 : d->ldb};
@@ -715,7 +721,8 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     }
     const int taps = d->ksize * d->ksize;
     const long Ktot = static_cast<long>(taps) * (d->C1 + C2);
-    const int BN = pick_bn(d->Cout);
+    const long conv_tiles_m = static_cast<long>((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((d->B + bb - 1) / bb);
+    const int BN = pick_bn(d->Cout, conv_tiles_m);
     {
         const long dims[4] = {Ktot, d->Cout, 1, 1};
         const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};

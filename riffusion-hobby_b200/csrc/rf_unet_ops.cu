@@ -765,6 +765,7 @@ extern "C" int rf_conv_in_f16(const void* x_nchw, const void* w, const void* bia
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (W % 4 == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 3) == 0) &&
         (reinterpret_cast<uintptr_t>(y_nhwc) & 3) == 0) {
+        if (Cout == 512) return launch_conv_in_blk<8>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);   // VAE decoder
         if (Cout == 320) return launch_conv_in_blk<5>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);
         if (Cout == 128) return launch_conv_in_blk<2>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);
         if (Cout == 64) return launch_conv_in_blk<1>(x_nchw, w, bias, B, Cin, H, W, y_nhwc, st);

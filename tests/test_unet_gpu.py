@@ -48,7 +48,7 @@ def test_elementwise_ops_match_torch(native_lib):
     assert torch.equal(ops.concat_channels(a, bb), torch.cat([a, bb], dim=-1))
     # edge convolutions: register-blocked kernels (W % 4 == 0, Cout/Cin in {64, 128, 320}) and the generic fallback
     for (B, Cin, H, W, Cout) in ((2, 4, 12, 12, 320), (1, 3, 8, 20, 128), (3, 4, 5, 8, 64), (2, 4, 6, 7, 320),
-                                 (1, 4, 9, 12, 96)):
+                                 (1, 4, 9, 12, 96), (2, 4, 8, 8, 512)):
         x = torch.randn(B, Cin, H, W, device="cuda").half()
         w = (torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.1).half()
         bias = torch.randn(Cout, device="cuda").half()
