@@ -686,6 +686,249 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Short key sequences (Nk <= 128: the cross-attention to the 77 text tokens).  One key tile, so no online softmax; what
+// dominates the streaming kernel here is its fixed cost per CTA (TMEM allocation, barrier setup, a dependent chain of
+// TMA -> MMA -> tcgen05.ld -> MMA latencies: 5.4 us for 128 queries).  This kernel is persistent instead: a CTA takes a
+// contiguous range of (image, head, query block) items, keeps K / V^T of the current head in shared memory, and
+// software-pipelines the items over two Q / S / P / O buffers:
+//   control thread (warp 0): TMA of Q_{n+1}, K/V^T on a head change; issues Q_n K^T before it waits for P_{n-1}, then P_{n-1} V
+//   warps 1-4 (one query row per thread): scores_n -> max -> exp2 -> P_n ; then the epilogue of item n-1 (O / l -> fp16)
+// Row sums again come from 16 rows of ones under V^T.  TMEM: S0 | S1 | O0 | O1.
+template <int DPAD, int NV>
+__global__ void __launch_bounds__(160, 1)
+k_attn_short(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+             const __grid_constant__ CUtensorMap mapVt, const AttnParams p, int n_items, int nqb) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NSLAB = DPAD / 64;
+    constexpr int NVP = NV + 16;
+    static_assert(256 + 2 * NVP <= 512, "TMEM budget");
+    constexpr int Q_BYTES = NSLAB * TQ * 128;
+    constexpr int K_BYTES = NSLAB * TK * 128;
+    constexpr int V_SLAB = ((NVP * 128 + 1023) / 1024) * 1024;
+    constexpr int V_BYTES = 2 * V_SLAB;
+    constexpr int P_BYTES = 2 * TQ * 128;
+    uint8_t* sQ = smem;                         // [2][Q_BYTES]
+    uint8_t* sK = sQ + 2 * Q_BYTES;
+    uint8_t* sV = sK + K_BYTES;
+    uint8_t* sP = sV + V_BYTES;                 // [2][P_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint64_t* q_full = bars;                    // [2]
+    uint64_t* q_empty = bars + 2;               // [2]
+    uint64_t* kv_full = bars + 4;               // 1
+    uint64_t* s_full = bars + 5;                // [2]
+    uint64_t* s_empty = bars + 7;               // [2]
+    uint64_t* p_full = bars + 9;                // [2]
+    uint64_t* o_full = bars + 11;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (n_items + gridDim.x - 1) / gridDim.x;
+    const int w0 = blockIdx.x * per, w1 = min(n_items, w0 + per);
+    const int ncols = ((p.Nk + 31) / 32) * 32;  // score columns actually read back
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&q_full[i], 1);
+            tc::mbar_init(&q_empty[i], 1);
+            tc::mbar_init(&s_full[i], 1);
+            tc::mbar_init(&s_empty[i], 128);
+            tc::mbar_init(&p_full[i], 128);
+            tc::mbar_init(&o_full[i], 1);
+        }
+        tc::mbar_init(kv_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < 2 * 16 * 8; i += blockDim.x) {      // ones rows under V^T (outside the TMA boxes)
+        const int ch = i & 7, r = (i >> 3) & 15, sl = i >> 7;
+        *reinterpret_cast<uint4*>(sV + sl * V_SLAB + (NV + r) * 128 + ch * 16) =
+            make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    }
+    fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_mine = w1 - w0;
+
+    if (warp == 0 && lane == 0 && n_mine > 0) {
+        // ------------------------------------------------------------------ control thread: TMA + MMA issue
+        constexpr uint32_t idesc_qk = tc::make_idesc_f16(TQ, TK);
+        constexpr uint32_t idesc_pv = tc::make_idesc_f16(TQ, NVP);
+        const uint32_t k_lo = tc::desc_lo_sw128(tc::smem_u32(sK)), v_lo = tc::desc_lo_sw128(tc::smem_u32(sV));
+        auto load_q = [&](int n) {               // item w0+n -> Q buffer n&1
+            const int w = w0 + n, i = n & 1;
+            const int q_blk = w % nqb, head = (w / nqb) % p.heads, b = w / (nqb * p.heads);
+            if (n >= 2) tc::mbar_wait(&q_empty[i], ((n >> 1) - 1) & 1);   // Q K^T of item n-2 has completed
+            tc::mbar_expect_tx(&q_full[i], Q_BYTES);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+                tc::tma_load_4d(&mapQ, &q_full[i], sQ + i * Q_BYTES + s * TQ * 128, s * 64, q_blk * TQ, head, b);
+        };
+        auto issue_pv = [&](int n) {             // O_{n&1} = P_n V
+            const int i = n & 1;
+            tc::mbar_wait(&p_full[i], (n >> 1) & 1);
+            tc::fence_after_sync();
+            const uint32_t p_lo = tc::desc_lo_sw128(tc::smem_u32(sP + i * P_BYTES));
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16_lo(tmem_base + 256 + i * NVP, p_lo + ((s * TQ * 128 + k * 32) >> 4),
+                                   v_lo + ((s * V_SLAB + k * 32) >> 4), idesc_pv, (s | k) ? 1u : 0u);
+            tc::mma_commit(&o_full[i]);
+        };
+        int cur_head = -1, kv_phase = 0;
+        load_q(0);
+        for (int n = 0; n < n_mine; ++n) {
+            const int w = w0 + n, i = n & 1;
+            const int head_id = w / nqb;         // (image, head) pair
+            if (n + 1 < n_mine) load_q(n + 1);
+            if (head_id != cur_head) {
+                // K / V^T are single buffered: everything issued for the previous head must have completed
+                if (n > 0) {
+                    issue_pv(n - 1);
+                    tc::mbar_wait(&o_full[(n - 1) & 1], ((n - 1) >> 1) & 1);
+                }
+                const int head = head_id % p.heads, b = head_id / p.heads;
+                tc::mbar_expect_tx(kv_full, K_BYTES + 2 * NV * 128);
+#pragma unroll
+                for (int s = 0; s < NSLAB; ++s) tc::tma_load_4d(&mapK, kv_full, sK + s * TK * 128, s * 64, 0, head, b);
+                tc::tma_load_4d(&mapVt, kv_full, sV, 0, 0, head, b);
+                tc::tma_load_4d(&mapVt, kv_full, sV + V_SLAB, 64, 0, head, b);
+                tc::mbar_wait(kv_full, kv_phase);
+                kv_phase ^= 1;
+            }
+            // scores of item n (the softmax warps have pulled S of item n-2 into registers)
+            tc::mbar_wait(&q_full[i], (n >> 1) & 1);
+            if (n >= 2) tc::mbar_wait(&s_empty[i], ((n >> 1) - 1) & 1);
+            tc::fence_after_sync();
+            const uint32_t q_lo = tc::desc_lo_sw128(tc::smem_u32(sQ + i * Q_BYTES));
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16_lo(tmem_base + i * 128, q_lo + ((s * TQ * 128 + k * 32) >> 4),
+                                   k_lo + ((s * TK * 128 + k * 32) >> 4), idesc_qk, (s | k) ? 1u : 0u);
+            tc::mma_commit(&s_full[i]);
+            tc::mma_commit(&q_empty[i]);
+            // P V of the previous item, unless the head change above already issued it
+            if (n > 0 && head_id == cur_head) issue_pv(n - 1);
+            cur_head = head_id;
+        }
+        issue_pv(n_mine - 1);
+    } else if (warp >= 1 && n_mine > 0) {
+        // ------------------------------------------------------------------ softmax + epilogue warps
+        const int q = (warp - 1) & 3;            // TMEM lane quarter == warp % 4 is NOT required here: see t_row
+        const int qq = warp & 3;                 // hardware: a warp may only touch TMEM lanes [32*(warp%4), +32)
+        const int row = qq * 32 + lane;
+        (void)q;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qq * 32) << 16);
+        const float c = p.c;
+        auto epilogue = [&](int n) {
+            const int w = w0 + n, i = n & 1;
+            const int q_blk = w % nqb, head = (w / nqb) % p.heads, b = w / (nqb * p.heads);
+            tc::mbar_wait(&o_full[i], (n >> 1) & 1);
+            tc::fence_after_sync();
+            uint32_t l16[16];
+            tmem_ld16(t_row + 256 + i * NVP + NV, l16);
+            tc::tmem_wait_ld();
+            const float inv = 1.f / __uint_as_float(l16[0]);
+            const int qi = q_blk * TQ + row;
+            __half* dst = p.out + (static_cast<long>(b) * p.Nq + qi) * p.out_pitch + head * p.d;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NV; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld16(t_row + 256 + i * NVP + c0, o);
+                tc::tmem_wait_ld();
+                if (qi < p.Nq) {
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const int col = c0 + 8 * ch;
+                        if (col < p.d) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __half2 h = __floats2half2_rn(__uint_as_float(o[8 * ch + 2 * e]) * inv,
+                                                                    __uint_as_float(o[8 * ch + 2 * e + 1]) * inv);
+                                pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(dst + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+        };
+        for (int n = 0; n < n_mine; ++n) {
+            const int i = n & 1;
+            tc::mbar_wait(&s_full[i], (n >> 1) & 1);
+            tc::fence_after_sync();
+            uint32_t v[128];
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                if (c0 < ncols) {
+                    tc::tmem_ld_32x32(t_row + i * 128 + c0, v + c0);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[c0 + e] = 0xff800000u;
+                }
+            }
+            tc::tmem_wait_ld();
+            tc::fence_before_sync();
+            tc::mbar_arrive(&s_empty[i]);
+#pragma unroll
+            for (int e = 0; e < 128; ++e)
+                if (e >= p.Nk) v[e] = 0xff800000u;
+            float mx[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mx[e] = __uint_as_float(v[e]);
+#pragma unroll
+            for (int e0 = 8; e0 < 128; e0 += 8)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], __uint_as_float(v[e0 + e]));
+            const float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+            const float mc = mt * c;
+            uint8_t* myP = sP + i * P_BYTES;     // P buffer i was last read by P V of item n-2: its epilogue ran already
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 8) {
+                uint32_t pk[4];
+                if (c0 < ncols) {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        float e0, e1;
+                        const float a0 = fmaf(__uint_as_float(v[c0 + e]), c, -mc);
+                        const float a1 = fmaf(__uint_as_float(v[c0 + e + 1]), c, -mc);
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+                        const __half2 h = __floats2half2_rn(e0, e1);
+                        pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                } else {
+                    pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+                }
+                const int slab = c0 >> 6, chunk = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4*>(myP + slab * TQ * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_async_smem();
+            tc::fence_before_sync();
+            tc::mbar_arrive(&p_full[i]);
+            if (n > 0) epilogue(n - 1);
+        }
+        epilogue(n_mine - 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -761,6 +1004,31 @@ int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     return RF_OK;
 }
 
+template <int DPAD, int NV>
+int launch_attn_short(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int B,
+                      cudaStream_t st) {
+    constexpr int NSLAB = DPAD / 64;
+    constexpr int V_SLAB = (((NV + 16) * 128 + 1023) / 1024) * 1024;
+    constexpr size_t smem = 2 * static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NSLAB) * TK * 128 + 2 * V_SLAB +
+                            2 * (2 * TQ * 128) + 256 + 1024;
+    static_assert(smem <= 232448, "shared memory budget");
+    static std::once_flag once;
+    static cudaError_t aerr = cudaSuccess;
+    static int num_sms = 148;
+    std::call_once(once, [&] {
+        aerr = cudaFuncSetAttribute(k_attn_short<DPAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    });
+    if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_attn_short): ") + cudaGetErrorString(aerr));
+    const int nqb = (p.Nq + TQ - 1) / TQ;
+    const int n_items = nqb * p.heads * B;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    k_attn_short<DPAD, NV><<<grid, 160, smem, st>>>(mq, mk, mv, p, n_items, nqb);
+    RF_CUDA_LAUNCH_CHECK("k_attn_short");
+    return RF_OK;
+}
+
 }  // namespace
 
 // q: [B][Nq][heads*d], k: [B][Nk][heads*d], vt: [B][heads*d][vt_pitch] (V transposed), out: [B][Nq][heads*d]; fp16.
@@ -774,7 +1042,8 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     static const bool two_pass = getenv("RF_ATTN_TWO_PASS") != nullptr;   // A/B switch for the older kernel
     static const bool two_groups = getenv("RF_ATTN_TWO_GROUPS") != nullptr;     // A/B switch (four groups: 766 vs 830 us)
     const bool one_pass = !two_pass && d <= 112;
-    const int ng = (one_pass && d <= 48 && !two_groups) ? 4 : 2;         // softmax groups; key tile = 256 / ng keys
+    const bool short_keys = one_pass && Nk <= TK && getenv("RF_ATTN_NO_SHORT") == nullptr;
+    const int ng = (one_pass && d <= 48 && !two_groups && !short_keys) ? 4 : 2;   // softmax groups; key tile = 256 / ng keys
     const int tkt = one_pass ? 256 / ng : TK;
     CUtensorMap mq, mk, mv;
     {
@@ -808,6 +1077,14 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     p.out_pitch = C;
     dim3 grid((Nq + TQ - 1) / TQ, heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool no_short = getenv("RF_ATTN_NO_SHORT") != nullptr;
+    if (one_pass && Nk <= TK && !no_short) {     // one key tile: persistent kernel (cross-attention to the text tokens)
+        if (d <= 48) return launch_attn_short<64, 48>(mq, mk, mv, p, B, st);
+        if (d <= 64) return launch_attn_short<64, 64>(mq, mk, mv, p, B, st);
+        if (d <= 80) return launch_attn_short<128, 80>(mq, mk, mv, p, B, st);
+        if (d <= 96) return launch_attn_short<128, 96>(mq, mk, mv, p, B, st);
+        return launch_attn_short<128, 112>(mq, mk, mv, p, B, st);
+    }
     if (one_pass) {
         // ring depths fill the 227 KB of shared memory next to Q and the P tiles
         if (ng == 4) return launch_attn1<64, 48, 8, 6, 4>(mq, mk, mv, p, grid, st);
