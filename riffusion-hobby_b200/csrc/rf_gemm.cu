@@ -29,6 +29,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+// epilogue warp sets (4 warps = the 4 TMEM lane quarters each); set s drains the 32-column runs s, s + EPI_SETS, ...
+// Four sets: a 128-column tile is drained in one run per warp — the K <= 640 GEMMs are epilogue bound (MMA 0.8 us vs
+// ~4 us of tcgen05.ld / convert / store per tile with two sets).
+constexpr int EPI_SETS = 4;
+constexpr int GEMM_THREADS = 64 + 128 * EPI_SETS;
 
 struct TcParams {
     // problem
@@ -73,11 +78,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Persistent kernel: grid = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
 //   warp 0: TMA producer — streams the K slabs of all its tiles through one STAGES-deep ring (phases run across tiles)
 //   warp 1: MMA issuer  — accumulates tile i in TMEM buffer i&1, commits tmem_full[i&1]
-//   warps 2-9: epilogue — drain buffer i&1 (tcgen05.ld -> bias/act/residual -> global) while the MMA warp already works
+//   warps 2-17: epilogue (4 sets x 4 warps) — drain buffer i&1 (tcgen05.ld -> bias/act/residual -> global) while the MMA warp already works
 //              on tile i+1 in the other buffer; arrive tmem_empty[i&1] (256 threads) when done
 // Tile order: n fastest, then m, then batch, so CTAs running at the same time share activation rows in L2.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -102,7 +107,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tmem_full[i], 1);
-            tc::mbar_init(&tmem_empty[i], 256);
+            tc::mbar_init(&tmem_empty[i], 128 * EPI_SETS);
         }
         tc::fence_barrier_init();
     }
@@ -189,7 +194,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             tc::mma_commit(&tmem_full[acc]);
         }
     } else if (warp >= 2) {
-        // ------------------------------------------------------------ epilogue (8 warps)
+        // ------------------------------------------------------------ epilogue (EPI_SETS x 4 warps)
         // warp w reads TMEM lanes [32*(w%4), +32) (hardware restriction) and the column half (w-2)/4 of the tile.
         const int q = warp & 3;
         const int half_id = (warp - 2) >> 2;
@@ -234,7 +239,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             tc::mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int c0 = half_id * 32; c0 < BN; c0 += 64) {   // the two warp sets take alternate 32-column runs
+            for (int c0 = half_id * 32; c0 < BN; c0 += 32 * EPI_SETS) {   // the warp sets take the 32-column runs round-robin
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
                 tc::tmem_wait_ld();
@@ -374,7 +379,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 }
             }
             tc::fence_before_sync();
-            tc::mbar_arrive(&tmem_empty[acc]);   // 256 epilogue threads: the accumulator may be overwritten
+            tc::mbar_arrive(&tmem_empty[acc]);   // all epilogue threads: the accumulator may be overwritten
         }
     }
     tc::fence_before_sync();
@@ -464,7 +469,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         RF_CUDA_TRY(cudaEventCreate(&e1));
         RF_CUDA_TRY(cudaEventRecord(e0, st));
     }
-    k_tc_gemm<BN, STAGES><<<grid, 320, smem, st>>>(a0, a1, b, p);
+    k_tc_gemm<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
     RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
     if (prof) {
         RF_CUDA_TRY(cudaEventRecord(e1, st));
