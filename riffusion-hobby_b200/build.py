@@ -26,12 +26,24 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
+STAMP = HERE / "librf_b200.so.sha256"
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (file mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(CSRC.glob("*")) + [HERE.parent / "include" / "rf_b200.h"]:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not STAMP.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [HERE.parent / "include" / "rf_b200.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    return STAMP.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -48,6 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    STAMP.write_text(source_hash() + "\n")
     return LIB
 
 

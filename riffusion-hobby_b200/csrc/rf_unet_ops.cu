@@ -32,7 +32,7 @@ __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); 
 // pass 1: per (image, slab of pixels, group) partial sum and sum of squares.  Threads read 16-byte channel octets,
 //         park their partials in shared memory, and one thread per group adds them in a fixed order (no atomics:
 //         repeated runs are bit-identical).
-// pass 2: one warp per (image, group) adds the slab partials in a fixed order -> (mean, rstd).
+// pass 2 (inside the apply kernel): the slab partials are added in a fixed order -> (mean, rstd) per group.
 // pass 3: y = (x - mean) * rstd * gamma + beta, optional SiLU.
 // Vectorised pass 1 (C % 8 == 0, C <= 2560): blockDim = PPI * C/8 threads; a thread owns 8 fixed channels (one 16-byte
 // load per pixel) and walks every PPI-th pixel of the slab, four loads in flight.  Same deterministic two-level sum.
@@ -89,10 +89,42 @@ __device__ __forceinline__ float silu_tanh(float v) {
 
 // Vectorised pass 3, same thread -> channel mapping: the affine form y = x * sc + sh (sc = rstd * gamma,
 // sh = beta - mean * sc) of the thread's 8 channels lives in registers for the whole slab.
-__global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restrict__ stats,
-                             const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int G,
-                             int act, int slab, __half* __restrict__ y) {
+__global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restrict__ part, int nslabs, float inv_n,
+                             float eps, const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C,
+                             int G, int act, int slab, __half* __restrict__ y) {
+    // pass 2 folded in: every CTA reduces the slab partials of its image to (mean, rstd) per group — a few KB from L2, in a
+    // fixed order (P strided sub-sums per group, then added in index order), instead of a separate launch
+    __shared__ float st[64 * 2];              // [G][2] mean, rstd   (G <= 64)
+    __shared__ float sub[64 * 8 * 2];
     const int b = blockIdx.y;
+    {
+        const int P = min(8, static_cast<int>(blockDim.x) / G);
+        const int t = threadIdx.x;
+        if (t < G * P) {
+            const int g = t / P, pi = t - g * P;
+            float s = 0.f, ss = 0.f;
+            for (int i = pi; i < nslabs; i += P) {
+                const float* o = part + ((static_cast<size_t>(b) * nslabs + i) * G + g) * 2;
+                s += o[0];
+                ss += o[1];
+            }
+            sub[(g * 8 + pi) * 2] = s;
+            sub[(g * 8 + pi) * 2 + 1] = ss;
+        }
+        __syncthreads();
+        if (t < G) {
+            float s = 0.f, ss = 0.f;
+            for (int pi = 0; pi < P; ++pi) {
+                s += sub[(t * 8 + pi) * 2];
+                ss += sub[(t * 8 + pi) * 2 + 1];
+            }
+            const float mean = s * inv_n;
+            const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+            st[2 * t] = mean;
+            st[2 * t + 1] = rsqrtf(var + eps);
+        }
+        __syncthreads();
+    }
     const int C8 = C >> 3;
     const int c8 = threadIdx.x % C8, pp = threadIdx.x / C8, PPI = blockDim.x / C8;
     const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
@@ -103,7 +135,6 @@ __global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restri
         const uint4 bv = *reinterpret_cast<const uint4*>(beta + c8 * 8);
         const __half* gh = reinterpret_cast<const __half*>(&gv);
         const __half* bh = reinterpret_cast<const __half*>(&bv);
-        const float* st = stats + static_cast<size_t>(b) * G * 2;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int g = (c8 * 8 + e) / cpg;
@@ -138,27 +169,6 @@ __global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restri
         yb[static_cast<size_t>(p + 3 * PPI) * C8] = xf(v3);
     }
     for (; p < p1; p += PPI) yb[static_cast<size_t>(p) * C8] = xf(xb[static_cast<size_t>(p) * C8]);
-}
-
-__global__ void k_gn_finalize(const float* __restrict__ part, int nslabs, int G, float inv_n, float eps,
-                              float* __restrict__ stats /*[B][G][2] = mean, rstd*/) {
-    const int bg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b, g) flattened
-    const int lane = threadIdx.x & 31;
-    const int b = bg / G, g = bg % G;
-    float s = 0.f, ss = 0.f;
-    for (int i = lane; i < nslabs; i += 32) {
-        const float* o = part + ((static_cast<size_t>(b) * nslabs + i) * G + g) * 2;
-        s += o[0];
-        ss += o[1];
-    }
-    s = warp_sum(s);
-    ss = warp_sum(ss);
-    if (lane == 0) {
-        const float mean = s * inv_n;
-        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-        stats[static_cast<size_t>(bg) * 2] = mean;
-        stats[static_cast<size_t>(bg) * 2 + 1] = rsqrtf(var + eps);
-    }
 }
 
 // ---------------------------------------------------------------- LayerNorm over the last dim
@@ -638,8 +648,6 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
         return rf_fail(RF_ERR_INVALID, "rf_group_norm_f16: bad argument (channels per group must be even)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (C > 2560 || (C % 8)) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: C must be a multiple of 8, <= 2560");
-    const int nbg = B * groups;
-    if (nbg % 8) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: B*groups must be a multiple of 8");
     // thread -> (pixel phase, 8-channel column): blockDim = PPI * C/8 (<= 320 threads)
     const int C8 = C / 8;
     const int PPI = C8 >= 256 ? 1 : 256 / C8;
@@ -648,17 +656,16 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
     int slab = 32;
     while (slab < 256 && static_cast<long>(B) * (HW / (2 * slab)) >= 4 * 148) slab *= 2;
     const int nslabs = (HW + slab - 1) / slab;
-    float* stats = d_scratch;                                          // [B][G][2]
     float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
     const size_t smem = static_cast<size_t>(PPI) * (C / 2) * sizeof(float2);
     dim3 grid(nslabs, B);
     k_gn_partial_v<<<grid, threads, smem, st>>>(static_cast<const __half*>(x), HW, C, groups, slab, nslabs, part);
     RF_CUDA_LAUNCH_CHECK("k_gn_partial_v");
-    k_gn_finalize<<<nbg / 8, 256, 0, st>>>(part, nslabs, groups, 1.f / (static_cast<float>(HW) * (C / groups)), eps, stats);
-    RF_CUDA_LAUNCH_CHECK("k_gn_finalize");
-    k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), stats, static_cast<const __half*>(gamma),
-                                           static_cast<const __half*>(beta), HW, C, groups, act, slab,
-                                           static_cast<__half*>(y));
+    if (groups > 64 || threads < groups) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: at most 64 groups (and not more groups than threads)");
+    k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), part, nslabs,
+                                           1.f / (static_cast<float>(HW) * (C / groups)), eps,
+                                           static_cast<const __half*>(gamma), static_cast<const __half*>(beta), HW, C,
+                                           groups, act, slab, static_cast<__half*>(y));
     RF_CUDA_LAUNCH_CHECK("k_gn_apply_v");
     return RF_OK;
 }

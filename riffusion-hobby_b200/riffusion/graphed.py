@@ -32,6 +32,16 @@ class GraphedUNet:
         with torch.cuda.graph(self.graph):
             self.out = unet(self.x, self.t, encoder_hidden_states=self.ctx, ctx_cache=self.cache).sample
 
+    def set_context(self, context: torch.Tensor) -> None:
+        """Re-target the captured graph to another text context of the same shape: the graph reads the context only
+        through the cached cross-attention K / V^T tensors, which are recomputed into the same storage."""
+        assert context.shape == self.ctx.shape
+        self.ctx.copy_(context)
+        for key, (k, vt) in self.cache.items():
+            k_new, vt_new = self.unet._kv(key, self.ctx)
+            k.copy_(k_new)
+            vt.copy_(vt_new)
+
     def __call__(self, latents: torch.Tensor, timestep: int) -> torch.Tensor:
         """latents: (B,4,H,W); evaluates the [uncond | text] pair and returns the (2B,4,H,W) static output."""
         B = latents.shape[0]

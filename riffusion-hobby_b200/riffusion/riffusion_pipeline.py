@@ -212,7 +212,14 @@ class RiffusionPipeline:
         if self.use_cuda_graph and do_cfg:
             from riffusion.graphed import GraphedUNet
 
-            graphed = GraphedUNet(self.unet, latents.shape, context)
+            # one captured graph per (latent shape, context shape); a new request only refreshes the cross-attention
+            # K / V^T that the graph reads (capture costs two eager evaluations + instantiation)
+            gkey = (tuple(latents.shape), tuple(context.shape))
+            graphed = self._graphs.get(gkey)
+            if graphed is None:
+                graphed = self._graphs[gkey] = GraphedUNet(self.unet, latents.shape, context)
+            else:
+                graphed.set_context(context)
         n_evals = 0
         for t in timesteps:                                                                        # :398
             t_int = int(t)

@@ -115,7 +115,7 @@ class UNetB200:
         k = ops.gemm(ctx.reshape(B * nk, cdim), w[pfx + "to_k.weight"]).reshape(B, nk, -1)
         C = k.shape[-1]
         pitch = (nk + 7) // 8 * 8
-        vt = torch.zeros((B, 1, C, pitch), dtype=torch.float16, device=ctx.device)
+        vt = torch.empty((B, 1, C, pitch), dtype=torch.float16, device=ctx.device)   # columns >= nk are never read (TMA extent)
         ops.gemm(w[pfx + "to_v.weight"], ctx.unsqueeze(1), out=vt[..., :nk])
         return k, vt.reshape(B, C, pitch)
 

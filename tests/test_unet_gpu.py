@@ -211,6 +211,37 @@ def test_denoising_loop_matches_oracle_loop(native_lib):
         assert e < 2e-2          # fp16 latents through n_ref guided steps (guidance 7 amplifies eps rounding 7x)
 
 
+def test_cuda_graph_reuse_with_new_context(native_lib):
+    """the captured CFG evaluation is reused across requests: a second request with another text context (same shape)
+    only refreshes the cached cross-attention K / V^T; results must equal the eager (no graph) path bit for bit"""
+    from riffusion.riffusion_pipeline import RiffusionPipeline
+
+    cfg = dict(block_out_channels=(64, 128, 128, 128), heads=4, cross_attention_dim=64)
+    _, ours = _build(cfg, seed=11)
+    pipe = RiffusionPipeline(vae=None, unet=ours, device="cuda")
+    torch.manual_seed(12)
+    lat = torch.randn(2, 4, 16, 16, device="cuda").half()
+    noise = torch.randn_like(lat)
+    uncond = torch.randn(1, 77, 64, device="cuda").half()
+
+    def run(text, graph):
+        pipe.use_cuda_graph = graph
+        return pipe.interpolate_img2img(text_embeddings=text, init_latents=lat, generator_a=None, generator_b=None,
+                                        interpolate_alpha=0.0, strength_a=1.0, strength_b=1.0, num_inference_steps=4,
+                                        guidance_scale=7.0, uncond_embeddings=uncond, noise=noise,
+                                        output_type="latent")["latents"]
+
+    t1 = torch.randn(2, 77, 64, device="cuda").half()
+    t2 = torch.randn(2, 77, 64, device="cuda").half()
+    g1 = run(t1, True).clone()
+    assert len(pipe._graphs) == 1
+    g2 = run(t2, True).clone()                      # same graph object, new context
+    assert len(pipe._graphs) == 1
+    e1, e2 = run(t1, False), run(t2, False)
+    assert torch.equal(g1, e1) and torch.equal(g2, e2)
+    assert not torch.equal(g1, g2)
+
+
 def test_device_slerp_matches_reference_numpy(native_lib):
     """device slerp (fp32 reductions) vs the reference's host-numpy slerp in fp16 (torch_util.py:21-48): within the
     1e-3 bar; exact lerp fallback for nearly parallel vectors"""
