@@ -162,7 +162,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="clip", choices=["clip", "gl"])
-    ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step (clip workload)")
+    ap.add_argument("--clips", type=int, default=32, help="clips per GPU per step (clip workload)")
     ap.add_argument("--evals", type=int, default=50, help="scheduler steps = UNet evaluations per clip (denoising 1.0)")
     args = ap.parse_args()
     if args.workload == "clip" and args.impl == "b200":
