@@ -167,6 +167,8 @@ def main() -> None:
     args = ap.parse_args()
     if args.workload == "clip" and args.impl == "b200":
         return main_clip(args)
+    if args.workload == "clip" and args.impl == "reference":
+        return main_clip_reference(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -367,6 +369,45 @@ def time_reference_clip(host_cores: int, budget_s: float = 25.0) -> dict:
             "audio_threads": audio["cores"]}
 
 
+def clip_config(n_steps: int, n_evals: int, clips_per_gpu: int) -> dict:
+    """`config` of the clip workload: shared by the B200 arm and the reference arm (the driver compares them)"""
+    return {"workload": f"full clip: {n_steps}-step img2img (denoising 1.0 -> {n_evals} CFG UNet evaluations, guidance 7, PNDM) + VAE "
+                        f"decode + image->mel + inverse-mel + Griffin-Lim {N_ITER} it, 512x512, {clips_per_gpu} clips per GPU per step",
+            "includes_denoise": True, "n_unet_evals": n_evals, "weights": "random-init SD-1.5 (N(0,0.02^2)), broadcast from rank 0 at init",
+            "clips_per_gpu": clips_per_gpu, "cuda_graph": True,
+            "l2": "UNet weights 1.7 GB + activations larger than L2; no explicit flush",
+            "sharding": "independent clips per rank; NCCL broadcast of weights at init only"}
+
+
+def main_clip_reference(args) -> None:
+    """`--impl reference`, clip workload: the reference's CPU arithmetic for one clip on the host cores.  diffusers is
+    not installable here, so the UNet / VAE are the torch-eager fp32 restatement (oracle/unet_oracle.py: kind "port");
+    torchaudio is the reference's own audio path.  Each step is a bounded sample: ONE CFG UNet evaluation + one clip of
+    inverse-mel + Griffin-Lim, extrapolated to n_evals evaluations + VAE decode (stated in `sample`)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_evals = args.evals
+    steps = max(1, min(args.steps, 3))
+    per_clip, last = [], None
+    for _ in range(steps):
+        last = time_reference_clip(cores)
+        per_clip.append(n_evals * last["t_unet_cfg_eval_s"] * (1 + VAE_DEC_TFLOP / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE))
+                        + last["t_audio_s"])
+    sec = sum(per_clip) / len(per_clip)
+    value = 1.0 / sec
+    sample = (f"{steps} x [1 CFG UNet evaluation ({last['t_unet_cfg_eval_s']:.1f} s, torch-eager fp32 restatement, {last['threads']} "
+              f"threads) extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of torchaudio inverse-mel + "
+              f"Griffin-Lim ({last['t_audio_s']:.1f} s, {last['audio_threads']} threads)]; host has {cores} cores")
+    line = {"impl": "reference", "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": 0, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": clip_config(args.evals, n_evals, args.clips),
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": last["threads"], "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
 def main_clip(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -552,12 +593,7 @@ def main_clip(args) -> None:
                             "sample": f"1 CFG UNet evaluation ({r['t_unet_cfg_eval_s']:.1f} s, torch-eager fp32 restatement, "
                                       f"{r['threads']} threads) extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of "
                                       f"torchaudio inverse-mel + Griffin-Lim ({r['t_audio_s']:.1f} s, {r['audio_threads']} threads); host has {cores} cores"}
-    config = {"workload": f"full clip: {n_steps}-step img2img (denoising 1.0 -> {n_evals} CFG UNet evaluations, guidance 7, PNDM) + VAE "
-                          f"decode + image->mel + inverse-mel + Griffin-Lim {N_ITER} it, 512x512, {B} clips per GPU per step",
-              "includes_denoise": True, "n_unet_evals": n_evals, "weights": "random-init SD-1.5 (N(0,0.02^2)), broadcast from rank 0 at init",
-              "clips_per_gpu": B, "cuda_graph": True,
-              "l2": "UNet weights 1.7 GB + activations larger than L2; no explicit flush",
-              "sharding": "independent clips per rank; NCCL broadcast of weights at init only"}
+    config = clip_config(n_steps, n_evals, B)
     line = {
         "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
