@@ -598,7 +598,7 @@ def main_clip(args) -> None:
         "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * (n_evals * 600 + 400)), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "gpu_launches": int(args.steps * (n_evals * 590 + 400)), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "griffinlim": gl,
     }
     print(json.dumps(line))
