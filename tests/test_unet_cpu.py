@@ -65,3 +65,23 @@ def test_product_spec_matches_oracle_state_dicts():
         got = dict(spec)
         assert len(got) == len(spec) and got == want
     assert sum(p.numel() for p in v.parameters()) == 83_653_863       # published SD VAE size
+
+
+def test_geglu_weight_interleave_matches_chunk_semantics():
+    """tc_ops.interleave_geglu reorders GEGLU.proj rows into runs of [16 value | 16 gate]; the fused epilogue of
+    rf_gemm_f16 (act = 2) then computes out[:, 16 r + j] = v_j * gelu(g_j) from columns 32 r + j and 32 r + 16 + j.
+    Emulated here in torch against diffusers' GEGLU: hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate)."""
+    import torch.nn.functional as F
+
+    from riffusion import tc_ops
+
+    torch.manual_seed(0)
+    C, inner, M = 48, 64, 10                       # inner % 16 == 0
+    x = torch.randn(M, C)
+    w, b = torch.randn(2 * inner, C), torch.randn(2 * inner)
+    hidden, gate = (x @ w.t() + b).chunk(2, dim=-1)
+    ref = hidden * F.gelu(gate)
+    y = x @ tc_ops.interleave_geglu(w).t() + tc_ops.interleave_geglu(b)          # what the GEMM accumulates
+    y = y.reshape(M, inner // 16, 2, 16)
+    got = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(M, inner)
+    assert torch.allclose(got, ref, atol=1e-5)
