@@ -382,27 +382,48 @@ def clip_config(n_steps: int, n_evals: int, clips_per_gpu: int) -> dict:
 def main_clip_reference(args) -> None:
     """`--impl reference`, clip workload: the reference's CPU arithmetic for one clip on the host cores.  diffusers is
     not installable here, so the UNet / VAE are the torch-eager fp32 restatement (oracle/unet_oracle.py: kind "port");
-    torchaudio is the reference's own audio path.  Each step is a bounded sample: ONE CFG UNet evaluation + one clip of
-    inverse-mel + Griffin-Lim, extrapolated to n_evals evaluations + VAE decode (stated in `sample`)."""
+    torchaudio is the reference's own audio path.  Each step is a bounded sample of one clip: ONE CFG UNet evaluation
+    + the inverse-mel + Griffin-Lim of one clip, extrapolated to n_evals evaluations + VAE decode (stated in `sample`)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    from oracle import unet_oracle as uo
+    from oracle.torchaudio_ref import TorchaudioConverter
+
     cores = os.cpu_count() or 1
     n_evals = args.evals
-    steps = max(1, min(args.steps, 3))
-    per_clip, last = [], None
-    for _ in range(steps):
-        last = time_reference_clip(cores)
-        per_clip.append(n_evals * last["t_unet_cfg_eval_s"] * (1 + VAE_DEC_TFLOP / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE))
-                        + last["t_audio_s"])
-    sec = sum(per_clip) / len(per_clip)
+    steps = max(1, min(args.steps, 20))
+    warm = max(0, min(args.warmup, 1))
+    audio = time_reference(1, 1, cores)                  # picks the fastest thread count for torch's CPU FFT path
+    audio_threads = audio["cores"]
+    unet_threads = min(cores, 32)
+    conv = TorchaudioConverter(n_iter=N_ITER)
+    mel = synthetic_mel(1, seed=0)
+    with torch.no_grad():
+        unet = uo.init_weights_(uo.UNet2DConditionOracle()).eval()
+        x, ctx = torch.randn(2, 4, 64, 64), torch.randn(2, 77, 768)
+        t_unet = t_audio = 0.0
+        for it in range(warm + steps):
+            torch.set_num_threads(unet_threads)
+            t0 = time.perf_counter()
+            unet(x, 741, ctx)
+            t1 = time.perf_counter()
+            torch.set_num_threads(audio_threads)
+            conv.waveform_from_mel_amplitudes(mel)
+            t2 = time.perf_counter()
+            if it >= warm:
+                t_unet += t1 - t0
+                t_audio += t2 - t1
+    t_unet /= steps
+    t_audio /= steps
+    sec = n_evals * t_unet * (1 + VAE_DEC_TFLOP / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE)) + t_audio
     value = 1.0 / sec
-    sample = (f"{steps} x [1 CFG UNet evaluation ({last['t_unet_cfg_eval_s']:.1f} s, torch-eager fp32 restatement, {last['threads']} "
-              f"threads) extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of torchaudio inverse-mel + "
-              f"Griffin-Lim ({last['t_audio_s']:.1f} s, {last['audio_threads']} threads)]; host has {cores} cores")
+    sample = (f"{steps} x [1 CFG UNet evaluation ({t_unet:.1f} s, torch-eager fp32 restatement, {unet_threads} threads) "
+              f"extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of torchaudio inverse-mel + "
+              f"Griffin-Lim ({t_audio:.1f} s, {audio_threads} threads)]; host has {cores} cores")
     line = {"impl": "reference", "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": 0, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": clip_config(args.evals, n_evals, args.clips),
-            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": last["threads"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": unet_threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
