@@ -209,8 +209,10 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
     // ---- time-decimated loop tables.  Eligible when every live bin k satisfies 2k + 800 <= N/2: the spectrum of a
     // windowed frame at distance >= 800 bins from its content is < 4e-8 of the peak (Hann side lobes fall with the
     // cube of the offset), below fp32 rounding, so sampling the loop signal at every second sample aliases nothing
-    // measurable.  Needs an odd hop (frame parities alternate) and an even chunk size.
-    p.decimate = (p.H % 2 == 1) && (RF_CHUNK % 2 == 0) && (2 * p.k_hi + 800 <= p.N / 2) && (p.W == 4410);
+    // measurable.  Needs an odd hop (frame parities alternate) and an even chunk size.  The full-rate edge strips of the
+    // hybrid loop (rf_dec_geom: 3 head pairs, E = W + H, tail chunks from (T-17)/G) are laid out for hop = W/10 = 441,
+    // the reference's default step; other odd hops (2205) run the full-rate loop.
+    p.decimate = (p.H == 441) && (RF_CHUNK % 2 == 0) && (2 * p.k_hi + 800 <= p.N / 2) && (p.W == 4410);
     if (p.decimate) {
         const int W2 = 2205, N2 = p.N / 2;
         p.pp2.resize(p.n_live);

@@ -217,3 +217,14 @@ def test_decimation_eligibility(hostemu):
     p, _ = _emu_plan(hostemu, False, 0.0, 10000.0)
     assert hostemu.emu_plan_decimate(p) == 1
     hostemu.emu_plan_destroy(p)
+    # the edge strips of the hybrid loop are laid out for hop = 441: another odd hop (step 50 ms) must stay full rate
+    # (it was eligible once and came out 40 % wrong in the emulator)
+    from riffusion import _native
+    from riffusion.spectrogram_converter import mel_filterbank
+
+    desc = _native.PlanDesc(44100, N, W, 2205, 512, 0.0, 10000.0, 0, 0, 0)
+    fb = np.ascontiguousarray(mel_filterbank(F, 0.0, 10000.0, 512, 44100).numpy())
+    win = torch.hann_window(W).numpy()
+    p = hostemu.emu_plan_create(ctypes.byref(desc), win.ctypes.data, fb.ctypes.data)
+    assert p and hostemu.emu_plan_decimate(p) == 0
+    hostemu.emu_plan_destroy(p)
