@@ -85,3 +85,35 @@ def test_geglu_weight_interleave_matches_chunk_semantics():
     y = y.reshape(M, inner // 16, 2, 16)
     got = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(M, inner)
     assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_product_scheduler_bookkeeping_matches_oracle(monkeypatch):
+    """host side of PNDMSchedulerB200 (timestep table, counter == 1 re-step, history rotation, Adams-Bashforth weights,
+    ca / cb) against the oracle scheduler, with the fused device kernel (rf_cfg_pndm_step_f16) replaced by its torch
+    definition: eps = eu + g (et - eu); e = sum c_i h_i; x' = ca x - cb e"""
+    from riffusion import tc_ops
+    from riffusion.scheduler_b200 import PNDMSchedulerB200
+
+    def fake_step(eps_pair, guidance, hist, coef, sample, ca, cb, want_eps=True):
+        n = sample.shape[0]
+        eu, et = eps_pair[:n].double(), eps_pair[n:].double()
+        eps = eu + guidance * (et - eu)
+        e = coef[0] * eps
+        for c, h in zip(coef[1:], hist):
+            e = e + c * h.double()
+        return (eps if want_eps else None), ca * sample.double() - cb * e
+
+    monkeypatch.setattr(tc_ops, "cfg_pndm_step", fake_step)
+    ours, ref = PNDMSchedulerB200(), uo.PNDMSchedulerOracle()
+    ours.set_timesteps(50)
+    ref.set_timesteps(50)
+    assert [int(t) for t in ours.timesteps] == [int(t) for t in ref.timesteps]
+    torch.manual_seed(3)
+    x_o = x_r = torch.randn(2, 4, 8, 8, dtype=torch.float64)
+    g = 7.0
+    for t in [int(v) for v in ref.timesteps[13:24]]:                # 11 steps: Euler, re-step, 2-, 3-, 4-term PLMS
+        pair = torch.randn(4, 4, 8, 8, dtype=torch.float64)
+        guided = pair[:2] + g * (pair[2:] - pair[:2])
+        x_r = ref.step(guided, t, x_r)
+        x_o = ours.step_cfg(pair, g, t, x_o)
+        assert torch.allclose(x_o, x_r, rtol=1e-5, atol=1e-5), t      # ca / cb are fp32 table look-ups on both sides
