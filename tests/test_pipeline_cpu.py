@@ -66,3 +66,63 @@ def test_riffuse_mask_and_preprocess():
     assert x.shape == (1, 3, 512, 512) and float(x[0, 0].min()) == 1.0 and float(x[0, 1].max()) == -1.0
     assert abs(float(x[0, 2, 0, 0]) - (2 * 127 / 255 - 1)) < 1e-6
     assert preprocess_mask(mask_img, scale_factor=8).dtype == torch.float32
+
+
+def _fake_ops(monkeypatch):
+    """torch definitions of the three device ops the loop calls (rf_axpby_f16, rf_cfg_pndm_step_f16, device slerp off)"""
+    from riffusion import tc_ops
+
+    def axpby(x, noise, a, b, mask=None, z=None):
+        y = a * x.float() + b * noise.float()
+        if mask is not None:
+            y = y * mask.float() + z.float() * (1 - mask.float())
+        return y.to(x.dtype)
+
+    def cfg_step(eps_pair, guidance, hist, coef, sample, ca, cb, want_eps=True):
+        n = sample.shape[0]
+        eu, et = eps_pair[:n].float(), eps_pair[n:].float()
+        eps = eu + guidance * (et - eu)
+        e = coef[0] * eps
+        for c, h in zip(coef[1:], hist):
+            e = e + c * h.float()
+        return (eps.to(sample.dtype) if want_eps else None), (ca * sample.float() - cb * e).to(sample.dtype)
+
+    monkeypatch.setattr(tc_ops, "axpby", axpby)
+    monkeypatch.setattr(tc_ops, "cfg_pndm_step", cfg_step)
+
+
+def test_interpolate_img2img_control_flow_matches_oracle_loop(monkeypatch):
+    """strength interpolation, init_timestep / t_start arithmetic, noise slerp, add_noise, CFG doubling, PLMS stepping and
+    the mask blend of interpolate_img2img (reference :311-425) against the oracle loop, with a smooth stand-in for the
+    UNet so that the whole thing runs on the CPU (fp16 tensors like the product, fp32 oracle)"""
+    from oracle import unet_oracle as uo
+
+    _fake_ops(monkeypatch)
+
+    def model(x, t, ctx):
+        return 0.3 * torch.tanh(x.float()) + 0.002 * (t / 1000.0) + 0.05 * ctx.float().mean(dim=(1, 2))[:, None, None, None]
+
+    class FakeUNet:
+        def __call__(self, x, t, encoder_hidden_states=None, **kw):
+            return types.SimpleNamespace(sample=model(x, int(t), encoder_hidden_states).to(torch.float16))
+
+    pipe = RiffusionPipeline(vae=None, unet=FakeUNet(), device="cpu")
+    pipe.use_cuda_graph = False
+    pipe.device_slerp = False                      # the reference's host-numpy slerp
+    torch.manual_seed(5)
+    lat = torch.randn(1, 4, 8, 8).half()
+    na, nb = torch.randn(1, 4, 8, 8).half(), torch.randn(1, 4, 8, 8).half()
+    text, uncond = torch.randn(1, 77, 16).half(), torch.randn(1, 77, 16).half()
+    mask = (torch.rand(1, 4, 8, 8) > 0.5).half()
+    for steps, sa, sb, alpha, m in ((50, 0.75, 0.75, 0.5, None), (20, 0.5, 0.9, 0.25, None), (10, 1.0, 1.0, 0.0, mask)):
+        strength = (1 - alpha) * sa + alpha * sb
+        ref, n_ref = uo.img2img_loop(lambda x, t, c: model(x, t, c), uo.PNDMSchedulerOracle(), text.float(), uncond.float(),
+                                     lat.float(), na.float(), nb.float(), alpha, strength, steps, 7.0,
+                                     mask=None if m is None else m.float())
+        out = pipe.interpolate_img2img(text_embeddings=text, init_latents=lat, generator_a=None, generator_b=None,
+                                       interpolate_alpha=alpha, strength_a=sa, strength_b=sb, num_inference_steps=steps,
+                                       guidance_scale=7.0, uncond_embeddings=uncond, noise_a=na, noise_b=nb, mask=m,
+                                       output_type="latent")
+        assert out["n_unet_evals"] == n_ref, (steps, sa, sb)
+        err = float((out["latents"].float() - ref).norm() / ref.norm())
+        assert err < 2e-2, (steps, err)            # fp16 latents through up to 38 guided steps
