@@ -62,3 +62,83 @@ def test_sample_clips_wav(tmp_path):
     for c in clips:
         seg = AudioSegment.from_file(str(c))
         assert seg.channels == 1 and seg.frame_rate == rate and abs(len(seg) - 500) <= 1
+
+
+class _FakeImageConverter:
+    """stands in for the GPU-backed SpectrogramImageConverter: records what the CLI passes to it"""
+    instances = []
+
+    def __init__(self, params, device):
+        self.p, self.device, self.calls = params, device, []
+        _FakeImageConverter.instances.append(self)
+
+    def spectrogram_image_from_audio(self, segment):
+        from PIL import Image
+
+        from riffusion.spectrogram_params import SpectrogramParams
+
+        self.calls.append(("to_image", segment.channels, segment.frame_rate))
+        img = Image.new("RGB", (64, self.p.num_frequencies), (1, 2, 3))
+        tags = self.p.to_exif()
+        tags[SpectrogramParams.ExifTags.MAX_VALUE.value] = 123.0
+        img.getexif().update(tags.items())
+        return img
+
+    def audio_from_spectrogram_image(self, image, apply_filters=True, max_value=30e6):
+        import numpy as np
+
+        from riffusion.util.audio_util import AudioSegment
+
+        self.calls.append(("to_audio", image.size))
+        n = self.p.sample_rate // 10
+        return AudioSegment((np.zeros((n, 2 if self.p.stereo else 1)) + 100).astype(np.int16), self.p.sample_rate)
+
+
+def test_commands_with_recorded_converter(tmp_path, monkeypatch, capsys):
+    """audio-to-image / image-to-audio / audio-to-images-batch argument plumbing (flags -> SpectrogramParams, EXIF written
+    and read back, channel / sample-rate conforming in the batch command, unreadable files skipped) without a GPU"""
+    import numpy as np
+    from PIL import Image
+    from scipy.io import wavfile
+
+    from riffusion import cli
+    from riffusion.spectrogram_params import SpectrogramParams
+
+    monkeypatch.setattr(cli, "SpectrogramImageConverter", _FakeImageConverter)
+    _FakeImageConverter.instances.clear()
+    rate = 22050
+    wav = (np.sin(np.arange(rate) / 20.0) * 8000).astype(np.int16)
+    wavfile.write(tmp_path / "a.wav", rate, wav)
+    cli.main(["audio-to-image", "--audio", str(tmp_path / "a.wav"), "--image", str(tmp_path / "a.png"), "--stereo",
+              "--num-frequencies", "256", "--max-frequency", "8000", "--power-for-image", "0.5", "--device", "cuda:1"])
+    conv = _FakeImageConverter.instances[-1]
+    assert conv.device == "cuda:1"
+    assert conv.p == SpectrogramParams(sample_rate=rate, stereo=True, num_frequencies=256, max_frequency=8000,
+                                       power_for_image=0.5)
+    assert conv.calls == [("to_image", 1, rate)]
+    img = Image.open(tmp_path / "a.png")
+    assert img.format == "PNG" and SpectrogramParams.from_exif(img.getexif()) == conv.p     # EXIF survives the save
+    assert f"Wrote {tmp_path / 'a.png'}" in capsys.readouterr().out
+
+    cli.main(["image-to-audio", "--image", str(tmp_path / "a.png"), "--audio", str(tmp_path / "back.wav")])
+    conv2 = _FakeImageConverter.instances[-1]
+    assert conv2.p == conv.p and conv2.calls == [("to_audio", (64, 256))] and conv2.device == "cuda"
+    r2, back = wavfile.read(tmp_path / "back.wav")
+    assert r2 == rate and back.shape == (rate // 10, 2)
+    assert "seconds)" in capsys.readouterr().out
+    # an image without our EXIF tags falls back to the defaults with the reference's warning (cli.py:79-83)
+    Image.new("RGB", (32, 512)).save(tmp_path / "plain.png")
+    cli.main(["image-to-audio", "--image", str(tmp_path / "plain.png"), "--audio", str(tmp_path / "plain.wav")])
+    assert "Using defaults" in capsys.readouterr().out and _FakeImageConverter.instances[-1].p == SpectrogramParams()
+
+    # batch: stereo default -> mono files are widened, junk files are skipped (resampling needs pydub: same rate here)
+    clips = tmp_path / "clips"
+    clips.mkdir()
+    wavfile.write(clips / "x.wav", rate, wav)
+    wavfile.write(clips / "y.wav", rate, np.stack([wav, wav], axis=1))
+    (clips / "notes.txt").write_text("not audio")
+    cli.main(["audio-to-images-batch", "--audio-dir", str(clips), "--output-dir", str(tmp_path / "imgs"),
+              "--image-extension", "png", "--num-threads", "2", "--sample-rate", str(rate)])
+    shared = _FakeImageConverter.instances[-1]
+    assert sorted(shared.calls) == [("to_image", 2, rate), ("to_image", 2, rate)] and shared.p.stereo
+    assert sorted(p.name for p in (tmp_path / "imgs").iterdir()) == ["x.png", "y.png"]

@@ -136,3 +136,25 @@ def test_int16_truncation_and_joint_normalisation():
     pcm = ao.int16_from_waveform(w, normalize=True)
     assert pcm.shape == (3, 2) and pcm.dtype == np.int16
     assert pcm[1, 1] == -32767 and pcm[0, 0] == int(0.5 * np.float32(32767 / 2.0))
+
+
+def test_host_slerp_bit_exact_against_reference_vectors():
+    """riffusion.util.torch_util.slerp (host mode) reproduces the reference's own function bit for bit on fp16 and fp32
+    tensors, including the lerp branch for nearly parallel vectors (tests/golden/make_golden_host.py); the oracle's
+    slerp agrees with it"""
+    import torch
+
+    from oracle import unet_oracle as uo
+    from riffusion.util import torch_util
+
+    from pathlib import Path
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "host_vectors.npz")
+    for name in ("f16", "f32", "par16"):
+        a, b = torch.from_numpy(g[f"slerp_{name}_a"]), torch.from_numpy(g[f"slerp_{name}_b"])
+        for i, t in enumerate(g["ts"]):
+            got = torch_util.slerp(float(t), a, b)
+            assert got.dtype == a.dtype
+            assert np.array_equal(got.numpy(), g[f"slerp_{name}_out"][i]), (name, t)
+            ref32 = uo.slerp(float(t), a.float(), b.float()).numpy()
+            assert np.allclose(got.float().numpy(), ref32, atol=4e-3 if a.dtype == torch.float16 else 1e-6)
