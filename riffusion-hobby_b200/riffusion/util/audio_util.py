@@ -5,6 +5,7 @@ pydub is used when it is installed; otherwise the numpy AudioSegment stand-in fr
 """
 from __future__ import annotations
 
+import functools
 import io
 import typing as T
 
@@ -43,33 +44,30 @@ def audio_from_waveform(samples: np.ndarray, sample_rate: int, normalize: bool =
     return AudioSegment.from_wav(wav_bytes)
 
 
+_TARGET_DBFS = -12.0          # loudness every clip is brought to before the final peak normalisation
+_PEAK_HEADROOM_DB = 0.1
+
+
 def apply_filters(segment, compression: bool = False):
-    """Post-process a segment to about -12 dBFS with 0.1 dB peak headroom (audio_util.py:39-72)."""
+    """Loudness post-processing of a reconstructed clip (audio_util.py:39-72): optional dynamic-range compression (pydub
+    only), then gain to -12 dBFS and a peak normalisation that leaves 0.1 dB of headroom."""
     if compression:
         if not HAVE_PYDUB:
             raise NotImplementedError("compress_dynamic_range needs pydub (not installed)")
-        segment = _normalize(segment, headroom=0.1)
-        segment = segment.apply_gain(-10 - segment.dBFS)
-        segment = pydub.effects.compress_dynamic_range(
-            segment, threshold=-20.0, ratio=4.0, attack=5.0, release=50.0)
-    desired_db = -12
-    segment = segment.apply_gain(desired_db - segment.dBFS)
-    return _normalize(segment, headroom=0.1)
+        levelled = _normalize(segment, headroom=_PEAK_HEADROOM_DB)
+        levelled = levelled.apply_gain(-10 - levelled.dBFS)
+        segment = pydub.effects.compress_dynamic_range(levelled, threshold=-20.0, ratio=4.0, attack=5.0, release=50.0)
+    at_target = segment.apply_gain(_TARGET_DBFS - segment.dBFS)
+    return _normalize(at_target, headroom=_PEAK_HEADROOM_DB)
 
 
 def stitch_segments(segments: T.Sequence, crossfade_s: float):
-    """Concatenate segments with a crossfade (audio_util.py:75-85)."""
-    crossfade_ms = int(crossfade_s * 1000)
-    combined = segments[0]
-    for segment in segments[1:]:
-        combined = combined.append(segment, crossfade=crossfade_ms)
-    return combined
+    """Play the segments one after another, blending each junction over `crossfade_s` seconds (audio_util.py:75-85)."""
+    fade_ms = int(crossfade_s * 1000)
+    return functools.reduce(lambda so_far, nxt: so_far.append(nxt, crossfade=fade_ms), segments[1:], segments[0])
 
 
 def overlay_segments(segments: T.Sequence):
-    """Mix segments on top of each other (audio_util.py:88-99)."""
+    """Mix all segments on top of the first one (audio_util.py:88-99)."""
     assert len(segments) > 0
-    output = None
-    for segment in segments:
-        output = segment if output is None else output.overlay(segment)
-    return output
+    return functools.reduce(lambda mix, nxt: mix.overlay(nxt), segments[1:], segments[0])

@@ -126,3 +126,27 @@ def test_interpolate_img2img_control_flow_matches_oracle_loop(monkeypatch):
         assert out["n_unet_evals"] == n_ref, (steps, sa, sb)
         err = float((out["latents"].float() - ref).norm() / ref.norm())
         assert err < 2e-2, (steps, err)            # fp16 latents through up to 38 guided steps
+
+
+def test_datatypes_schema_and_from_dict():
+    """same fields / order / defaults as riffusion/datatypes.py:10-73; from_dict = the server's dacite construction"""
+    import dataclasses
+
+    import pytest
+
+    from riffusion.datatypes import InferenceOutput
+
+    assert [f.name for f in dataclasses.fields(PromptInput)] == ["prompt", "seed", "negative_prompt", "denoising", "guidance"]
+    assert [f.name for f in dataclasses.fields(InferenceInput)] == ["start", "end", "alpha", "num_inference_steps",
+                                                                    "seed_image_id", "mask_image_id"]
+    assert [f.name for f in dataclasses.fields(InferenceOutput)] == ["image", "audio", "duration_s"]
+    p = PromptInput("a", 1)
+    assert (p.negative_prompt, p.denoising, p.guidance) == (None, 0.75, 7.0)
+    req = InferenceInput.from_dict({"alpha": 0.75, "num_inference_steps": 50, "seed_image_id": "og_beat",
+                                    "start": {"prompt": "church bells on sunday", "seed": 42},
+                                    "end": {"prompt": "jazz with piano", "seed": 123, "denoising": 0.8}})     # README.md:155-171
+    assert req.start == PromptInput("church bells on sunday", 42) and req.end.denoising == 0.8 and req.mask_image_id is None
+    with pytest.raises(KeyError):
+        InferenceInput.from_dict({"alpha": 0.1, "start": {"prompt": "x", "seed": 1, "bogus": 2}, "end": {"prompt": "y", "seed": 2}})
+    with pytest.raises(dataclasses.FrozenInstanceError):
+        req.alpha = 0.5
