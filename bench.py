@@ -450,7 +450,6 @@ def main_clip(args) -> None:
     from riffusion.spectrogram_params import SpectrogramParams
     from riffusion.unet_b200 import UNetB200
     from riffusion.vae_b200 import VaeB200
-    from riffusion.util import torch_util
 
     lib = _native.lib()
     # frozen weights: created on rank 0 and broadcast once over NCCL (init only; no collective in the step loop)

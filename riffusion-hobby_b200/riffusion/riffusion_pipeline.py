@@ -14,7 +14,6 @@ encoder is supplied, otherwise callers pass text embeddings directly.
 """
 from __future__ import annotations
 
-import dataclasses
 import functools
 import inspect
 import typing as T
