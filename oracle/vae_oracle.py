@@ -142,3 +142,16 @@ class AutoencoderKLOracle(nn.Module):
         """(mean, logvar) of DiagonalGaussianDistribution; sample = mean + exp(0.5 logvar) * eps"""
         mean, logvar = self.quant_conv(self.encoder(x)).chunk(2, dim=1)
         return mean, logvar.clamp(-30.0, 20.0)
+
+
+def u8_from_image_fp16(image_fp16: torch.Tensor):
+    """riffusion/riffusion_pipeline.py:430-434 on the reference's fp16 CUDA path, restated on the host:
+    `(image / 2 + 0.5).clamp(0, 1)` on an fp16 tensor (one fp16 rounding per op), `.cpu().permute(0, 2, 3, 1).numpy()`
+    (a float16 array), then DiffusionPipeline.numpy_to_pil `(images * 255).round().astype("uint8")` in float16.
+    image_fp16: (B, 3, H, W) torch.float16 -> (B, H, W, 3) uint8 numpy."""
+    assert image_fp16.dtype == torch.float16
+    x = image_fp16.detach().cpu()
+    x = ((x / 2) + 0.5).clamp(0, 1)
+    arr = x.permute(0, 2, 3, 1).numpy()
+    assert arr.dtype.name == "float16"
+    return (arr * 255).round().astype("uint8")

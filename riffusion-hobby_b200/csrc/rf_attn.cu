@@ -973,11 +973,8 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     constexpr int V_SLAB = ((NV * 128 + 1023) / 1024) * 1024;
     const size_t smem = static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NS) * (NSLAB * TK * 128 + 2 * V_SLAB) +
                         2 * (2 * TQ * 128) + 256 + 2 * 128 * 4 + 1024;
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [&] {
-        aerr = cudaFuncSetAttribute(k_flash_attn<DPAD, NV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    });
+    static rf_dev_once once;
+    const cudaError_t aerr = rf_set_smem_once(once, k_flash_attn<DPAD, NV, NS>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn): ") + cudaGetErrorString(aerr));
     k_flash_attn<DPAD, NV, NS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
     RF_CUDA_LAUNCH_CHECK("k_flash_attn");
@@ -993,11 +990,8 @@ int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
                             static_cast<size_t>(NVS) * KSL * V_SLAB + static_cast<size_t>(NG) * KSL * TQ * 128 + 512 +
                             NG * 128 * 4 + 1024;
     static_assert(smem <= 232448, "shared memory budget");
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [&] {
-        aerr = cudaFuncSetAttribute(k_flash_attn1<DPAD, NV, NKS, NVS, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    });
+    static rf_dev_once once;
+    const cudaError_t aerr = rf_set_smem_once(once, k_flash_attn1<DPAD, NV, NKS, NVS, NG>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn1): ") + cudaGetErrorString(aerr));
     k_flash_attn1<DPAD, NV, NKS, NVS, NG><<<grid, 96 + 128 * NG, smem, st>>>(mq, mk, mv, p);
     RF_CUDA_LAUNCH_CHECK("k_flash_attn1");
@@ -1012,14 +1006,14 @@ int launch_attn_short(const CUtensorMap& mq, const CUtensorMap& mk, const CUtens
     constexpr size_t smem = 2 * static_cast<size_t>(NSLAB) * TQ * 128 + static_cast<size_t>(NSLAB) * TK * 128 + 2 * V_SLAB +
                             2 * (2 * TQ * 128) + 256 + 1024;
     static_assert(smem <= 232448, "shared memory budget");
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    static int num_sms = 148;
-    std::call_once(once, [&] {
-        aerr = cudaFuncSetAttribute(k_attn_short<DPAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    });
+    static rf_dev_once once;
+    const cudaError_t aerr = rf_set_smem_once(once, k_attn_short<DPAD, NV>, int(smem));
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        num_sms = n;
+    }
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_attn_short): ") + cudaGetErrorString(aerr));
     const int nqb = (p.Nq + TQ - 1) / TQ;
     const int n_items = nqb * p.heads * B;

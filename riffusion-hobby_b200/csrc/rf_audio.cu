@@ -65,7 +65,16 @@ static cudaError_t upload(rf_plan* p, T** dst, const void* src, size_t count) {
 
 static int rf_plan_upload(rf_plan* p) {
     std::lock_guard<std::mutex> lk(p->mu);
-    if (p->uploaded) return RF_OK;
+    if (p->uploaded) {
+        // the tables live on the device that was current at first use: a plan is bound to that device
+        int cur = 0;
+        RF_CUDA_TRY(cudaGetDevice(&cur));
+        if (cur != p->device)
+            return rf_fail(RF_ERR_INVALID, "rf_plan: plan tables were uploaded to cuda:" + std::to_string(p->device) +
+                                               " but the current device is cuda:" + std::to_string(cur) +
+                                               " (create one plan per device)");
+        return RF_OK;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -675,21 +684,13 @@ static int check_T(const rf_plan* p, int T, const char* who) {
 }
 
 static int set_smem_attrs() {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
-        err = cudaFuncSetAttribute(k_istft_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(k_istft_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(k_stft_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(k_stft_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(k_stft_mel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(k_inverse_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    });
+    static rf_dev_once once[6];
+    cudaError_t err = rf_set_smem_once(once[0], k_istft_chunk, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[1], k_istft_dec, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[2], k_stft_pair, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[3], k_stft_dec, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[4], k_stft_mel_pair, 227 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[5], k_inverse_mel, 200 * 1024);
     if (err != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
     return RF_OK;
 }

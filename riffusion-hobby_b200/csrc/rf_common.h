@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <string>
 
@@ -24,3 +25,21 @@ int rf_fail(int code, const std::string& msg);
             return rf_fail(RF_ERR_CUDA, std::string("launch ") + name + ": " +                 \
                                             cudaGetErrorString(_e));                           \
     } while (0)
+
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: remember it per (call site,
+// device) so that a process driving several GPUs sets it on each of them.  Up to 64 devices.
+struct rf_dev_once {
+    std::atomic<unsigned long long> done{0};
+};
+template <class F>
+inline cudaError_t rf_set_smem_once(rf_dev_once& o, F* func, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (o.done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) o.done.fetch_or(bit, std::memory_order_release);
+    return e;
+}

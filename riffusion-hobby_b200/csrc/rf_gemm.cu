@@ -456,11 +456,8 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     }
     const int n_tiles = static_cast<int>(grid.x * grid.y * grid.z);
     grid = dim3(static_cast<unsigned>(n_tiles < num_sms ? n_tiles : num_sms));
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [&] {
-        aerr = cudaFuncSetAttribute(k_tc_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    });
+    static rf_dev_once once;
+    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(aerr));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = g_prof.on;

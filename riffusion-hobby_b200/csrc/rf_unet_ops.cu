@@ -560,9 +560,12 @@ __global__ void k_vae_to_u8(const __half* __restrict__ x, int B, size_t HW, uint
         const size_t b = i / HW, p = i % HW;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float v = __half2float(x[(b * 3 + c) * HW + p]);       // fp16 tensor, upcast like image.float()
-            v = fminf(fmaxf(v / 2.f + 0.5f, 0.f), 1.f);
-            y[i * 3 + c] = static_cast<uint8_t>(rintf(v * 255.f));
+            // riffusion_pipeline.py:430-434 on the reference's fp16 CUDA path: `(image / 2 + 0.5).clamp(0, 1)` is fp16
+            // tensor arithmetic (one rounding per op), `.numpy()` keeps float16, and numpy_to_pil's `(images * 255).round()`
+            // is float16 arithmetic too (product rounded to fp16, then round-half-even) -> the same ops in __half here
+            const __half h = __hadd(__hmul(x[(b * 3 + c) * HW + p], __float2half(0.5f)), __float2half(0.5f));
+            const __half cl = __hmin(__hmax(h, __float2half(0.f)), __float2half(1.f));
+            y[i * 3 + c] = static_cast<uint8_t>(__half2int_rn(hrint(__hmul(cl, __float2half(255.f)))));
         }
     }
 }

@@ -235,13 +235,21 @@ class RiffusionPipeline:
                 m = mask.to(device=dev, dtype=latents_dtype).expand_as(latents).contiguous()
                 latents = self.scheduler.add_noise(init_latents_orig, noise, t_int, mask=m, blend_with=latents)
 
-        out: T.Dict[str, T.Any] = dict(latents=latents, nsfw_content_detected=False, n_unet_evals=n_evals)
+        # :427 — the reference rescales in fp16 (`1.0 / 0.18215 * latents`) and returns THAT tensor under "latents"; the
+        # un-scaled loop state and the evaluation count are extra keys of this implementation
+        scaled = (1.0 / VAE_SCALE) * latents
+        out: T.Dict[str, T.Any] = dict(latents=scaled, nsfw_content_detected=False, latents_unscaled=latents,
+                                       n_unet_evals=n_evals)
         if output_type == "latent" or self.vae is None:
             out["images"] = None
             return out
-        image = self.vae.decode(latents, scale=1.0 / VAE_SCALE).sample                              # :427-428
-        image = (image.float() / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()             # :430-431
-        out["images"] = self.numpy_to_pil(image) if output_type == "pil" else image
+        image = self.vae.decode(scaled).sample                                                       # :428
+        if output_type == "pil":
+            # :430-434 `(image / 2 + 0.5).clamp(0, 1)` -> numpy_to_pil, in the fp16 arithmetic of the reference's CUDA path
+            u8 = ops.vae_image_to_u8(image).cpu().numpy()
+            out["images"] = [Image.fromarray(im) for im in u8]
+        else:
+            out["images"] = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()         # float16 array, like the reference
         return out
 
     # ------------------------------------------------------------------------------ batched request -> audio
@@ -260,8 +268,8 @@ class RiffusionPipeline:
             text_embeddings=text_embeddings, init_latents=init_latents, generator_a=None, generator_b=None,
             interpolate_alpha=0.0, strength_a=strength, strength_b=strength, num_inference_steps=num_inference_steps,
             guidance_scale=guidance_scale, uncond_embeddings=uncond_embeddings, noise=noise, output_type="latent")
-        latents = out["latents"]
-        image = self.vae.decode(latents, scale=1.0 / VAE_SCALE).sample
+        latents = out["latents_unscaled"]
+        image = self.vae.decode(out["latents"]).sample
         u8 = ops.vae_image_to_u8(image)
         B, H, W, _ = u8.shape
         mel = torch.empty((B, H, W), dtype=torch.float32, device=u8.device)
@@ -271,7 +279,8 @@ class RiffusionPipeline:
             _native.check(lib.rf_image_to_mel(u8[i].data_ptr(), H, W, 0, float(p.power_for_image), 30e6, mel[i].data_ptr(),
                                               _native.stream_ptr(u8.device)))
         wave = converter.waveform_from_mel_amplitudes(mel, init_angles)
-        return dict(images=u8, waveform=wave, latents=latents, n_unet_evals=out["n_unet_evals"])
+        return dict(images=u8, waveform=wave, latents=out["latents"], latents_unscaled=latents,
+                    n_unet_evals=out["n_unet_evals"])
 
     @staticmethod
     def numpy_to_pil(images: np.ndarray) -> T.List[Image.Image]:

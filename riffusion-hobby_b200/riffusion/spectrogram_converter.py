@@ -84,8 +84,19 @@ _PLAN_CACHE: T.Dict[T.Tuple, _native.Plan] = {}
 _PLAN_LOCK = threading.Lock()
 
 
-def get_plan(p: SpectrogramParams, full_band: bool) -> _native.Plan:
-    key = (p.sample_rate, p.n_fft, p.win_length, p.hop_length, p.num_frequencies, p.min_frequency,
+def _device_index(device) -> int:
+    if device is None:
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+    d = torch.device(device)
+    if d.index is not None:
+        return d.index
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
+def get_plan(p: SpectrogramParams, full_band: bool, device=None) -> _native.Plan:
+    """One plan per (geometry, device): the device tables of a plan are uploaded on first use to the device that is
+    current then and stay bound to it (rf_plan checks it), so a second GPU in the same process gets its own plan."""
+    key = (_device_index(device), p.sample_rate, p.n_fft, p.win_length, p.hop_length, p.num_frequencies, p.min_frequency,
            p.max_frequency, p.mel_scale_norm, p.mel_scale_type, bool(full_band))
     with _PLAN_LOCK:
         plan = _PLAN_CACHE.get(key)
@@ -133,8 +144,8 @@ class Spectrogram(_Transform):
     as configured at spectrogram_converter.py:47-59."""
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:
-        plan = get_plan(self.p, full_band=True)
         x, lead = _flatten(_native.require_cuda(waveform, "waveform", torch.float32), 1)
+        plan = get_plan(self.p, full_band=True, device=x.device)
         B, L = x.shape
         Tn = 1 + L // self.p.hop_length
         spec = torch.empty((B, plan.info.n_freq, Tn), dtype=torch.complex64, device=x.device)
@@ -148,8 +159,8 @@ class MelScale(_Transform):
     """torchaudio.transforms.MelScale as configured at spectrogram_converter.py:75-84."""
 
     def forward(self, specgram: torch.Tensor) -> torch.Tensor:
-        plan = get_plan(self.p, full_band=True)
         s, lead = _flatten(_native.require_cuda(specgram, "specgram", torch.float32), 2)
+        plan = get_plan(self.p, full_band=True, device=s.device)
         B, F, Tn = s.shape
         if F != plan.info.n_freq:
             raise ValueError(f"Expected {plan.info.n_freq} frequency bins. Found: {F}")
@@ -166,8 +177,8 @@ class InverseMelScale(_Transform):
     reproducible and not implemented; `max_mel_iters` is accepted and ignored."""
 
     def forward(self, melspec: torch.Tensor) -> torch.Tensor:
-        plan = get_plan(self.p, full_band=False)
         m, lead = _flatten(_native.require_cuda(melspec, "melspec", torch.float32), 2)
+        plan = get_plan(self.p, full_band=False, device=m.device)
         B, n_mels, Tn = m.shape
         if n_mels != self.p.num_frequencies:
             raise ValueError("Expected an input with {} mel bins. Found: {}".format(self.p.num_frequencies, n_mels))
@@ -185,8 +196,8 @@ class GriffinLim(_Transform):
     momentum = 0.99
 
     def forward(self, specgram: torch.Tensor, init_angles: T.Optional[torch.Tensor] = None) -> torch.Tensor:
-        plan = get_plan(self.p, full_band=True)
         s, lead = _flatten(_native.require_cuda(specgram, "specgram", torch.float32), 2)
+        plan = get_plan(self.p, full_band=True, device=s.device)
         B, F, Tn = s.shape
         if F != plan.info.n_freq:
             raise ValueError(f"Expected {plan.info.n_freq} frequency bins. Found: {F}")
@@ -227,7 +238,7 @@ class SpectrogramConverter:
                 "in CUDA kernels only; there is no CPU implementation"
             )
         # validates the geometry now (raises NotImplementedError for unsupported sizes)
-        get_plan(params, full_band=False)
+        get_plan(params, full_band=False, device=self.device)
 
         self.spectrogram_func = Spectrogram(params, self.device)
         self.inverse_spectrogram_func = GriffinLim(params, self.device)
@@ -258,8 +269,8 @@ class SpectrogramConverter:
     def mel_amplitudes_from_waveform(self, waveform: torch.Tensor) -> torch.Tensor:
         """(batch, samples) -> (batch, n_mels, frames): STFT, magnitude and mel projection in one
         kernel (spectrogram_converter.py:165-185)."""
-        plan = get_plan(self.p, full_band=False)
         x, lead = _flatten(_native.require_cuda(waveform, "waveform", torch.float32), 1)
+        plan = get_plan(self.p, full_band=False, device=x.device)
         B, L = x.shape
         Tn = 1 + L // self.p.hop_length
         mel = torch.empty((B, self.p.num_frequencies, Tn), dtype=torch.float32, device=x.device)
@@ -274,8 +285,8 @@ class SpectrogramConverter:
         """(batch, n_mels, frames) -> (batch, hop*(frames-1)): inverse mel + Griffin-Lim, fused
         (spectrogram_converter.py:187-204).  `init_angles` (batch, n_freq, frames) complex64
         overrides the random phase initialisation (used by the parity tests)."""
-        plan = get_plan(self.p, full_band=False)
         m, lead = _flatten(_native.require_cuda(amplitudes_mel, "amplitudes_mel", torch.float32), 2)
+        plan = get_plan(self.p, full_band=False, device=m.device)
         B, n_mels, Tn = m.shape
         if n_mels != self.p.num_frequencies:
             raise ValueError("Expected an input with {} mel bins. Found: {}".format(self.p.num_frequencies, n_mels))

@@ -206,7 +206,7 @@ def test_denoising_loop_matches_oracle_loop(native_lib):
                                        num_inference_steps=steps, guidance_scale=7.0, uncond_embeddings=uncond,
                                        noise_a=na, noise_b=nb, output_type="latent")
         assert out["n_unet_evals"] == n_ref
-        e = rel_l2(out["latents"], ref)
+        e = rel_l2(out["latents_unscaled"], ref)
         print(f"loop steps={steps} strength={strength}: evals {n_ref}, rel_l2 {e:.3e}")
         assert e < 2e-2          # fp16 latents through n_ref guided steps (guidance 7 amplifies eps rounding 7x)
 
@@ -229,7 +229,7 @@ def test_cuda_graph_reuse_with_new_context(native_lib):
         return pipe.interpolate_img2img(text_embeddings=text, init_latents=lat, generator_a=None, generator_b=None,
                                         interpolate_alpha=0.0, strength_a=1.0, strength_b=1.0, num_inference_steps=4,
                                         guidance_scale=7.0, uncond_embeddings=uncond, noise=noise,
-                                        output_type="latent")["latents"]
+                                        output_type="latent")["latents_unscaled"]
 
     t1 = torch.randn(2, 77, 64, device="cuda").half()
     t2 = torch.randn(2, 77, 64, device="cuda").half()
