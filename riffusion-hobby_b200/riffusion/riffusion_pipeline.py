@@ -102,11 +102,16 @@ class RiffusionPipeline:
 
     @functools.lru_cache()
     def embed_text_weighted(self, text) -> torch.Tensor:
-        """The reference routes through the (word:1.2) prompt-weighting parser (external/prompt_weighting.py),
-        which is out of scope here; un-weighted prompts give the same embedding as `embed_text`."""
-        if any(ch in text for ch in "()[]"):
-            raise NotImplementedError("prompt attention weighting '(word:1.2)' is outside this build's scope")
-        return self.embed_text(text)
+        """CLIP embedding with "(word:1.2)" / "[word]" attention weights (riffusion_pipeline.py:193-206 ->
+        external/prompt_weighting.py:236-372): parse, encode in chunks of 75 tokens, scale token rows by their weights,
+        restore the mean."""
+        from riffusion.external.prompt_weighting import get_weighted_text_embeddings
+
+        if self.tokenizer is None or self.text_encoder is None:
+            raise RuntimeError("no text encoder loaded: pass text embeddings to interpolate_img2img directly")
+        with torch.no_grad():
+            return get_weighted_text_embeddings(pipe=self, prompt=text, uncond_prompt=None, max_embeddings_multiples=3,
+                                                no_boseos_middle=False, skip_parsing=False, skip_weighting=False)[0]
 
     # ------------------------------------------------------------------------------ riffuse
     @torch.no_grad()
