@@ -138,6 +138,55 @@ class RiffusionPipeline:
             num_inference_steps=inputs.num_inference_steps, guidance_scale=guidance_scale)
         return outputs["images"][0]
 
+    @torch.no_grad()
+    def riffuse_batch(self, inputs: T.Sequence[InferenceInput], init_images: T.Union[Image.Image, T.Sequence[Image.Image]],
+                      mask_image: T.Optional[Image.Image] = None, use_reweighting: bool = True) -> T.List[Image.Image]:
+        """`riffuse` for a list of requests in one batched denoising loop — what
+        streamlit/tasks/interpolation.py:146-164 does one request at a time.  Every request draws exactly what `riffuse`
+        draws for it (posterior noise and noise_a from generator(start.seed), noise_b from generator(end.seed), per-request
+        alpha for the slerp and the prompt interpolation), so result i equals `riffuse(inputs[i], ...)` up to the batch-size
+        dependent accumulation order of the kernels.  Requests are grouped by (strength, guidance, steps): the PNDM state
+        and the guidance scalar are shared inside a group."""
+        images = [init_images] * len(inputs) if isinstance(init_images, Image.Image) else list(init_images)
+        assert len(images) == len(inputs)
+        embed = self.embed_text_weighted if use_reweighting else self.embed_text
+        groups: T.Dict[T.Tuple, T.List[int]] = {}
+        for i, inp in enumerate(inputs):
+            a = inp.alpha
+            strength = (1 - a) * inp.start.denoising + a * inp.end.denoising
+            guidance = inp.start.guidance * (1.0 - a) + inp.end.guidance * a
+            groups.setdefault((round(strength, 9), round(guidance, 9), inp.num_inference_steps), []).append(i)
+        mask = None
+        if mask_image:
+            vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
+            mask = preprocess_mask(mask_image, scale_factor=vae_scale_factor).to(device=self.device, dtype=torch.float16)
+        results: T.List[T.Optional[Image.Image]] = [None] * len(inputs)
+        for (strength, guidance, steps), idx in groups.items():
+            texts, lats, nas, nbs, alphas = [], [], [], [], []
+            for i in idx:
+                inp = inputs[i]
+                e0, e1 = embed(inp.start.prompt), embed(inp.end.prompt)
+                texts.append(e0 + inp.alpha * (e1 - e0))
+                lats.append(self.encode_image(images[i], torch.Generator(device=self.device).manual_seed(inp.start.seed)))
+                ga = torch.Generator(device=self.device).manual_seed(inp.start.seed)
+                gb = torch.Generator(device=self.device).manual_seed(inp.end.seed)
+                shape = lats[-1].shape
+                nas.append(torch.randn(shape, generator=ga, device=self.device, dtype=torch.float16))
+                nbs.append(torch.randn(shape, generator=gb, device=self.device, dtype=torch.float16))
+                alphas.append(float(inp.alpha))
+            na, nb = torch.cat(nas), torch.cat(nbs)
+            if self.device_slerp:
+                noise = ops.slerp(alphas, na, nb)
+            else:
+                noise = torch.cat([torch_util.slerp(al, na[j:j + 1], nb[j:j + 1]) for j, al in enumerate(alphas)])
+            out = self.interpolate_img2img(
+                text_embeddings=torch.cat(texts), init_latents=torch.cat(lats), mask=mask, generator_a=None, generator_b=None,
+                interpolate_alpha=0.0, strength_a=strength, strength_b=strength, num_inference_steps=steps,
+                guidance_scale=guidance, noise=noise)
+            for j, i in enumerate(idx):
+                results[i] = out["images"][j]
+        return results  # type: ignore[return-value]
+
     def encode_image(self, init_image: Image.Image, generator: torch.Generator) -> torch.Tensor:
         """preprocess + VAE posterior sample * 0.18215 (:252-264).  The (mean, logvar) moments only depend on the
         image and are cached; the posterior noise is drawn from `generator` like the reference."""
@@ -174,9 +223,14 @@ class RiffusionPipeline:
         do_cfg = guidance_scale > 1.0
         if do_cfg:
             if uncond_embeddings is None:
-                uncond_tokens = [""] if negative_prompt is None else ([negative_prompt] if isinstance(negative_prompt, str) else negative_prompt)
-                if len(uncond_tokens) != batch_size:
+                if negative_prompt is None:                                    # :328-335
+                    uncond_tokens = [""]
+                elif isinstance(negative_prompt, str):
+                    uncond_tokens = [negative_prompt]
+                elif batch_size != len(negative_prompt):
                     raise ValueError("The length of `negative_prompt` should be equal to batch_size.")
+                else:
+                    uncond_tokens = list(negative_prompt)
                 if self.tokenizer is None:
                     raise RuntimeError("classifier-free guidance needs the CLIP embedding of ''; pass uncond_embeddings")
                 ids = self.tokenizer(uncond_tokens, padding="max_length", max_length=self.tokenizer.model_max_length,

@@ -30,7 +30,8 @@ class _Out(types.SimpleNamespace):
 
 
 def _h(t: torch.Tensor, device) -> torch.Tensor:
-    return t.detach().to(device=device, dtype=torch.float16).contiguous()
+    """fp16 copy on `device`; a host tensor is converted on the host so that loading a checkpoint is memcpy only"""
+    return t.detach().to(dtype=torch.float16).contiguous().to(device)
 
 
 class UNetB200:
@@ -47,11 +48,11 @@ class UNetB200:
         dev = self.device
         for name, p in state_dict.items():
             if p.dim() == 4 and p.shape[2] == 3 and not name.endswith("conv_in.weight"):
-                self.w[name] = ops.pack_conv_weight(p.to(dev))               # (Cout, 3, 3, Cin)
+                self.w[name] = ops.pack_conv_weight(p.detach()).to(dev)      # (Cout, 3, 3, Cin), packed where the tensor lives
             elif p.dim() == 4 and p.shape[2] == 1:
                 self.w[name] = _h(p.reshape(p.shape[0], p.shape[1]), dev)    # 1x1 conv == linear over pixels
             elif ".ff.net.0.proj." in name:
-                self.w[name] = ops.interleave_geglu(_h(p, dev))              # value/gate rows paired for the epilogue
+                self.w[name] = ops.interleave_geglu(p.detach().to(torch.float16)).to(dev)   # value/gate rows paired for the epilogue
             else:
                 self.w[name] = _h(p, dev)
         # all resnets' time_emb_proj (Linear 1280 -> cout) stacked into one GEMM per forward

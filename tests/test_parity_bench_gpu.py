@@ -301,25 +301,21 @@ def test_generate_clips_50_evals_small_unet(small_unet, vae_pair, conv):
 
 
 # ----------------------------------------------------------------------------------------------- riffuse()
-class _StubTokenizer:
-    """stand-in for CLIPTokenizer in the riffuse() test (the text encoder is outside rows b-1..b-6): character codes"""
-    model_max_length = 77
+def _StubTokenizer():
+    """stand-in for CLIPTokenizer (the text encoder is outside rows b-1..b-6): tests/golden/prompt_stub.py"""
+    import sys
+    from pathlib import Path
 
-    def __call__(self, text, padding=None, max_length=77, truncation=True, return_tensors="pt"):
-        texts = [text] if isinstance(text, str) else list(text)
-        ids = torch.zeros((len(texts), max_length), dtype=torch.long)
-        for r, s in enumerate(texts):
-            codes = [1 + (ord(c) % 250) for c in s][: max_length]
-            ids[r, : len(codes)] = torch.tensor(codes, dtype=torch.long)
-        import types
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    from prompt_stub import StubTokenizer
 
-        return types.SimpleNamespace(input_ids=ids)
+    return StubTokenizer()
 
 
 class _StubTextEncoder:
     def __init__(self, dim=768):
         g = torch.Generator().manual_seed(123)
-        self.table = torch.randn(256, dim, generator=g).cuda()
+        self.table = torch.randn(49408, dim, generator=g).cuda()
         self.pos = torch.randn(77, dim, generator=g).cuda() * 0.3
 
     def __call__(self, ids):
@@ -406,3 +402,35 @@ def test_riffuse_pil_to_pil_with_mask(sd15, vae_pair):
             keep = (mask[0, 0] > 0.99)
             assert keep.any()
             assert rel_l2(out["latents_unscaled"][0][:, keep], ref[0][:, keep]) < 2e-3
+
+
+@torch.no_grad()
+def test_riffuse_batch_equals_single_requests(small_unet, vae_pair):
+    """`riffuse_batch` runs a list of InferenceInput in one batched loop; request i must reproduce
+    `riffuse(inputs[i])` (same generator draws, per-request alpha) up to batch-size dependent accumulation order."""
+    from pathlib import Path
+
+    from PIL import Image
+
+    from riffusion.datatypes import InferenceInput, PromptInput
+    from riffusion.riffusion_pipeline import RiffusionPipeline
+
+    _, unet = small_unet
+    _, vae = vae_pair
+    pipe = RiffusionPipeline(vae=vae, unet=unet, text_encoder=_StubTextEncoder(dim=64), tokenizer=_StubTokenizer(), device="cuda")
+    rgb = np.load(Path(__file__).parent / "golden" / "og_beat.npz")["rgb"]
+    init_image = Image.fromarray(rgb, mode="RGB")
+    reqs = [InferenceInput(alpha=a, num_inference_steps=20, seed_image_id="og_beat",
+                           start=PromptInput(prompt="church bells on sunday", seed=42 + i, denoising=0.75, guidance=7.0),
+                           end=PromptInput(prompt="jazz with (piano:1.2)", seed=123 + i, denoising=0.75, guidance=7.0))
+            for i, a in enumerate((0.0, 0.3, 1.0))]
+    reqs.append(InferenceInput(alpha=0.5, num_inference_steps=20, seed_image_id="og_beat",            # its own group
+                               start=PromptInput(prompt="a", seed=1, denoising=0.5), end=PromptInput(prompt="b", seed=2, denoising=0.5)))
+    batch = pipe.riffuse_batch(reqs, init_image)
+    assert len(batch) == 4 and all(im.size == (512, 512) for im in batch)
+    for i, r in enumerate(reqs):
+        single = pipe.riffuse(r, init_image)
+        d = np.abs(np.array(batch[i]).astype(np.int16) - np.array(single).astype(np.int16))
+        print(f"riffuse_batch request {i}: vs riffuse() mean |diff| {d.mean():.4f} LSB, max {d.max()}, equal pixels {100 * (d == 0).mean():.1f} %")
+        assert d.mean() < 0.25 and (d <= 1).mean() > 0.98
+    assert np.abs(np.array(batch[0]).astype(np.int16) - np.array(batch[2]).astype(np.int16)).mean() > 0.5   # requests differ
