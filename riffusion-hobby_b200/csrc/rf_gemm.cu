@@ -81,12 +81,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 //   warps 2-17: epilogue (4 sets x 4 warps) — drain buffer i&1 (tcgen05.ld -> bias/act/residual -> global) while the MMA warp already works
 //              on tile i+1 in the other buffer; arrive tmem_empty[i&1] (256 threads) when done
 // Tile order: n fastest, then m, then batch, so CTAs running at the same time share activation rows in L2.
-template <int BN, int STAGES>
+//
+// PAIR = true: the same kernel for a CTA pair (cluster of 2, cta_group::2).  A work unit is a 256 x BN tile: CTA rank r owns
+// the 128-row block m_blk = 2 * pair_row + r (its own A rows, its own TMEM accumulator rows, its own epilogue) and stages
+// only columns [r * BN/2, +BN/2) of the B tile; the leader (rank 0) issues one 256-row MMA per K step that reads both CTAs'
+// shared memory.  Barriers: the TMA loads of both CTAs credit the leader's full[stage]; the leader's MMA commits are
+// multicast to empty[stage] / tmem_full[acc] of both CTAs; both epilogues arrive on the leader's tmem_empty[acc].
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int B_TILE_BYTES = BN * BK * 2;
+    constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
     constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM allocations are powers of two
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_TILE_BYTES;
@@ -97,8 +103,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // PAIR: tiles_m counts 256-row blocks (the host passes ceil(tiles_m / 2)); work units are walked by the pair
     const int tiles_mn = p.tiles_n * p.tiles_m;
     const int n_tiles = tiles_mn * p.batch1 * p.batch2 * p.splits;   // work units (== tiles when splits == 1)
+    const int rank = PAIR ? static_cast<int>(tc::cluster_ctarank()) : 0;
+    const int unit0 = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+    const int unit_step = PAIR ? gridDim.x >> 1 : gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -107,7 +117,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tmem_full[i], 1);
-            tc::mbar_init(&tmem_empty[i], 128 * EPI_SETS);
+            tc::mbar_init(&tmem_empty[i], (PAIR ? 2 : 1) * 4 * EPI_SETS);   // one arrival per epilogue warp (of both CTAs)
         }
         tc::fence_barrier_init();
     }
@@ -116,22 +126,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         tc::tma_prefetch_desc(&mapB);
     }
     if (warp == 1) {
-        tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
-        tc::tmem_relinquish();
+        if constexpr (PAIR) {
+            tc::tmem_alloc_pair(tmem_slot, 2 * ACC_COLS);
+            tc::tmem_relinquish_pair();
+        } else {
+            tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
+            tc::tmem_relinquish();
+        }
     }
     tc::fence_before_sync();
-    __syncthreads();
+    if constexpr (PAIR) tc::cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------ TMA producer
         int it = 0;
-        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
+        for (int unit = unit0; unit < n_tiles; unit += unit_step) {
             const int tile = unit / p.splits, sp = unit - tile * p.splits;
             const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
-            const int m_blk = mn / p.tiles_n, n_blk = mn - m_blk * p.tiles_n;
+            const int m_row = mn / p.tiles_n, n_blk = mn - m_row * p.tiles_n;
+            const int m_blk = PAIR ? 2 * m_row + rank : m_row;
             const int b1 = z % p.batch1, b2 = z / p.batch1;
             int tx = 0, ty = 0, tb = 0;
             if (p.conv) {
@@ -139,35 +156,57 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 ty = (m_blk / p.tiles_x) % p.tiles_y;
                 tb = m_blk / (p.tiles_x * p.tiles_y);
             }
+            const int n0 = n_blk * BN + (PAIR ? rank * (BN / 2) : 0);      // this CTA's rows of the B tile
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t phase = (it / STAGES) & 1;
                 tc::mbar_wait(&empty[stage], phase ^ 1);
-                tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
                 void* dstA = sA + stage * A_TILE_BYTES;
                 void* dstB = sB + stage * B_TILE_BYTES;
-                if (!p.conv) {
-                    tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
-                    tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, b1 * p.b_m1, b2 * p.b_m2);
+                if constexpr (PAIR) {
+                    // only the leader posts the byte count: the loads of BOTH CTAs are credited to its barrier
+                    if (rank == 0) tc::mbar_expect_tx(&full[stage], 2 * (A_TILE_BYTES + B_TILE_BYTES));
+                    const uint32_t fb = tc::mapa_u32(tc::smem_u32(&full[stage]), 0);
+                    if (!p.conv) {
+                        tc::tma_load_4d_pair(&mapA0, fb, dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
+                        tc::tma_load_4d_pair(&mapB, fb, dstB, kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
+                    } else {
+                        const int kct = p.kc1 + p.kc2;
+                        const int tap = kb / kct, kc = kb - tap * kct;
+                        const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
+                        const int x0 = tx * p.bw * p.stride + dx - p.pad;
+                        const int y0 = ty * p.bh * p.stride + dy - p.pad;
+                        if (kc < p.kc1)
+                            tc::tma_load_4d_pair(&mapA0, fb, dstA, kc * BK, x0, y0, tb * p.bb);
+                        else
+                            tc::tma_load_4d_pair(&mapA1, fb, dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
+                        tc::tma_load_4d_pair(&mapB, fb, dstB, kb * BK, n0, 0, 0);
+                    }
                 } else {
-                    const int kct = p.kc1 + p.kc2;
-                    const int tap = kb / kct, kc = kb - tap * kct;
-                    const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
-                    const int x0 = tx * p.bw * p.stride + dx - p.pad;
-                    const int y0 = ty * p.bh * p.stride + dy - p.pad;
-                    if (kc < p.kc1)
-                        tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
-                    else
-                        tc::tma_load_4d(&mapA1, &full[stage], dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
-                    tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n_blk * BN, 0, 0);
+                    tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
+                    if (!p.conv) {
+                        tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
+                        tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
+                    } else {
+                        const int kct = p.kc1 + p.kc2;
+                        const int tap = kb / kct, kc = kb - tap * kct;
+                        const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
+                        const int x0 = tx * p.bw * p.stride + dx - p.pad;
+                        const int y0 = ty * p.bh * p.stride + dy - p.pad;
+                        if (kc < p.kc1)
+                            tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
+                        else
+                            tc::tma_load_4d(&mapA1, &full[stage], dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
+                        tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, 0, 0);
+                    }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = tc::make_idesc_f16(BM, BN);
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
+        constexpr uint32_t idesc = tc::make_idesc_f16(PAIR ? 2 * BM : BM, BN);
         int it = 0, lt = 0;
-        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++lt) {
+        for (int unit = unit0; unit < n_tiles; unit += unit_step, ++lt) {
             const int sp = unit % p.splits;
             const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int acc = lt & 1;
@@ -187,11 +226,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
                     const uint64_t db = tc::make_desc_sw128(b_base + k * 32);
-                    tc::mma_f16(d_tmem, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                    if constexpr (PAIR) tc::mma_f16_pair(d_tmem, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                    else tc::mma_f16(d_tmem, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
                 }
-                tc::mma_commit(&empty[stage]);
+                if constexpr (PAIR) tc::mma_commit_pair(&empty[stage]);
+                else tc::mma_commit(&empty[stage]);
             }
-            tc::mma_commit(&tmem_full[acc]);
+            if constexpr (PAIR) tc::mma_commit_pair(&tmem_full[acc]);
+            else tc::mma_commit(&tmem_full[acc]);
         }
     } else if (warp >= 2) {
         // ------------------------------------------------------------ epilogue (EPI_SETS x 4 warps)
@@ -211,11 +253,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             }
         };
         int lt = 0;
-        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++lt) {
+        const uint32_t tmem_empty_leader = PAIR ? tc::mapa_u32(tc::smem_u32(&tmem_empty[0]), 0) : 0;
+        for (int unit = unit0; unit < n_tiles; unit += unit_step, ++lt) {
             const int tile = unit / p.splits, sp = unit - tile * p.splits;
             const int acc = lt & 1;
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
-            const int m_blk = mn / p.tiles_n, n_blk = mn - m_blk * p.tiles_n;
+            const int m_row = mn / p.tiles_n, n_blk = mn - m_row * p.tiles_n;
+            const int m_blk = PAIR ? 2 * m_row + rank : m_row;
             const int b1 = z % p.batch1, b2 = z / p.batch1;
             bool row_ok;
             long out_off, res_off;
@@ -379,14 +423,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 }
             }
             tc::fence_before_sync();
-            tc::mbar_arrive(&tmem_empty[acc]);   // all epilogue threads: the accumulator may be overwritten
+            __syncwarp();
+            if (lane == 0) {   // one arrival per epilogue warp: the accumulator may be overwritten
+                if constexpr (PAIR) tc::mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+                else tc::mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
     tc::fence_before_sync();
-    __syncthreads();
+    if constexpr (PAIR) tc::cluster_sync_all();   // the leader's MMAs read the peer's shared memory until the very end
+    else __syncthreads();
     if (warp == 1) {
         tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
+        if constexpr (PAIR) tc::tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
+        else tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }
 }
 
@@ -438,16 +488,16 @@ struct TcProfile {
     std::vector<cudaEvent_t> ev;   // begin/end pairs
     double flops = 0.0;
     long launches = 0;
-    struct Rec { int conv, M, N, K, batch, splits; };
+    struct Rec { int conv, M, N, K, batch, splits, bn; };   // bn < 0: CTA-pair kernel
     std::vector<Rec> recs;
 };
 TcProfile g_prof;
 std::mutex g_prof_mu;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
            cudaStream_t st) {   // `grid` arrives as (tiles_n, tiles_m, batch) and is flattened to a persistent 1-D grid
-    const size_t smem = static_cast<size_t>(STAGES) * (A_TILE_BYTES + BN * BK * 2) + 1024;
+    const size_t smem = static_cast<size_t>(STAGES) * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -455,9 +505,14 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         RF_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int n_tiles = static_cast<int>(grid.x * grid.y * grid.z);
-    grid = dim3(static_cast<unsigned>(n_tiles < num_sms ? n_tiles : num_sms));
+    if (PAIR) {   // one CTA pair per TPC
+        const int pairs = num_sms / 2;
+        grid = dim3(static_cast<unsigned>(2 * (n_tiles < pairs ? n_tiles : pairs)));
+    } else {
+        grid = dim3(static_cast<unsigned>(n_tiles < num_sms ? n_tiles : num_sms));
+    }
     static rf_dev_once once;
-    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES>, int(smem));
+    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES, PAIR>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(aerr));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = g_prof.on;
@@ -466,7 +521,23 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         RF_CUDA_TRY(cudaEventCreate(&e1));
         RF_CUDA_TRY(cudaEventRecord(e0, st));
     }
-    k_tc_gemm<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
+    if (PAIR) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RF_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, PAIR>, a0, a1, b, p));
+    } else {
+        k_tc_gemm<BN, STAGES, PAIR><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
+    }
     RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
     if (prof) {
         RF_CUDA_TRY(cudaEventRecord(e1, st));
@@ -476,7 +547,8 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         g_prof.launches += 1;
         const double m = p.conv ? static_cast<double>(p.Bn) * p.Ho * p.Wo : static_cast<double>(p.M) * p.batch1 * p.batch2;
         g_prof.flops += 2.0 * m * p.N * p.K;
-        g_prof.recs.push_back({p.conv, p.conv ? p.Bn * p.Ho * p.Wo : p.M, p.N, p.K, p.batch1 * p.batch2, p.splits});
+        g_prof.recs.push_back({p.conv, p.conv ? p.Bn * p.Ho * p.Wo : p.M, p.N, p.K, p.batch1 * p.batch2, p.splits,
+                               PAIR ? -BN : BN});
     }
     return RF_OK;
 }
@@ -582,12 +654,58 @@ int num_sms_cached() {
     return n;
 }
 
-int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p, int tiles_m,
-             int nbatch, cudaStream_t st) {
-    // one persistent CTA per SM: 6-stage (BN=128/160) / 8-stage (BN=64) TMA ring, 2 TMEM accumulators
-    p.tiles_m = tiles_m;
-    const int bn = pick_bn(N, static_cast<long>(tiles_m) * nbatch);
+// Tile configuration of one problem: width BN and whether the CTA-pair kernel (256 x BN tiles, cta_group::2) runs it.
+// Pairs need at least two waves of 128-row tiles (smaller problems keep the 1-SM kernel and its split-K) and BN >= 128.
+// Pair tile width: 256 / 160 / 128 by (waves of 74 pairs) x width, wider tiles preferred (less shared-memory traffic per
+// FLOP: relative cost 1.00 / 1.08 / 1.15).  RF_GEMM_PAIR=0 disables, RF_GEMM_BN=<n> forces a width (A/B measurements).
+struct TileCfg {
+    int bn;
+    bool pair;
+};
+TileCfg pick_cfg(int N, long tiles_m_total, bool act_geglu) {
+    const char* env_pair = getenv("RF_GEMM_PAIR");      // read per call: the parity tests flip them inside one process
+    const char* env_bn = getenv("RF_GEMM_BN");
+    (void)act_geglu;
+    TileCfg c{pick_bn(N, tiles_m_total), false};
+    const bool pair_ok = !(env_pair && env_pair[0] == '0') && N >= 128 &&
+                         tiles_m_total * ((N + c.bn - 1) / c.bn) >= 2L * num_sms_cached();
+    if (!pair_ok) return c;
+    const long pairs = num_sms_cached() / 2, rows2 = (tiles_m_total + 1) / 2;
+    const int cand[3] = {256, 160, 128};
+    const double pen[3] = {1.00, 1.08, 1.15};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cand[i];
+        if (bn == 160 && (N % 160)) continue;
+        if (bn == 256 && (N % 256) && N > 256) continue;       // no ragged 256-wide tiles
+        if (env_bn && atoi(env_bn) != bn) continue;
+        const long t = rows2 * ((N + bn - 1) / bn);
+        const double cost = static_cast<double>((t + pairs - 1) / pairs) * bn * pen[i];
+        if (cost < best) {
+            best = cost;
+            c.bn = bn;
+            c.pair = true;
+        }
+    }
+    return c;
+}
+
+int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
+             int tiles_m, int nbatch, cudaStream_t st) {
+    // one persistent CTA (or CTA pair) per SM (TPC): 6-8 stage TMA ring, 2 TMEM accumulators
+    const int bn = cfg.bn;
     p.tiles_n = (N + bn - 1) / bn;
+    if (cfg.pair) {
+        p.tiles_m = (tiles_m + 1) / 2;          // 256-row blocks
+        p.splits = 1;
+        p.kb_per_split = p.num_kb;
+        p.ws = nullptr;
+        dim3 grid(p.tiles_n, p.tiles_m, nbatch);
+        if (bn == 256) return launch<256, 6, true>(a0, a1, b, p, grid, st);
+        if (bn == 160) return launch<160, 8, true>(a0, a1, b, p, grid, st);
+        return launch<128, 8, true>(a0, a1, b, p, grid, st);
+    }
+    p.tiles_m = tiles_m;
     // split-K: non-batched, plain or SiLU epilogue, 16-byte aligned fp16/fp32 rows
     const long rows = p.conv ? static_cast<long>(p.Bn) * p.Ho * p.Wo : p.M;
     const bool can_split = nbatch == 1 && p.act != 2 && (N % 8) == 0 && (p.ldo % 8) == 0 &&
@@ -614,9 +732,9 @@ int dispatch(int N, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     }
     dim3 grid(p.tiles_n * p.splits, tiles_m, nbatch);
     int rc;
-    if (bn == 160) rc = launch<160, 6>(a0, a1, b, p, grid, st);   // N = 320-type layers: two exact 160-column tiles
-    else if (bn == 128) rc = launch<128, 6>(a0, a1, b, p, grid, st);
-    else rc = launch<64, 8>(a0, a1, b, p, grid, st);
+    if (bn == 160) rc = launch<160, 6, false>(a0, a1, b, p, grid, st);   // N = 320-type layers: two exact 160-column tiles
+    else if (bn == 128) rc = launch<128, 6, false>(a0, a1, b, p, grid, st);
+    else rc = launch<64, 8, false>(a0, a1, b, p, grid, st);
     if (rc || p.splits == 1) return rc;
     const long work = rows * (N / 8);
     const unsigned blocks = static_cast<unsigned>(std::min<long>((work + 255) / 256, 8L * num_sms_cached()));
@@ -650,11 +768,11 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
         int rc = make_map(&ma, d->A, dims, str, box, es);
         if (rc) return rc;
     }
-    const int BN = pick_bn(d->N, static_cast<long>((d->M + BM - 1) / BM) * b1 * b2);
+    const TileCfg cfg = pick_cfg(d->N, static_cast<long>((d->M + BM - 1) / BM) * b1 * b2, d->act == 2);
     {
         const long dims[4] = {d->K, d->N, b_m1 ? b1 : 1, b_m2 ? b2 : 1};
         const long str[4] = {1, d->ldb, b_m1 ? d->sb1 : d->ldb, b_m2 ? d->sb2 : d->ldb};
-        const int box[4] = {BK, BN, 1, 1};
+        const int box[4] = {BK, cfg.pair ? cfg.bn / 2 : cfg.bn, 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&mb, d->B, dims, str, box, es);
         if (rc) return rc;
@@ -679,7 +797,7 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
                         (reinterpret_cast<uintptr_t>(d->D) & 15)))
         return rf_fail(RF_ERR_UNSUPPORTED, "rf_gemm_f16: GEGLU epilogue needs N % 32 == 0, fp16 output with 16-byte "
                                            "aligned rows and no residual");
-    return dispatch(d->N, ma, ma, mb, p, (d->M + BM - 1) / BM, b1 * b2, static_cast<cudaStream_t>(stream));
+    return dispatch(d->N, cfg, ma, ma, mb, p, (d->M + BM - 1) / BM, b1 * b2, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
@@ -724,11 +842,11 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     const int taps = d->ksize * d->ksize;
     const long Ktot = static_cast<long>(taps) * (d->C1 + C2);
     const long conv_tiles_m = static_cast<long>((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((d->B + bb - 1) / bb);
-    const int BN = pick_bn(d->Cout, conv_tiles_m);
+    const TileCfg cfg = pick_cfg(d->Cout, conv_tiles_m, false);
     {
         const long dims[4] = {Ktot, d->Cout, 1, 1};
         const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
-        const int box[4] = {BK, BN, 1, 1};
+        const int box[4] = {BK, cfg.pair ? cfg.bn / 2 : cfg.bn, 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&mb, d->w, dims, str, box, es);
         if (rc) return rc;
@@ -755,7 +873,7 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     p.residual = static_cast<const __half*>(d->residual);
     p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.act = d->act;
-    return dispatch(d->Cout, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+    return dispatch(d->Cout, cfg, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
 }
 
 // Live measurement aid for bench.py: between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed
@@ -777,14 +895,14 @@ extern "C" int rf_tc_profile_end(double* ms_out, double* flops_out, long* launch
     cudaError_t err = cudaDeviceSynchronize();
     FILE* dump = nullptr;
     if (const char* path = getenv("RF_TC_PROFILE_DUMP")) dump = fopen(path, "w");   // per-launch csv for profiles/
-    if (dump) fprintf(dump, "conv,M,N,K,batch,splits,ms\n");
+    if (dump) fprintf(dump, "conv,M,N,K,batch,splits,bn,ms\n");
     for (size_t i = 0; i + 1 < g_prof.ev.size() && err == cudaSuccess; i += 2) {
         float t = 0.f;
         err = cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
         ms += t;
         if (dump && i / 2 < g_prof.recs.size()) {
             const TcProfile::Rec& r = g_prof.recs[i / 2];
-            fprintf(dump, "%d,%d,%d,%d,%d,%d,%.4f\n", r.conv, r.M, r.N, r.K, r.batch, r.splits, t);
+            fprintf(dump, "%d,%d,%d,%d,%d,%d,%d,%.4f\n", r.conv, r.M, r.N, r.K, r.batch, r.splits, r.bn, t);
         }
     }
     if (dump) fclose(dump);

@@ -113,6 +113,68 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
         : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (cta_group::2): two SMs of one TPC issue one
+// 256-row MMA; each CTA stages its own 128 rows of A and HALF of the B tile, so the shared-memory fill and operand-read
+// traffic per SM drops by ~30-50 % (the 1-SM kernel is shared-memory-bandwidth bound on this part).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in the CTA with rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load issued by either CTA of a pair: data lands in THIS CTA's shared memory, the transaction bytes are
+// credited to the mbarrier at shared::cluster address `bar_cluster_addr` (the leader CTA's full barrier)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N rows: N/2 per CTA]^T; issued by one thread of the leader CTA
+__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior pair-MMAs arrives on the mbarrier at this shared-memory offset in BOTH CTAs (mask 0b11)
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane base + i), 32 consecutive columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
     asm volatile(

@@ -7,6 +7,7 @@
 // 0.9 [restated from memory, package absent]): torch.nn.GroupNorm / LayerNorm / F.gelu / softmax /
 // F.interpolate(nearest) / Conv2d, PNDMScheduler.step, classifier-free guidance combine.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -87,6 +88,14 @@ __device__ __forceinline__ float silu_tanh(float v) {
     return fmaf(h, t, h);
 }
 
+// accurate form: x / (1 + 2^(-x log2 e)) with ex2.approx + rcp.approx (two MUFU ops, ~2^-21 relative).  The GroupNorm apply
+// pass moves 4 bytes per element, so even at full HBM speed it needs < 80 % of the MUFU rate with two ops per element.
+// tanh.approx (2^-11 relative = one fp16 ulp of extra noise on every GroupNorm+SiLU output) showed up as the largest
+// difference between the kernels and the fp16-storage emulation of the oracle.
+__device__ __forceinline__ float silu_exp(float v) {
+    return __fdividef(v, 1.f + __expf(-v));
+}
+
 // Vectorised pass 3, same thread -> channel mapping: the affine form y = x * sc + sh (sc = rstd * gamma,
 // sh = beta - mean * sc) of the thread's 8 channels lives in registers for the whole slab.
 __global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restrict__ part, int nslabs, float inv_n,
@@ -151,7 +160,10 @@ __global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restri
         for (int j = 0; j < 4; ++j) {
             const float2 f = __half22float2(h[j]);
             float o0 = fmaf(f.x, sc[2 * j], sh[2 * j]), o1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-            if (act) {
+            if (act == 1) {
+                o0 = silu_exp(o0);
+                o1 = silu_exp(o1);
+            } else if (act == 2) {
                 o0 = silu_tanh(o0);
                 o1 = silu_tanh(o1);
             }
@@ -665,10 +677,11 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
     k_gn_partial_v<<<grid, threads, smem, st>>>(static_cast<const __half*>(x), HW, C, groups, slab, nslabs, part);
     RF_CUDA_LAUNCH_CHECK("k_gn_partial_v");
     if (groups > 64 || threads < groups) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: at most 64 groups (and not more groups than threads)");
+    static const int silu_form = getenv("RF_SILU_TANH") ? 2 : 1;      // A/B switch for measurements
     k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), part, nslabs,
                                            1.f / (static_cast<float>(HW) * (C / groups)), eps,
                                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), HW, C,
-                                           groups, act, slab, static_cast<__half*>(y));
+                                           groups, act ? silu_form : 0, slab, static_cast<__half*>(y));
     RF_CUDA_LAUNCH_CHECK("k_gn_apply_v");
     return RF_OK;
 }

@@ -19,8 +19,8 @@ lib.rf_tc_profile_end(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n))
 rows = list(csv.DictReader(open("gpurun_out/tc_launches.csv")))
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for r in rows:
-    k = (r["conv"], r["M"], r["N"], r["K"], r["batch"], r.get("splits", "1"))
+    k = (r["conv"], r["M"], r["N"], r["K"], r["batch"], r.get("splits", "1"), r.get("bn", "0"))
     a = agg[k]; a[0] += 1; a[1] += float(r["ms"]); a[2] += 2.0 * int(r["M"]) * int(r["N"]) * int(r["K"]) * int(r["batch"])
 print(f"total {ms.value:.2f} ms, {fl.value/1e12:.3f} TFLOP, {n.value} launches")
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
-    print(f"conv={k[0]} M={k[1]:>6} N={k[2]:>5} K={k[3]:>6} batch={k[4]:>3} S={k[5]}  n={a[0]:3d}  {a[1]:7.3f} ms  {a[2]/a[1]/1e9:8.1f} TFLOP/s")
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"conv={k[0]} M={k[1]:>6} N={k[2]:>5} K={k[3]:>6} batch={k[4]:>3} S={k[5]} bn={k[6]:>4}  n={a[0]:3d}  {a[1]:7.3f} ms  {a[2]/a[1]/1e9:8.1f} TFLOP/s")

@@ -156,3 +156,103 @@ def test_fused_attention_growing_scores(native_lib, Nk, d):
     assert torch.isfinite(got).all()
     _close(got, ref, tol=6e-3)
     assert float((got.float() - ref).norm() / ref.norm()) < 3e-3
+
+
+# ----------------------------------------------------------------------------------------------- CTA-pair kernel
+def _pair_env(bn):
+    import os
+
+    os.environ.pop("RF_GEMM_PAIR", None)
+    if bn is None:
+        os.environ.pop("RF_GEMM_BN", None)
+    else:
+        os.environ["RF_GEMM_BN"] = str(bn)
+
+
+@pytest.mark.parametrize("bn", [None, 256, 160, 128])
+def test_pair_kernel_gemm_matches_torch_and_single_cta(native_lib, bn):
+    """problems large enough for the cta_group::2 kernel (256 x BN tiles on CTA pairs), every tile width, ragged M
+    (odd number of 128-row blocks: the second CTA of the last pair is fully out of bounds), bias / SiLU / residual /
+    GEGLU epilogues, batched operands; results also compared with the 1-SM kernel (RF_GEMM_PAIR=0)"""
+    import os
+
+    import torch.nn.functional as F
+
+    from riffusion import tc_ops as ops
+
+    try:
+        for (M, N, K) in ((128 * 297 - 58, 320, 320), (40000, 1280, 640), (36000, 640, 320), (38000, 256, 192)):
+            if bn == 160 and N % 160:
+                continue
+            torch.manual_seed(M + N)
+            a = (torch.randn(M, K, device="cuda") * 0.5).half()
+            b = (torch.randn(N, K, device="cuda") * 0.5).half()
+            bias = torch.randn(N, device="cuda").half()
+            res = torch.randn(M, N, device="cuda").half()
+            ref = a.float() @ b.float().t()
+            _pair_env(bn)
+            g1 = ops.gemm(a, b).reshape(M, N)
+            g2 = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5).reshape(M, N)
+            g3 = ops.gemm(a, b, bias=bias, act=ops.ACT_SILU).reshape(M, N)
+            _close(g1, ref)
+            _close(g2, 0.5 * ref + bias.float() + res.float())
+            _close(g3, F.silu(ref + bias.float()))
+            os.environ["RF_GEMM_PAIR"] = "0"
+            s1 = ops.gemm(a, b).reshape(M, N)
+            # same K order inside a tile and fp32 accumulation in TMEM: the two kernels agree (to the last bit, if the
+            # 256-row instruction accumulates like the 128-row one; at most isolated fp16 rounding flips otherwise)
+            assert float((g1 != s1).float().mean()) < 1e-3 and float((g1.float() - s1.float()).abs().max()) <= 2e-3 * float(ref.abs().max()), (M, N, K)
+        # GEGLU epilogue (N = 8C interleaved) and a batched V^T-style product with 3 row blocks per batch entry
+        _pair_env(bn)
+        M, C = 33000, 320
+        x = torch.randn(M, C, device="cuda").half()
+        w = (torch.randn(8 * C, C, device="cuda") / C ** 0.5).half()
+        bb = (0.1 * torch.randn(8 * C, device="cuda")).half()
+        h, gate = (x.float() @ w.float().t() + bb.float()).chunk(2, dim=-1)
+        got = ops.gemm(x, ops.interleave_geglu(w), bias=ops.interleave_geglu(bb), act=ops.ACT_GEGLU).reshape(M, 4 * C)
+        assert (got.float() - h * F.gelu(gate)).abs().max() < 2e-2
+        Bt, T = 24, 4096
+        xt = (torch.randn(Bt, T, 320, device="cuda") * 0.3).half()
+        wv = (torch.randn(320, 320, device="cuda") * 0.05).half()
+        vt = torch.empty(Bt, 1, 320, T, dtype=torch.float16, device="cuda")
+        ops.gemm(wv, xt.unsqueeze(1), out=vt)
+        _close(vt.reshape(Bt, 320, T), torch.einsum("ck,btk->bct", wv.float(), xt.float()))
+    finally:
+        _pair_env(None)
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout,k,stride", [
+    (8, 64, 64, 320, 0, 320, 3, 1), (16, 32, 32, 640, 0, 640, 3, 1), (16, 32, 32, 640, 640, 1280, 3, 1),
+    (16, 64, 64, 320, 0, 320, 3, 2), (13, 48, 48, 128, 0, 256, 3, 1), (24, 32, 32, 960, 0, 640, 1, 1),
+    (3, 256, 256, 128, 0, 128, 3, 1),
+])
+def test_pair_kernel_conv_matches_torch(native_lib, B, H, W, C1, C2, Cout, k, stride):
+    """implicit-GEMM convolution on CTA pairs: each CTA of a pair gathers its own 128 output pixels (TMA im2col boxes),
+    stride 2, channel concat through the second tensor map, per-image bias, residual; vs torch and vs the 1-SM kernel"""
+    import os
+
+    from riffusion import tc_ops
+
+    torch.manual_seed(H + C1 + Cout + k)
+    x = (torch.randn(B, H, W, C1, device="cuda") * 0.5).half()
+    x2 = (torch.randn(B, H, W, C2, device="cuda") * 0.5).half() if C2 else None
+    w = (torch.randn(Cout, C1 + C2, k, k, device="cuda") * (C1 + C2) ** -0.5 / k).half()
+    bias = torch.randn(Cout, device="cuda").half()
+    temb = torch.randn(B, Cout, device="cuda").half()
+    xin = x if x2 is None else torch.cat([x, x2], dim=3)
+    ref = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2).float(), w.float(), bias.float(), stride=stride,
+                                     padding=1 if k == 3 else 0)
+    ref = (ref + temb.float()[:, :, None, None]).permute(0, 2, 3, 1)
+    wp = tc_ops.pack_conv_weight(w)
+    try:
+        _pair_env(None)
+        got = tc_ops.conv2d(x, wp, x2=x2, bias=bias, bias_per_image=temb, stride=stride)
+        _close(got, ref)
+        res = torch.randn_like(got)
+        got2 = tc_ops.conv2d(x, wp, x2=x2, bias=bias, residual=res, stride=stride)
+        _close(got2, ref - temb.float()[:, None, None, :] + res.float())
+        os.environ["RF_GEMM_PAIR"] = "0"
+        single = tc_ops.conv2d(x, wp, x2=x2, bias=bias, bias_per_image=temb, stride=stride)
+        assert float((got != single).float().mean()) < 1e-3
+    finally:
+        _pair_env(None)
