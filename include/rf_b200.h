@@ -219,6 +219,12 @@ int rf_tc_profile_end(double* ms_out, double* flops_out, long* launches_out);
 size_t rf_group_norm_scratch_floats(int B, int HW, int groups);
 int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups, const void* gamma, const void* beta,
                       float eps, int act, void* y, float* d_scratch, void* stream);
+/* Same on the channel concatenation [x | x2] read in place: x [B][HW][C1], x2 [B][HW][C - C1], y [B][HW][C] — the
+ * `torch.cat([hidden_states, res_hidden_states], dim=1)` of the UNet up blocks (diffusers unet_2d_blocks.py UpBlock2D /
+ * CrossAttnUpBlock2D [restated from memory]) followed by the resnet's norm1, without materialising the concatenation.
+ * x2 == NULL: identical to rf_group_norm_f16. */
+int rf_group_norm_cat_f16(const void* x, const void* x2, int C1, int B, int HW, int C, int groups, const void* gamma,
+                          const void* beta, float eps, int act, void* y, float* d_scratch, void* stream);
 /* torch.nn.LayerNorm(C, eps) over rows */
 int rf_layer_norm_f16(const void* x, int rows, int C, const void* gamma, const void* beta, float eps, void* y,
                       void* stream);

@@ -37,14 +37,19 @@ __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); 
 // pass 3: y = (x - mean) * rstd * gamma + beta, optional SiLU.
 // Vectorised pass 1 (C % 8 == 0, C <= 2560): blockDim = PPI * C/8 threads; a thread owns 8 fixed channels (one 16-byte
 // load per pixel) and walks every PPI-th pixel of the slab, four loads in flight.  Same deterministic two-level sum.
-__global__ void k_gn_partial_v(const __half* __restrict__ x, int HW, int C, int G, int slab, int nslabs,
-                               float* __restrict__ part /*[B][nslabs][G][2]*/) {
+// Two-source form (x2 != nullptr): the input is the channel concatenation [x | x2] (C1 + (C - C1) channels,
+// torch.cat([x, skip], dim=1) of the up blocks) read in place — a thread's 8 channels come from one of the two tensors.
+__global__ void k_gn_partial_v(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, int HW, int C, int G,
+                               int slab, int nslabs, float* __restrict__ part /*[B][nslabs][G][2]*/) {
     extern __shared__ float2 shp[];  // [PPI][C/2]
     const int b = blockIdx.y;
-    const int C8 = C >> 3, C2 = C >> 1;
-    const int c8 = threadIdx.x % C8, pp = threadIdx.x / C8, PPI = blockDim.x / C8;
+    const int C2 = C >> 1;
+    const int c8 = threadIdx.x % (C >> 3), pp = threadIdx.x / (C >> 3), PPI = blockDim.x / (C >> 3);
     const int p0 = blockIdx.x * slab, p1 = min(HW, p0 + slab);
-    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C) + c8;
+    const bool second = x2 != nullptr && c8 * 8 >= C1;
+    const int C8 = (second ? C - C1 : C1) >> 3;              // row pitch of the source tensor in 16-byte units
+    const uint4* xb = reinterpret_cast<const uint4*>((second ? x2 : x) + static_cast<size_t>(b) * HW * (C8 * 8)) +
+                      (second ? c8 - (C1 >> 3) : c8);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
     auto acc = [&](const uint4& v) {
         const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -98,7 +103,8 @@ __device__ __forceinline__ float silu_exp(float v) {
 
 // Vectorised pass 3, same thread -> channel mapping: the affine form y = x * sc + sh (sc = rstd * gamma,
 // sh = beta - mean * sc) of the thread's 8 channels lives in registers for the whole slab.
-__global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restrict__ part, int nslabs, float inv_n,
+__global__ void k_gn_apply_v(const __half* __restrict__ x, const __half* __restrict__ x2, int C1,
+                             const float* __restrict__ part, int nslabs, float inv_n,
                              float eps, const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C,
                              int G, int act, int slab, __half* __restrict__ y) {
     // pass 2 folded in: every CTA reduces the slab partials of its image to (mean, rstd) per group — a few KB from L2, in a
@@ -152,7 +158,10 @@ __global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restri
             sh[e] = fmaf(-mean, sc[e], __half2float(bh[e]));
         }
     }
-    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C) + c8;
+    const bool second = x2 != nullptr && c8 * 8 >= C1;
+    const int S8 = (second ? C - C1 : C1) >> 3;             // row pitch of the source tensor in 16-byte units
+    const uint4* xb = reinterpret_cast<const uint4*>((second ? x2 : x) + static_cast<size_t>(b) * HW * (S8 * 8)) +
+                      (second ? c8 - (C1 >> 3) : c8);
     uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(b) * HW * C) + c8;
     auto xf = [&](uint4 v) -> uint4 {
         __half2* h = reinterpret_cast<__half2*>(&v);
@@ -173,14 +182,14 @@ __global__ void k_gn_apply_v(const __half* __restrict__ x, const float* __restri
     };
     int p = p0 + pp;
     for (; p + 3 * PPI < p1; p += 4 * PPI) {
-        const uint4 v0 = xb[static_cast<size_t>(p) * C8], v1 = xb[static_cast<size_t>(p + PPI) * C8];
-        const uint4 v2 = xb[static_cast<size_t>(p + 2 * PPI) * C8], v3 = xb[static_cast<size_t>(p + 3 * PPI) * C8];
+        const uint4 v0 = xb[static_cast<size_t>(p) * S8], v1 = xb[static_cast<size_t>(p + PPI) * S8];
+        const uint4 v2 = xb[static_cast<size_t>(p + 2 * PPI) * S8], v3 = xb[static_cast<size_t>(p + 3 * PPI) * S8];
         yb[static_cast<size_t>(p) * C8] = xf(v0);
         yb[static_cast<size_t>(p + PPI) * C8] = xf(v1);
         yb[static_cast<size_t>(p + 2 * PPI) * C8] = xf(v2);
         yb[static_cast<size_t>(p + 3 * PPI) * C8] = xf(v3);
     }
-    for (; p < p1; p += PPI) yb[static_cast<size_t>(p) * C8] = xf(xb[static_cast<size_t>(p) * C8]);
+    for (; p < p1; p += PPI) yb[static_cast<size_t>(p) * C8] = xf(xb[static_cast<size_t>(p) * S8]);
 }
 
 // ---------------------------------------------------------------- LayerNorm over the last dim
@@ -208,6 +217,60 @@ __global__ void k_layernorm(const __half* __restrict__ x, const __half* __restri
         const float2 ga = __half22float2(g2[i]);
         const float2 be = __half22float2(b2[i]);
         yr[i] = __floats2half2_rn((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y);
+    }
+}
+
+// Vectorised LayerNorm for C = 40 * LPR (320, 640, 1280): LPR lanes per row (8 / 16 / 32), 32 / LPR rows per warp; a lane
+// holds five 16-byte vectors of its row in registers between the statistics and the normalisation, so the row is read
+// once (the scalar kernel above issues 4-byte loads and reads the row twice: 93 us for the 64x64 level at batch 64, i.e.
+// 3.6 TB/s).
+template <int LPR>
+__global__ void __launch_bounds__(256) k_layernorm_v(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                                     const __half* __restrict__ beta, int rows, float eps,
+                                                     __half* __restrict__ y) {
+    constexpr int NV = 5, C = 8 * NV * LPR, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool ok = row < rows;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(ok ? row : 0) * C);
+    uint4 v[NV];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = ok ? xr[sub + LPR * i] : make_uint4(0, 0, 0, 0);
+        const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            s += f.x + f.y;
+            ss += f.x * f.x + f.y * f.y;
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o; o >>= 1) {       // the lanes of a row are consecutive: xor-shuffles stay inside the group
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const float mean = s * (1.f / C);
+    const float rstd = rsqrtf(fmaxf(ss * (1.f / C) - mean * mean, 0.f) + eps);
+    if (!ok) return;
+    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * C);
+    const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+    const uint4* b4 = reinterpret_cast<const uint4*>(beta);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const uint4 gv = g4[sub + LPR * i], bv = b4[sub + LPR * i];
+        const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+        __half2* h = reinterpret_cast<__half2*>(&v[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            const float2 ga = __half22float2(gh[j]);
+            const float2 be = __half22float2(bh[j]);
+            h[j] = __floats2half2_rn((f.x - mean) * rstd * ga.x + be.x, (f.y - mean) * rstd * ga.y + be.y);
+        }
+        yr[sub + LPR * i] = v[i];
     }
 }
 
@@ -658,9 +721,18 @@ extern "C" size_t rf_group_norm_scratch_floats(int B, int HW, int groups) {
 
 extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups, const void* gamma, const void* beta,
                                  float eps, int act, void* y, float* d_scratch, void* stream) {
+    return rf_group_norm_cat_f16(x, nullptr, C, B, HW, C, groups, gamma, beta, eps, act, y, d_scratch, stream);
+}
+
+extern "C" int rf_group_norm_cat_f16(const void* x, const void* x2, int C1, int B, int HW, int C, int groups,
+                                     const void* gamma, const void* beta, float eps, int act, void* y, float* d_scratch,
+                                     void* stream) {
     if (!x || !y || !gamma || !beta || !d_scratch || B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups ||
         ((C / groups) & 1))
         return rf_fail(RF_ERR_INVALID, "rf_group_norm_f16: bad argument (channels per group must be even)");
+    if (!x2) C1 = C;
+    if (x2 && (C1 <= 0 || C1 >= C || (C1 % 8) || ((C - C1) % 8)))
+        return rf_fail(RF_ERR_INVALID, "rf_group_norm_cat_f16: both channel counts must be positive multiples of 8");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (C > 2560 || (C % 8)) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: C must be a multiple of 8, <= 2560");
     // thread -> (pixel phase, 8-channel column): blockDim = PPI * C/8 (<= 320 threads)
@@ -674,11 +746,12 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
     float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
     const size_t smem = static_cast<size_t>(PPI) * (C / 2) * sizeof(float2);
     dim3 grid(nslabs, B);
-    k_gn_partial_v<<<grid, threads, smem, st>>>(static_cast<const __half*>(x), HW, C, groups, slab, nslabs, part);
+    k_gn_partial_v<<<grid, threads, smem, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(x2), C1, HW, C,
+                                                groups, slab, nslabs, part);
     RF_CUDA_LAUNCH_CHECK("k_gn_partial_v");
     if (groups > 64 || threads < groups) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: at most 64 groups (and not more groups than threads)");
     static const int silu_form = getenv("RF_SILU_TANH") ? 2 : 1;      // A/B switch for measurements
-    k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), part, nslabs,
+    k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(x2), C1, part, nslabs,
                                            1.f / (static_cast<float>(HW) * (C / groups)), eps,
                                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), HW, C,
                                            groups, act ? silu_form : 0, slab, static_cast<__half*>(y));
@@ -689,6 +762,21 @@ extern "C" int rf_group_norm_f16(const void* x, int B, int HW, int C, int groups
 extern "C" int rf_layer_norm_f16(const void* x, int rows, int C, const void* gamma, const void* beta, float eps, void* y,
                                  void* stream) {
     if (!x || !y || !gamma || !beta || rows <= 0 || C <= 0 || (C & 1)) return rf_fail(RF_ERR_INVALID, "rf_layer_norm_f16: bad argument");
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                           reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    if (aligned && (C == 320 || C == 640 || C == 1280)) {
+        const int rpb = 8 * (C == 320 ? 4 : C == 640 ? 2 : 1);     // 8 warps x rows per warp
+        const int blocks = (rows + rpb - 1) / rpb;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const __half *xp = static_cast<const __half*>(x), *gp = static_cast<const __half*>(gamma),
+                     *bp = static_cast<const __half*>(beta);
+        __half* yp = static_cast<__half*>(y);
+        if (C == 320) k_layernorm_v<8><<<blocks, 256, 0, st>>>(xp, gp, bp, rows, eps, yp);
+        else if (C == 640) k_layernorm_v<16><<<blocks, 256, 0, st>>>(xp, gp, bp, rows, eps, yp);
+        else k_layernorm_v<32><<<blocks, 256, 0, st>>>(xp, gp, bp, rows, eps, yp);
+        RF_CUDA_LAUNCH_CHECK("k_layernorm_v");
+        return RF_OK;
+    }
     k_layernorm<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(x), static_cast<const __half*>(gamma), static_cast<const __half*>(beta), rows, C, eps,
         static_cast<__half*>(y));

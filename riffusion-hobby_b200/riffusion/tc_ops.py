@@ -124,17 +124,25 @@ def conv2d(
 
 
 # ------------------------------------------------------------------------------ memory-bound operators
-def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool) -> torch.Tensor:
-    """x: (B, H, W, C) or (B, HW, C) fp16 NHWC -> same shape; GroupNorm (+ SiLU)."""
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+               x2: T.Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: (B, H, W, C) or (B, HW, C) fp16 NHWC -> same shape; GroupNorm (+ SiLU).  With `x2` the input is the channel
+    concatenation [x | x2] (torch.cat(dim=1) of the up blocks), read in place; the result has C1 + C2 channels."""
     _f16(x, "x")
     assert x.is_contiguous()
-    B, C = x.shape[0], x.shape[-1]
-    HW = x.numel() // (B * C)
-    y = torch.empty_like(x)
+    B, C1 = x.shape[0], x.shape[-1]
+    C = C1
+    if x2 is not None:
+        _f16(x2, "x2")
+        assert x2.is_contiguous() and x2.shape[:-1] == x.shape[:-1]
+        C = C1 + x2.shape[-1]
+    HW = x.numel() // (B * C1)
+    y = torch.empty(x.shape[:-1] + (C,), dtype=torch.float16, device=x.device)
     stats = torch.empty((_native.lib().rf_group_norm_scratch_floats(B, HW, groups),), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _native.check(_native.lib().rf_group_norm_f16(x.data_ptr(), B, HW, C, groups, gamma.data_ptr(), beta.data_ptr(),
-                                                      float(eps), int(silu), y.data_ptr(), stats.data_ptr(), _stream(x)))
+        _native.check(_native.lib().rf_group_norm_cat_f16(
+            x.data_ptr(), None if x2 is None else x2.data_ptr(), C1, B, HW, C, groups, gamma.data_ptr(), beta.data_ptr(),
+            float(eps), int(silu), y.data_ptr(), stats.data_ptr(), _stream(x)))
     return y
 
 

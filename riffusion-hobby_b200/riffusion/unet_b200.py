@@ -69,16 +69,22 @@ class UNetB200:
         self._temb_all: T.Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ building blocks
-    def _resnet(self, pfx: str, x: torch.Tensor, st: T.Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    def _resnet(self, pfx: str, x: torch.Tensor, st: T.Optional[torch.Tensor], eps: float = 1e-5,
+                skip: T.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`skip`: the resnet's input is torch.cat([x, skip], dim=1) (up blocks); the concatenation is never materialised:
+        norm1 reads both tensors in place and the 1x1 shortcut convolution takes them through its two tensor maps."""
         w = self.w
-        h = ops.group_norm(x, w[pfx + "norm1.weight"], w[pfx + "norm1.bias"], self.groups, eps, silu=True)
+        h = ops.group_norm(x, w[pfx + "norm1.weight"], w[pfx + "norm1.bias"], self.groups, eps, silu=True, x2=skip)
         tproj = None
         if st is not None and pfx in self._temb_slices:
             a, b = self._temb_slices[pfx]
             tproj = self._temb_all[:, a:b]
         h = ops.conv2d(h, w[pfx + "conv1.weight"], bias=w[pfx + "conv1.bias"], bias_per_image=tproj)
         h = ops.group_norm(h, w[pfx + "norm2.weight"], w[pfx + "norm2.bias"], self.groups, eps, silu=True)
-        if (pfx + "conv_shortcut.weight") in w:
+        if skip is not None:                        # every concatenating resnet changes the channel count: shortcut exists
+            wsc = w[pfx + "conv_shortcut.weight"]
+            x = ops.conv2d(x, wsc.view(wsc.shape[0], 1, 1, wsc.shape[1]), x2=skip, bias=w[pfx + "conv_shortcut.bias"])
+        elif (pfx + "conv_shortcut.weight") in w:
             B, H, W, C = x.shape
             sc = ops.gemm(x.reshape(B * H * W, C), w[pfx + "conv_shortcut.weight"], bias=w[pfx + "conv_shortcut.bias"])
             x = sc.reshape(B, H, W, -1)
@@ -197,8 +203,7 @@ class UNetB200:
             p = f"up_blocks.{i}."
             has_attn = (p + "attentions.0.norm.weight") in w
             for j in range(3):
-                x = ops.concat_channels(x, skips.pop())        # torch.cat([x, skip], dim=1)
-                x = self._resnet(f"{p}resnets.{j}.", x, st)
+                x = self._resnet(f"{p}resnets.{j}.", x, st, skip=skips.pop())    # torch.cat([x, skip], dim=1) folded in
                 if has_attn:
                     x = self._transformer(f"{p}attentions.{j}.", x, ctx, ctx_cache)
             if (p + "upsamplers.0.conv.weight") in w:

@@ -82,7 +82,7 @@ def test_gemm_batched_strided_heads(native_lib):
     (2, 64, 64, 320, 0, 320, 3, 1), (2, 32, 32, 640, 0, 640, 3, 1), (2, 16, 16, 1280, 1280, 1280, 3, 1),
     (2, 8, 8, 1280, 0, 1280, 3, 1), (3, 8, 8, 1280, 0, 1280, 3, 1), (2, 64, 64, 320, 0, 320, 3, 2),
     (2, 16, 16, 640, 0, 640, 3, 2), (2, 32, 32, 960, 0, 640, 1, 1), (1, 128, 128, 256, 0, 128, 3, 1),
-    (2, 32, 32, 320, 640, 64, 3, 1),
+    (2, 32, 32, 320, 640, 64, 3, 1), (2, 16, 16, 1280, 640, 1280, 1, 1),
 ])
 def test_conv_matches_torch(native_lib, B, H, W, C1, C2, Cout, k, stride):
     from riffusion import tc_ops

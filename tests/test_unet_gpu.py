@@ -31,6 +31,22 @@ def test_elementwise_ops_match_torch(native_lib):
             ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
             got = ops.group_norm(x, g, b, 32, 1e-5, silu)
             assert (got.float() - ref).abs().max() < 4e-3
+    # GroupNorm over a channel concatenation read in place (up blocks): groups straddle the seam (1920 / 32 = 60)
+    for (C1, C2) in ((1280, 640), (320, 320), (64, 128)):
+        a = torch.randn(2, 8, 8, C1, device="cuda").half()
+        c = (torch.randn(2, 8, 8, C2, device="cuda") * 2 + 0.5).half()
+        g = (1 + 0.1 * torch.randn(C1 + C2, device="cuda")).half()
+        b = (0.1 * torch.randn(C1 + C2, device="cuda")).half()
+        cat = torch.cat([a, c], dim=-1)
+        got = ops.group_norm(a, g, b, 32, 1e-5, True, x2=c)
+        assert torch.equal(got, ops.group_norm(cat, g, b, 32, 1e-5, True))
+        ref = F.silu(F.group_norm(cat.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), eps=1e-5)).permute(0, 2, 3, 1)
+        assert (got.float() - ref).abs().max() < 4e-3
+    for rows, Cn in ((77, 640), (1000, 320), (130, 1280), (33, 96)):       # vectorised (320/640/1280) and generic LayerNorm
+        x = torch.randn(rows, Cn, device="cuda").half()
+        g = (1 + 0.1 * torch.randn(Cn, device="cuda")).half()
+        b = (0.1 * torch.randn(Cn, device="cuda")).half()
+        assert (ops.layer_norm(x, g, b).float() - F.layer_norm(x.float(), (Cn,), g.float(), b.float())).abs().max() < 4e-3
     x = torch.randn(77, 640, device="cuda").half()
     g = (1 + 0.1 * torch.randn(640, device="cuda")).half()
     b = (0.1 * torch.randn(640, device="cuda")).half()
