@@ -31,6 +31,30 @@ def r16(x: torch.Tensor, site: str = "branch") -> torch.Tensor:
     return x.to(torch.float16).to(torch.float32)
 
 
+HI: bool = False       # True: every contraction (conv / linear / attention matmul) is evaluated in float64 before the same fp16
+                       # roundings — a second, equally valid fp16-storage evaluation that differs from the first only below
+                       # fp32 rounding.  Its distance to the default evaluation is how far apart two correct fp16
+                       # implementations of this network sit (tests/test_parity_bench_gpu.py).
+
+
+def _conv(x, w, b=None, **kw):
+    if HI:
+        return F.conv2d(x.double(), w.double(), None if b is None else b.double(), **kw).float()
+    return F.conv2d(x, w, b, **kw)
+
+
+def _lin(x, w, b=None):
+    if HI:
+        return F.linear(x.double(), w.double(), None if b is None else b.double()).float()
+    return F.linear(x, w, b)
+
+
+def _mm(a, b):
+    if HI:
+        return torch.matmul(a.double(), b.double()).float()
+    return torch.matmul(a, b)
+
+
 def _gn(m, x, silu: bool):
     y = F.group_norm(x, m.num_groups, m.weight, m.bias, m.eps)
     return r16(F.silu(y) if silu else y, "norm")
@@ -39,14 +63,14 @@ def _gn(m, x, silu: bool):
 def _resnet(m: uo.ResnetBlock2D, x, st):
     """x: fp16-valued fp32 NCHW; st = r16(silu(temb)) (B, 1280) or None"""
     h = _gn(m.norm1, x, True)
-    h = F.conv2d(h, m.conv1.weight, m.conv1.bias, padding=1)
+    h = _conv(h, m.conv1.weight, m.conv1.bias, padding=1)
     if m.time_emb_proj is not None and st is not None:
-        h = h + r16(F.linear(st, m.time_emb_proj.weight, m.time_emb_proj.bias))[:, :, None, None]   # batched temb GEMM stores fp16
+        h = h + r16(_lin(st, m.time_emb_proj.weight, m.time_emb_proj.bias))[:, :, None, None]   # batched temb GEMM stores fp16
     h = r16(h)
     h = _gn(m.norm2, h, True)
     if m.conv_shortcut is not None:
-        x = r16(F.conv2d(x, m.conv_shortcut.weight, m.conv_shortcut.bias))
-    return r16(F.conv2d(h, m.conv2.weight, m.conv2.bias, padding=1) + x, "stream")
+        x = r16(_conv(x, m.conv_shortcut.weight, m.conv_shortcut.bias))
+    return r16(_conv(h, m.conv2.weight, m.conv2.bias, padding=1) + x, "stream")
 
 
 def _attention(q, k, v, heads: int, scale: float):
@@ -59,19 +83,19 @@ def _attention(q, k, v, heads: int, scale: float):
     out = torch.empty_like(qh)
     step = max(1, (1 << 28) // max(1, Nq * kh.shape[2] * heads))      # bound the score tensor
     for b0 in range(0, B, step):
-        s = torch.matmul(qh[b0:b0 + step], kh[b0:b0 + step].transpose(-1, -2)) * scale
+        s = _mm(qh[b0:b0 + step], kh[b0:b0 + step].transpose(-1, -2)) * scale
         p = r16(torch.exp(s - s.amax(dim=-1, keepdim=True)), "attn")
-        out[b0:b0 + step] = torch.matmul(p, vh[b0:b0 + step]) / p.sum(dim=-1, keepdim=True)
+        out[b0:b0 + step] = _mm(p, vh[b0:b0 + step]) / p.sum(dim=-1, keepdim=True)
     return r16(out.transpose(1, 2).reshape(B, Nq, C), "attn")
 
 
 def _cross_attn(m: uo.CrossAttention, x, ctx, residual):
     context = x if ctx is None else ctx
-    q = r16(F.linear(x, m.to_q.weight))
-    k = r16(F.linear(context, m.to_k.weight))
-    v = r16(F.linear(context, m.to_v.weight))
+    q = r16(_lin(x, m.to_q.weight))
+    k = r16(_lin(context, m.to_k.weight))
+    v = r16(_lin(context, m.to_v.weight))
     o = _attention(q, k, v, m.heads, m.scale)
-    return r16(F.linear(o, m.to_out[0].weight, m.to_out[0].bias) + residual, "stream")
+    return r16(_lin(o, m.to_out[0].weight, m.to_out[0].bias) + residual, "stream")
 
 
 def _ln(m, x):
@@ -81,16 +105,16 @@ def _ln(m, x):
 def _transformer(m: uo.Transformer2DModel, x, ctx):
     B, C, H, W = x.shape
     h = _gn(m.norm, x, False)
-    h = r16(F.conv2d(h, m.proj_in.weight, m.proj_in.bias)).permute(0, 2, 3, 1).reshape(B, H * W, C)
+    h = r16(_conv(h, m.proj_in.weight, m.proj_in.bias)).permute(0, 2, 3, 1).reshape(B, H * W, C)
     for blk in m.transformer_blocks:
         h = _cross_attn(blk.attn1, _ln(blk.norm1, h), None, h)
         h = _cross_attn(blk.attn2, _ln(blk.norm2, h), ctx, h)
         n3 = _ln(blk.norm3, h)
-        val, gate = F.linear(n3, blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias).chunk(2, dim=-1)
+        val, gate = _lin(n3, blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias).chunk(2, dim=-1)
         g = r16(val * F.gelu(gate))                                   # GEGLU in the GEMM epilogue: one rounding
-        h = r16(F.linear(g, blk.ff.net[2].weight, blk.ff.net[2].bias) + h, "stream")
+        h = r16(_lin(g, blk.ff.net[2].weight, blk.ff.net[2].bias) + h, "stream")
     h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
-    return r16(F.conv2d(h, m.proj_out.weight, m.proj_out.bias) + x, "stream")
+    return r16(_conv(h, m.proj_out.weight, m.proj_out.bias) + x, "stream")
 
 
 @torch.no_grad()
@@ -101,10 +125,10 @@ def unet_forward(m: uo.UNet2DConditionOracle, sample, timestep, ctx):
     t = torch.as_tensor(timestep, device=x.device).reshape(-1).expand(x.shape[0])
     emb = r16(uo.timestep_sinusoid(t, m.config["block_out_channels"][0]))
     te = m.time_embedding
-    e1 = r16(F.silu(F.linear(emb, te.linear_1.weight, te.linear_1.bias)))
-    e2 = r16(F.linear(e1, te.linear_2.weight, te.linear_2.bias))
+    e1 = r16(F.silu(_lin(emb, te.linear_1.weight, te.linear_1.bias)))
+    e2 = r16(_lin(e1, te.linear_2.weight, te.linear_2.bias))
     st = r16(F.silu(e2))
-    x = r16(F.conv2d(x, m.conv_in.weight, m.conv_in.bias, padding=1))
+    x = r16(_conv(x, m.conv_in.weight, m.conv_in.bias, padding=1))
     skips = [x]
     for blk in m.down_blocks:
         for i, res in enumerate(blk.resnets):
@@ -114,7 +138,7 @@ def unet_forward(m: uo.UNet2DConditionOracle, sample, timestep, ctx):
             skips.append(x)
         if blk.downsamplers is not None:
             c = blk.downsamplers[0].conv
-            x = r16(F.conv2d(x, c.weight, c.bias, stride=2, padding=1))
+            x = r16(_conv(x, c.weight, c.bias, stride=2, padding=1))
             skips.append(x)
     mb = m.mid_block
     x = _resnet(mb.resnets[0], x, st)
@@ -127,24 +151,24 @@ def unet_forward(m: uo.UNet2DConditionOracle, sample, timestep, ctx):
                 x = _transformer(blk.attentions[i], x, ctx)
         if blk.upsamplers is not None:
             c = blk.upsamplers[0].conv
-            x = r16(F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), c.weight, c.bias, padding=1))
+            x = r16(_conv(F.interpolate(x, scale_factor=2.0, mode="nearest"), c.weight, c.bias, padding=1))
     x = _gn(m.conv_norm_out, x, True)
-    return r16(F.conv2d(x, m.conv_out.weight, m.conv_out.bias, padding=1))
+    return r16(_conv(x, m.conv_out.weight, m.conv_out.bias, padding=1))
 
 
 # ------------------------------------------------------------------------------------------ VAE
 def _vae_attn(m, x):
     B, C, H, W = x.shape
     h = _gn(m.group_norm, x, False).view(B, C, H * W).transpose(1, 2)
-    q = r16(F.linear(h, m.query.weight, m.query.bias))
-    k = r16(F.linear(h, m.key.weight, m.key.bias))
-    v = r16(F.linear(h, m.value.weight, m.value.bias))
+    q = r16(_lin(h, m.query.weight, m.query.bias))
+    k = r16(_lin(h, m.key.weight, m.key.bias))
+    v = r16(_lin(h, m.value.weight, m.value.bias))
     # VaeB200 goes GEMM -> fp16 scores -> row softmax (fp16 out) -> GEMM for the 512-wide single head
-    s = r16(torch.bmm(q, k.transpose(1, 2)) * C ** -0.5)
+    s = r16(_mm(q, k.transpose(1, 2)) * C ** -0.5)
     p = r16(torch.softmax(s, dim=-1))
-    o = r16(torch.bmm(p, v))
+    o = r16(_mm(p, v))
     xt = x.view(B, C, H * W).transpose(1, 2)
-    return r16(F.linear(o, m.proj_attn.weight, m.proj_attn.bias) + xt).transpose(1, 2).reshape(B, C, H, W)
+    return r16(_lin(o, m.proj_attn.weight, m.proj_attn.bias) + xt).transpose(1, 2).reshape(B, C, H, W)
 
 
 def _vae_mid(m, x):
@@ -157,18 +181,18 @@ def _vae_mid(m, x):
 def vae_decode(m, z, scale: float = 1.0):
     """emulation of VaeB200.decode(z, scale): z fp16 latents, the 1/0.18215 factor folded into post_quant_conv"""
     z = r16(z.float())
-    z = r16(F.conv2d(z * scale, m.post_quant_conv.weight, m.post_quant_conv.bias))
+    z = r16(_conv(z * scale, m.post_quant_conv.weight, m.post_quant_conv.bias))
     d = m.decoder
-    x = r16(F.conv2d(z, d.conv_in.weight, d.conv_in.bias, padding=1))
+    x = r16(_conv(z, d.conv_in.weight, d.conv_in.bias, padding=1))
     x = _vae_mid(d.mid_block, x)
     for u in d.up_blocks:
         for res in u.resnets:
             x = _resnet(res, x, None)
         if u.upsamplers is not None:
             c = u.upsamplers[0].conv
-            x = r16(F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), c.weight, c.bias, padding=1))
+            x = r16(_conv(F.interpolate(x, scale_factor=2.0, mode="nearest"), c.weight, c.bias, padding=1))
     x = _gn(d.conv_norm_out, x, True)
-    return r16(F.conv2d(x, d.conv_out.weight, d.conv_out.bias, padding=1))
+    return r16(_conv(x, d.conv_out.weight, d.conv_out.bias, padding=1))
 
 
 # ------------------------------------------------------------------------------------------ denoising loop

@@ -46,7 +46,11 @@ struct TcParams {
     int conv;               // 0 = GEMM, 1 = conv
     int taps;               // 1 or 9
     int kc1, kc2;           // 64-channel slabs in source tensor 1 / 2 (channel concat)
-    int stride, pad;        // conv stride and padding
+    int stride, pad;        // conv stride and padding (tap (dy, dx) reads input pixel out * stride + d - pad + off)
+    int tap_w;              // taps per filter row: 3 (3x3), 2 (2x2 sub-pixel phase), 1
+    int off_x, off_y;       // extra tap offset (sub-pixel phases of the fused nearest-2x upsample: phase - 1 + pad)
+    int osx, osy, oox, ooy; // output pixel (y, x) of the tile grid lands at (y * osy + ooy, x * osx + oox) ...
+    int HoF, WoF;           // ... of an output image of HoF x WoF pixels (== Ho x Wo, scale 1, offset 0 for plain convs)
     int Ho, Wo, Bn;         // output image size and image count
     int bw, bh, bb;         // output pixels per tile: bw * bh * bb == 128
     int tiles_x, tiles_y;   // tiles per image row / column
@@ -173,9 +177,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                     } else {
                         const int kct = p.kc1 + p.kc2;
                         const int tap = kb / kct, kc = kb - tap * kct;
-                        const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
-                        const int x0 = tx * p.bw * p.stride + dx - p.pad;
-                        const int y0 = ty * p.bh * p.stride + dy - p.pad;
+                        const int dy = tap / p.tap_w, dx = tap - dy * p.tap_w;
+                        const int x0 = tx * p.bw * p.stride + dx - p.pad + p.off_x;
+                        const int y0 = ty * p.bh * p.stride + dy - p.pad + p.off_y;
                         if (kc < p.kc1)
                             tc::tma_load_4d_pair(&mapA0, fb, dstA, kc * BK, x0, y0, tb * p.bb);
                         else
@@ -190,9 +194,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                     } else {
                         const int kct = p.kc1 + p.kc2;
                         const int tap = kb / kct, kc = kb - tap * kct;
-                        const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
-                        const int x0 = tx * p.bw * p.stride + dx - p.pad;
-                        const int y0 = ty * p.bh * p.stride + dy - p.pad;
+                        const int dy = tap / p.tap_w, dx = tap - dy * p.tap_w;
+                        const int x0 = tx * p.bw * p.stride + dx - p.pad + p.off_x;
+                        const int y0 = ty * p.bh * p.stride + dy - p.pad + p.off_y;
                         if (kc < p.kc1)
                             tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
                         else
@@ -275,8 +279,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 const int x = tx * p.bw + xi, y = ty * p.bh + yi;
                 img = tb * p.bb + bi;
                 row_ok = (x < p.Wo) && (y < p.Ho) && (img < p.Bn);
-                out_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldo;
-                res_off = ((static_cast<long>(img) * p.Ho + y) * p.Wo + x) * p.ldr;
+                const long pix = (static_cast<long>(img) * p.HoF + (y * p.osy + p.ooy)) * p.WoF + (x * p.osx + p.oox);
+                out_off = pix * p.ldo;
+                res_off = pix * p.ldr;
             }
             const int m_glob = m_blk * BM + row;
             const float bias_row = (p.bias_mode == 2 && row_ok) ? __half2float(p.bias[m_glob]) : 0.f;
@@ -655,37 +660,39 @@ int num_sms_cached() {
 }
 
 // Tile configuration of one problem: width BN and whether the CTA-pair kernel (256 x BN tiles, cta_group::2) runs it.
-// Pairs need at least two waves of 128-row tiles (smaller problems keep the 1-SM kernel and its split-K) and BN >= 128.
-// Pair tile width: 256 / 160 / 128 by (waves of 74 pairs) x width, wider tiles preferred (less shared-memory traffic per
-// FLOP: relative cost 1.00 / 1.08 / 1.15).  RF_GEMM_PAIR=0 disables, RF_GEMM_BN=<n> forces a width (A/B measurements).
+// Measured (profiles/r02_tile_configs.md): pairs pay off with 256-wide tiles only — 1.25-1.30x the 1-SM kernel on the
+// N = 1280 / 2560 / 5120 / 10240 layers (up to 1460 TFLOP/s) — while pair tiles of 160 / 128 columns are no faster than
+// the 1-SM kernel.  So: pair + BN 256 when 256 divides N (or N == 256), the problem fills two waves, and the padding of
+// odd row-block counts (per batch entry) does not eat the gain; otherwise the 1-SM kernel with pick_bn's width.
+// RF_GEMM_PAIR=0 disables pairs, RF_GEMM_BN=<256|160|128> forces a pair tile width (A/B measurements, parity tests).
 struct TileCfg {
     int bn;
     bool pair;
 };
-TileCfg pick_cfg(int N, long tiles_m_total, bool act_geglu) {
+TileCfg pick_cfg(int N, long tiles_m, int nbatch) {
     const char* env_pair = getenv("RF_GEMM_PAIR");      // read per call: the parity tests flip them inside one process
     const char* env_bn = getenv("RF_GEMM_BN");
-    (void)act_geglu;
+    const long tiles_m_total = tiles_m * nbatch;
     TileCfg c{pick_bn(N, tiles_m_total), false};
-    const bool pair_ok = !(env_pair && env_pair[0] == '0') && N >= 128 &&
-                         tiles_m_total * ((N + c.bn - 1) / c.bn) >= 2L * num_sms_cached();
-    if (!pair_ok) return c;
-    const long pairs = num_sms_cached() / 2, rows2 = (tiles_m_total + 1) / 2;
-    const int cand[3] = {256, 160, 128};
-    const double pen[3] = {1.00, 1.08, 1.15};
-    double best = 1e30;
-    for (int i = 0; i < 3; ++i) {
-        const int bn = cand[i];
-        if (bn == 160 && (N % 160)) continue;
-        if (bn == 256 && (N % 256) && N > 256) continue;       // no ragged 256-wide tiles
-        if (env_bn && atoi(env_bn) != bn) continue;
-        const long t = rows2 * ((N + bn - 1) / bn);
-        const double cost = static_cast<double>((t + pairs - 1) / pairs) * bn * pen[i];
-        if (cost < best) {
-            best = cost;
+    if ((env_pair && env_pair[0] == '0') || N < 128) return c;
+    const long sms = num_sms_cached(), pairs = sms / 2;
+    const long rows2 = ((tiles_m + 1) / 2) * nbatch;
+    if (env_bn) {                                        // forced pair width
+        const int bn = atoi(env_bn);
+        if ((bn == 256 || bn == 160 || bn == 128) && !(bn == 160 && N % 160) && tiles_m_total * ((N + c.bn - 1) / c.bn) >= 2 * sms) {
             c.bn = bn;
             c.pair = true;
         }
+        return c;
+    }
+    if ((N % 256) != 0) return c;
+    const long t1 = tiles_m_total * ((N + c.bn - 1) / c.bn), t2 = rows2 * (N / 256);
+    if (t1 < 2 * sms) return c;
+    const double cost1 = static_cast<double>((t1 + sms - 1) / sms) * c.bn;
+    const double cost2 = static_cast<double>((t2 + pairs - 1) / pairs) * 256 / 1.25;
+    if (cost2 < cost1) {
+        c.bn = 256;
+        c.pair = true;
     }
     return c;
 }
@@ -708,7 +715,7 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
     p.tiles_m = tiles_m;
     // split-K: non-batched, plain or SiLU epilogue, 16-byte aligned fp16/fp32 rows
     const long rows = p.conv ? static_cast<long>(p.Bn) * p.Ho * p.Wo : p.M;
-    const bool can_split = nbatch == 1 && p.act != 2 && (N % 8) == 0 && (p.ldo % 8) == 0 &&
+    const bool can_split = nbatch == 1 && p.act != 2 && (N % 8) == 0 && (p.ldo % 8) == 0 && (!p.conv || p.osx == 1) &&
                            (!p.residual || (p.ldr % 8) == 0) &&
                            ((reinterpret_cast<uintptr_t>(p.out ? static_cast<void*>(p.out) : static_cast<void*>(p.out_f32)) & 15) == 0);
     p.splits = pick_splits(rows, N, p.tiles_n * tiles_m, p.num_kb, num_sms_cached(), can_split);
@@ -768,7 +775,7 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
         int rc = make_map(&ma, d->A, dims, str, box, es);
         if (rc) return rc;
     }
-    const TileCfg cfg = pick_cfg(d->N, static_cast<long>((d->M + BM - 1) / BM) * b1 * b2, d->act == 2);
+    const TileCfg cfg = pick_cfg(d->N, (d->M + BM - 1) / BM, b1 * b2);
     {
         const long dims[4] = {d->K, d->N, b_m1 ? b1 : 1, b_m2 ? b2 : 1};
         const long str[4] = {1, d->ldb, b_m1 ? d->sb1 : d->ldb, b_m2 ? d->sb2 : d->ldb};
@@ -803,15 +810,19 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
 extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     if (!d || !d->x1 || !d->w || !d->out || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C1 <= 0 || d->Cout <= 0)
         return rf_fail(RF_ERR_INVALID, "rf_conv2d_f16: bad argument");
-    if (d->ksize != 1 && d->ksize != 3) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: kernel size must be 1 or 3");
+    const bool up2 = d->pad_mode == 2;      // nearest-2x upsample fused in: four 2x2 sub-pixel convolutions
+    if (up2 && (d->ksize != 2 || d->stride != 1 || d->x2 || d->residual))
+        return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: pad_mode 2 (fused upsample) takes ksize 2 phase weights, stride 1, "
+                                           "one input, no residual");
+    if (!up2 && d->ksize != 1 && d->ksize != 3) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: kernel size must be 1 or 3");
     if (d->stride != 1 && d->stride != 2) return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: stride must be 1 or 2");
     if ((d->C1 % BK) || (d->x2 && (d->C2 % BK)))
         return rf_fail(RF_ERR_UNSUPPORTED, "rf_conv2d_f16: channel counts must be multiples of 64 (use the direct "
                                            "convolution for the 4- and 3-channel layers)");
     const int pad = (d->ksize == 3 && d->pad_mode == 0) ? 1 : 0;
     const int extra = (d->ksize == 3 && d->pad_mode == 1) ? 1 : 0;   // one implicit zero row/column at the far edge
-    const int Ho = (d->H + 2 * pad + extra - d->ksize) / d->stride + 1;
-    const int Wo = (d->W + 2 * pad + extra - d->ksize) / d->stride + 1;
+    const int Ho = up2 ? d->H : (d->H + 2 * pad + extra - d->ksize) / d->stride + 1;   // up2: the tile grid is the input grid
+    const int Wo = up2 ? d->W : (d->W + 2 * pad + extra - d->ksize) / d->stride + 1;
     // output pixels per tile
     int bw = Wo >= 128 ? 128 : Wo;
     while (BM % bw) --bw;  // bw must divide 128
@@ -842,7 +853,7 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     const int taps = d->ksize * d->ksize;
     const long Ktot = static_cast<long>(taps) * (d->C1 + C2);
     const long conv_tiles_m = static_cast<long>((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((d->B + bb - 1) / bb);
-    const TileCfg cfg = pick_cfg(d->Cout, conv_tiles_m, false);
+    const TileCfg cfg = pick_cfg(d->Cout, conv_tiles_m, 1);
     {
         const long dims[4] = {Ktot, d->Cout, 1, 1};
         const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
@@ -858,7 +869,10 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     p.kc1 = d->C1 / BK; p.kc2 = C2 / BK;
     p.num_kb = taps * (p.kc1 + p.kc2);
     p.stride = s; p.pad = pad;
+    p.tap_w = d->ksize; p.off_x = 0; p.off_y = 0;
+    p.osx = 1; p.osy = 1; p.oox = 0; p.ooy = 0;
     p.Ho = Ho; p.Wo = Wo; p.Bn = d->B;
+    p.HoF = Ho; p.WoF = Wo;
     p.bw = bw; p.bh = bh; p.bb = bb;
     p.tiles_x = (Wo + bw - 1) / bw;
     p.tiles_y = (Ho + bh - 1) / bh;
@@ -873,7 +887,28 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     p.residual = static_cast<const __half*>(d->residual);
     p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.act = d->act;
-    return dispatch(d->Cout, cfg, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+    if (!up2) return dispatch(d->Cout, cfg, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+    // conv3x3(pad 1) of the nearest-2x upsampled image == four 2x2 convolutions of the input, one per output parity
+    // (py, px): output (2y + py, 2x + px) reads input rows y + py - 1 + {0, 1} and columns x + px - 1 + {0, 1}; the 3x3 taps
+    // that fall on the same input pixel are pre-summed in the phase weights w[phase][Cout][2][2][Cin] (9 -> 4 taps: 2.25x
+    // fewer FLOPs, and the upsampled tensor is never written).
+    p.osx = 2; p.osy = 2; p.HoF = 2 * Ho; p.WoF = 2 * Wo;
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        p.off_y = py - 1; p.off_x = px - 1;
+        p.ooy = py; p.oox = px;
+        CUtensorMap mph;
+        const long dims[4] = {Ktot, d->Cout, 1, 1};
+        const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
+        const int box[4] = {BK, cfg.pair ? cfg.bn / 2 : cfg.bn, 1, 1};
+        const int es[4] = {1, 1, 1, 1};
+        int rc = make_map(&mph, static_cast<const __half*>(d->w) + static_cast<long>(ph) * d->Cout * Ktot, dims, str, box, es);
+        if (rc) return rc;
+        TcParams q = p;
+        rc = dispatch(d->Cout, cfg, m1, m2, mph, q, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    }
+    return RF_OK;
 }
 
 // Live measurement aid for bench.py: between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed

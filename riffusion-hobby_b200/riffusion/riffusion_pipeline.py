@@ -155,7 +155,9 @@ class RiffusionPipeline:
             a = inp.alpha
             strength = (1 - a) * inp.start.denoising + a * inp.end.denoising
             guidance = inp.start.guidance * (1.0 - a) + inp.end.guidance * a
-            groups.setdefault((round(strength, 9), round(guidance, 9), inp.num_inference_steps), []).append(i)
+            # exact floats, not rounded: `int(num_inference_steps * strength)` (:361) depends on the last bit of the
+            # reference's own lerp (alpha 0.3, denoising 0.75 -> 0.7499999999999999 -> one evaluation fewer)
+            groups.setdefault((strength, guidance, inp.num_inference_steps), []).append(i)
         mask = None
         if mask_image:
             vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)

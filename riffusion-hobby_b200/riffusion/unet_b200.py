@@ -43,11 +43,15 @@ class UNetB200:
         self.heads, self.groups = heads, groups
         self.max_score_bytes = max_score_bytes
         self.fused_attention = True     # False: materialise fp16 scores (GEMM -> softmax -> GEMM), as the reference does
+        self.fused_upsample = True      # False: nearest-2x upsample kernel + 3x3 conv, as the reference does
         self.in_channels = int(state_dict["conv_in.weight"].shape[1]) if "conv_in.weight" in state_dict else 4
         self.w: T.Dict[str, torch.Tensor] = {}
         dev = self.device
         for name, p in state_dict.items():
-            if p.dim() == 4 and p.shape[2] == 3 and not name.endswith("conv_in.weight"):
+            if p.dim() == 4 and p.shape[2] == 3 and ".upsamplers." in name:
+                self.w[name] = ops.pack_conv_weight(p.detach()).to(dev)
+                self.w[name + ".up2x"] = ops.pack_upsample_weight(p.detach()).to(dev)   # four 2x2 sub-pixel phase kernels
+            elif p.dim() == 4 and p.shape[2] == 3 and not name.endswith("conv_in.weight"):
                 self.w[name] = ops.pack_conv_weight(p.detach()).to(dev)      # (Cout, 3, 3, Cin), packed where the tensor lives
             elif p.dim() == 4 and p.shape[2] == 1:
                 self.w[name] = _h(p.reshape(p.shape[0], p.shape[1]), dev)    # 1x1 conv == linear over pixels
@@ -89,6 +93,13 @@ class UNetB200:
             sc = ops.gemm(x.reshape(B * H * W, C), w[pfx + "conv_shortcut.weight"], bias=w[pfx + "conv_shortcut.bias"])
             x = sc.reshape(B, H, W, -1)
         return ops.conv2d(h, w[pfx + "conv2.weight"], bias=w[pfx + "conv2.bias"], residual=x)
+
+    def _upsample_conv(self, pfx: str, x: torch.Tensor) -> torch.Tensor:
+        """Upsample2D: F.interpolate(scale_factor=2, mode="nearest") then conv 3x3 pad 1"""
+        w = self.w
+        if self.fused_upsample and x.shape[-1] % 64 == 0:
+            return ops.conv2d_upsample2x(x, w[pfx + "weight.up2x"], bias=w[pfx + "bias"])
+        return ops.conv2d(ops.upsample2x(x), w[pfx + "weight"], bias=w[pfx + "bias"])
 
     def _attention(self, q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, nk: int) -> torch.Tensor:
         """q: (B, Nq, C), k: (B, Nk, C), vt: (B, C, pitch>=Nk) (V transposed).  softmax(q k^T / sqrt(d)) v per head,
@@ -207,8 +218,7 @@ class UNetB200:
                 if has_attn:
                     x = self._transformer(f"{p}attentions.{j}.", x, ctx, ctx_cache)
             if (p + "upsamplers.0.conv.weight") in w:
-                x = ops.upsample2x(x)
-                x = ops.conv2d(x, w[p + "upsamplers.0.conv.weight"], bias=w[p + "upsamplers.0.conv.bias"])
+                x = self._upsample_conv(p + "upsamplers.0.conv.", x)
         x = ops.group_norm(x, w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.groups, 1e-5, silu=True)
         out = ops.conv_out(x, w["conv_out.weight"], w["conv_out.bias"])
         return _Out(sample=out)

@@ -74,8 +74,7 @@ class VaeB200(UNetB200):
             for j in range(3):
                 x = self._resnet(f"{p}resnets.{j}.", x, None, eps=1e-6)
             if (p + "upsamplers.0.conv.weight") in w:
-                x = ops.upsample2x(x)
-                x = ops.conv2d(x, w[p + "upsamplers.0.conv.weight"], bias=w[p + "upsamplers.0.conv.bias"])
+                x = self._upsample_conv(p + "upsamplers.0.conv.", x)
         x = ops.group_norm(x, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], self.groups, 1e-6, silu=True)
         return types.SimpleNamespace(sample=ops.conv_out(x, w["decoder.conv_out.weight"], w["decoder.conv_out.bias"]))
 

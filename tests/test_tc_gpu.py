@@ -256,3 +256,25 @@ def test_pair_kernel_conv_matches_torch(native_lib, B, H, W, C1, C2, Cout, k, st
         assert float((got != single).float().mean()) < 1e-3
     finally:
         _pair_env(None)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 1280, 1280), (2, 32, 32, 640, 640), (1, 8, 8, 128, 64),
+                                            (16, 32, 32, 640, 640), (3, 64, 64, 256, 256), (2, 5, 7, 64, 192)])
+def test_fused_upsample_conv_matches_torch(native_lib, B, H, W, Cin, Cout):
+    """Upsample2D = F.interpolate(nearest, 2x) + conv 3x3 pad 1, computed as four 2x2 sub-pixel convolutions on the
+    low-resolution input (rf_conv2d_f16 pad_mode 2): vs torch on the upsampled tensor, and vs the unfused kernels"""
+    import torch.nn.functional as F
+
+    from riffusion import tc_ops as ops
+
+    torch.manual_seed(H + Cin + Cout)
+    x = (torch.randn(B, H, W, Cin, device="cuda") * 0.5).half()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") * Cin ** -0.5 / 3).half()
+    bias = torch.randn(Cout, device="cuda").half()
+    ref = F.conv2d(F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest"), w.float(), bias.float(),
+                   padding=1).permute(0, 2, 3, 1)
+    got = ops.conv2d_upsample2x(x, ops.pack_upsample_weight(w), bias=bias)
+    assert got.shape == (B, 2 * H, 2 * W, Cout)
+    _close(got, ref, tol=3e-3)             # + one fp16 rounding of the pre-summed phase weights
+    unfused = ops.conv2d(ops.upsample2x(x), ops.pack_conv_weight(w), bias=bias)
+    assert float((got.float() - unfused.float()).norm() / unfused.float().norm()) < 1e-3
