@@ -3,9 +3,10 @@ against the plain-PyTorch oracle (oracle/unet_oracle.py) evaluated in fp32 with 
 and the same inputs.  The oracle's parity is UNPINNED (diffusers is not installable here); its architecture is
 checked by parameter count and scheduler constants in tests/test_unet_cpu.py.
 
-Tolerance for whole-network outputs ("within 1e-3 relative fp16"): our fp16 network and a torch
-fp16 run of the oracle are two differently-rounded fp16 evaluations of the same function, so the bar is
-    rel_l2(ours, fp32 oracle) <= max(1e-3, 1.5 * rel_l2(torch-fp16 oracle, fp32 oracle)).
+Tolerance for whole-network outputs ("within 1e-3 relative fp16"): fp16 storage between operators alone
+costs `floor = rel_l2(fp16-storage emulation of the oracle, fp32 oracle)` (oracle/unet_emul.py; 1.4-1.7e-3 for these
+networks, and two equally valid fp16 evaluations sit sqrt(2) x floor apart — measured in tests/test_parity_bench_gpu.py),
+so the bar is  rel_l2(ours, fp32 oracle) <= 1.15 * floor + 1e-4 : nothing beyond what fp16 storage itself costs.
 """
 import pytest
 import torch
@@ -103,15 +104,18 @@ def _compare(oracle, ours, B, HW, ctx_dim, t):
     torch.manual_seed(1)
     x = torch.randn(B, 4, HW, HW, device="cuda").half()
     ctx = torch.randn(B, 77, ctx_dim, device="cuda").half()
+    from oracle import unet_emul as ue
+
     ref32 = oracle(x.float(), t, ctx.float())
+    floor = rel_l2(ue.unet_forward(oracle, x, t, ctx), ref32)
     ref16 = oracle.half()(x, t, ctx).float()
     oracle.float()
     got = ours(x, t, encoder_hidden_states=ctx).sample
     assert got.shape == ref32.shape and got.dtype == torch.float16
     e_ours, e_t16 = rel_l2(got, ref32), rel_l2(ref16, ref32)
-    print(f"rel_l2 ours vs fp32 oracle {e_ours:.3e}; torch fp16 vs fp32 oracle {e_t16:.3e}")
+    print(f"rel_l2 ours vs fp32 oracle {e_ours:.3e}; fp16-storage floor {floor:.3e}; torch fp16 (the reference's dtype) {e_t16:.3e}")
     assert torch.isfinite(got).all()
-    assert e_ours <= max(1e-3, 1.5 * e_t16)
+    assert e_ours <= 1.15 * floor + 1e-4
     return e_ours, e_t16
 
 
@@ -182,11 +186,12 @@ def test_vae_decode_and_encode_match_oracle(native_lib):
     z = torch.randn(1, 4, 32, 32, device="cuda").half()
     ref = oracle.decode(z.float() / 0.18215)
     got = ours.decode(z, scale=1 / 0.18215).sample
-    ref16 = oracle.half().decode(z / 0.18215).float()
-    oracle.float()
-    e, e16 = rel_l2(got, ref), rel_l2(ref16, ref)
-    print(f"vae decode rel_l2 ours {e:.3e} torch-fp16 {e16:.3e}")
-    assert got.shape == (1, 3, 256, 256) and e <= max(1e-3, 1.5 * e16)
+    from oracle import unet_emul as ue
+
+    floor = rel_l2(ue.vae_decode(oracle, z, 1 / 0.18215), ref)
+    e = rel_l2(got, ref)
+    print(f"vae decode rel_l2 ours {e:.3e} fp16-storage floor {floor:.3e}")
+    assert got.shape == (1, 3, 256, 256) and e <= 1.15 * floor + 1e-4
     img = (torch.rand(1, 3, 128, 160, device="cuda") * 2 - 1).half()
     mean_ref, logvar_ref = oracle.encode_moments(img.float())
     mean, logvar = ours.encode_moments(img)
@@ -194,7 +199,7 @@ def test_vae_decode_and_encode_match_oracle(native_lib):
     oracle.float()
     e, e16 = rel_l2(mean, mean_ref), rel_l2(m16, mean_ref)
     print(f"vae encode mean rel_l2 ours {e:.3e} torch-fp16 {e16:.3e}")
-    assert mean.shape == (1, 4, 16, 20) and e <= max(1e-3, 1.5 * e16)
+    assert mean.shape == (1, 4, 16, 20) and e <= 1.25 * e16 + 1e-4       # no emulation of the encoder: torch-fp16 as the yardstick
     assert rel_l2(logvar, logvar_ref.clamp(-1e9, 1e9)) <= max(2e-3, 2 * rel_l2(oracle.half().encode_moments(img)[1].float(), logvar_ref))
     oracle.float()
 
@@ -222,9 +227,13 @@ def test_denoising_loop_matches_oracle_loop(native_lib):
                                        num_inference_steps=steps, guidance_scale=7.0, uncond_embeddings=uncond,
                                        noise_a=na, noise_b=nb, output_type="latent")
         assert out["n_unet_evals"] == n_ref
-        e = rel_l2(out["latents_unscaled"], ref)
-        print(f"loop steps={steps} strength={strength}: evals {n_ref}, rel_l2 {e:.3e}")
-        assert e < 2e-2          # fp16 latents through n_ref guided steps (guidance 7 amplifies eps rounding 7x)
+        from oracle import unet_emul as ue
+
+        noise = uo.slerp(0.25, na.float(), nb.float())
+        emul, _ = ue.img2img_loop_emul(oracle, uo.PNDMSchedulerOracle(), text, uncond, lat, noise, strength, steps, 7.0)
+        e, floor = rel_l2(out["latents_unscaled"], ref), rel_l2(emul, ref)
+        print(f"loop steps={steps} strength={strength}: evals {n_ref}, rel_l2 {e:.3e}, fp16-storage floor of the loop {floor:.3e}")
+        assert e <= 1.3 * floor + 2e-4
 
 
 def test_cuda_graph_reuse_with_new_context(native_lib):
