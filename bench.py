@@ -8,6 +8,10 @@ Two workloads:
       per GPU per step.  roofline = the tcgen05 GEMM/conv kernel (tensor bound).  The Griffin-Lim sub-benchmark of
       configs[1] is run too and reported under "griffinlim" (its own HBM roofline = "GL HBM GB/s" of the metric).
   --workload gl: only BASELINE configs[1] — inverse-mel + 32-iteration Griffin-Lim, 512x512 mel, batch 64 per GPU.
+  --workload riffuse: BASELINE configs[2] — ONE request through RiffusionPipeline.riffuse() (PIL in -> PIL out, seed image
+      og_beat, alpha 0.5, 50 scheduler steps, --denoising 0.75 -> 38 CFG evaluations; 1.0 -> 50): latency per request.
+  --workload roundtrip: BASELINE configs[4] — audio -> image -> audio: STFT + mel + image quantisation of 16 waveforms per
+      GPU, VAE encode, 50-step denoise, VAE decode, image -> mel -> inverse mel + Griffin-Lim -> int16.
 
 gl workload: one "step" = one pass of the hot path over one batch of 64 synthetic clips per GPU.
   value  : clips/s, whole job, inputs (mel amplitudes + initial phases) resident in HBM
@@ -161,13 +165,18 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="clip", choices=["clip", "gl"])
+    ap.add_argument("--workload", default="clip", choices=["clip", "gl", "riffuse", "roundtrip"])
+    ap.add_argument("--denoising", type=float, default=0.75, help="riffuse workload: img2img strength (0.75 -> 38 of 50 evals)")
     ap.add_argument("--clips", type=int, default=32, help="clips per GPU per step (clip workload)")
     ap.add_argument("--evals", type=int, default=50, help="scheduler steps = UNet evaluations per clip (denoising 1.0)")
     args = ap.parse_args()
-    if args.workload == "clip" and args.impl == "b200":
+    if args.workload == "roundtrip" and args.clips == 32:
+        args.clips = 16                      # BASELINE configs[4]: batch 128 on 8 GPUs
+    if args.workload in ("clip", "roundtrip") and args.impl == "b200":
         return main_clip(args)
-    if args.workload == "clip" and args.impl == "reference":
+    if args.workload == "riffuse" and args.impl == "b200":
+        return main_riffuse(args)
+    if args.workload in ("clip", "roundtrip", "riffuse") and args.impl == "reference":
         return main_clip_reference(args)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -355,74 +364,118 @@ def time_reference_clip(host_cores: int, budget_s: float = 25.0) -> dict:
     rate) — stated in `sample`."""
     from oracle import unet_oracle as uo
 
-    threads = min(host_cores, 32)
-    torch.set_num_threads(threads)
     with torch.no_grad():
         unet = uo.init_weights_(uo.UNet2DConditionOracle()).eval()
         x = torch.randn(2, 4, 64, 64)
         ctx = torch.randn(2, 77, 768)
-        t0 = time.perf_counter()
-        unet(x, 741, ctx)
-        t_unet = time.perf_counter() - t0
+        t_unet, threads = None, None
+        for th in sorted({min(host_cores, 32), host_cores}):      # fastest of 32 threads and all cores (BASELINE.md 4)
+            torch.set_num_threads(th)
+            t0 = time.perf_counter()
+            unet(x, 741, ctx)
+            dt = time.perf_counter() - t0
+            if t_unet is None or dt < t_unet:
+                t_unet, threads = dt, th
     audio = time_reference(1, 1, host_cores)
     return {"t_unet_cfg_eval_s": t_unet, "t_audio_s": audio["seconds_per_clip"], "threads": threads,
             "audio_threads": audio["cores"]}
 
 
-def clip_config(n_steps: int, n_evals: int, clips_per_gpu: int) -> dict:
-    """`config` of the clip workload: shared by the B200 arm and the reference arm (the driver compares them)"""
-    return {"workload": f"full clip: {n_steps}-step img2img (denoising 1.0 -> {n_evals} CFG UNet evaluations, guidance 7, PNDM) + VAE "
-                        f"decode + image->mel + inverse-mel + Griffin-Lim {N_ITER} it, 512x512, {clips_per_gpu} clips per GPU per step",
+def clip_config(n_steps: int, n_evals: int, clips_per_gpu: int, workload: str = "clip", denoising: float = 1.0) -> dict:
+    """`config` of the clip-type workloads: shared by the B200 arm and the reference arm (the driver compares them)"""
+    if workload == "roundtrip":
+        name = (f"configs[4] audio->image->audio round trip: STFT + mel + uint8 image of {L_WAVE}-sample waveforms, VAE encode, "
+                f"{n_steps}-step img2img (denoising 1.0 -> {n_evals} CFG UNet evaluations, guidance 7, PNDM), VAE decode, image->mel + "
+                f"inverse-mel + Griffin-Lim {N_ITER} it -> int16, 512x512, {clips_per_gpu} clips per GPU per step")
+    elif workload == "riffuse":
+        name = (f"configs[2] RiffusionPipeline.riffuse(): one request, seed image og_beat 512x512, alpha 0.5, {n_steps} scheduler steps, "
+                f"denoising {denoising} -> {n_evals} CFG UNet evaluations, guidance 7, PIL image in -> PIL image out")
+    else:
+        name = (f"full clip: {n_steps}-step img2img (denoising 1.0 -> {n_evals} CFG UNet evaluations, guidance 7, PNDM) + VAE "
+                f"decode + image->mel + inverse-mel + Griffin-Lim {N_ITER} it, 512x512, {clips_per_gpu} clips per GPU per step")
+    return {"workload": name,
             "includes_denoise": True, "n_unet_evals": n_evals, "weights": "random-init SD-1.5 (N(0,0.02^2)), broadcast from rank 0 at init",
             "clips_per_gpu": clips_per_gpu, "cuda_graph": True,
             "l2": "UNet weights 1.7 GB + activations larger than L2; no explicit flush",
             "sharding": "independent clips per rank; NCCL broadcast of weights at init only"}
 
 
+VAE_ENC_TFLOP = 1.117            # SURVEY 8(a): VAE encoder, 512x512 image
+
+
+def n_evals_for(n_steps: int, denoising: float) -> int:
+    """UNet evaluations of the reference's img2img loop (riffusion_pipeline.py:358-396, PNDM table, steps_offset 1)"""
+    init = min(int(n_steps * denoising) + 1, n_steps)
+    return (n_steps + 1) - max(n_steps - init + 1, 0)
+
+
 def main_clip_reference(args) -> None:
-    """`--impl reference`, clip workload: the reference's CPU arithmetic for one clip on the host cores.  diffusers is
-    not installable here, so the UNet / VAE are the torch-eager fp32 restatement (oracle/unet_oracle.py: kind "port");
-    torchaudio is the reference's own audio path.  Each step is a bounded sample of one clip: ONE CFG UNet evaluation
-    + the inverse-mel + Griffin-Lim of one clip, extrapolated to n_evals evaluations + VAE decode (stated in `sample`)."""
+    """`--impl reference`: the reference's CPU arithmetic for one unit of the workload on the host cores.  diffusers is not
+    installable here, so the UNet / VAE are the torch-eager fp32 restatement (oracle/unet_oracle.py: kind "port");
+    torchaudio is the reference's own audio path.  Each step is a bounded sample: ONE CFG UNet evaluation (+ one clip of
+    torchaudio inverse-mel + Griffin-Lim, + one forward STFT/mel for the round trip), extrapolated to the workload's n_evals
+    evaluations and its VAE passes at the UNet's measured FLOP rate (stated in `sample`)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import unet_oracle as uo
     from oracle.torchaudio_ref import TorchaudioConverter
 
     cores = os.cpu_count() or 1
-    n_evals = args.evals
+    wl = args.workload
+    n_evals = n_evals_for(args.evals, args.denoising) if wl == "riffuse" else args.evals
     steps = max(1, min(args.steps, 20))
     warm = max(0, min(args.warmup, 1))
     audio = time_reference(1, 1, cores)                  # picks the fastest thread count for torch's CPU FFT path
     audio_threads = audio["cores"]
-    unet_threads = min(cores, 32)
+    # UNet leg: the fastest of 32 threads and all cores (BASELINE.md 4 asks for all host cores; torch's CPU conv does not
+    # always scale past a socket) — one evaluation each, then the timed steps with the winner
     conv = TorchaudioConverter(n_iter=N_ITER)
     mel = synthetic_mel(1, seed=0)
+    wave = torch.randn(1, L_WAVE) * 3000.0
     with torch.no_grad():
         unet = uo.init_weights_(uo.UNet2DConditionOracle()).eval()
         x, ctx = torch.randn(2, 4, 64, 64), torch.randn(2, 77, 768)
-        t_unet = t_audio = 0.0
+        cand = sorted({min(cores, 32), cores})
+        best = None
+        for th in cand:
+            torch.set_num_threads(th)
+            t0 = time.perf_counter()
+            unet(x, 741, ctx)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[1]:
+                best = (th, dt)
+        unet_threads = best[0]
+        t_unet = t_audio = t_fwd = 0.0
         for it in range(warm + steps):
             torch.set_num_threads(unet_threads)
             t0 = time.perf_counter()
             unet(x, 741, ctx)
             t1 = time.perf_counter()
             torch.set_num_threads(audio_threads)
-            conv.waveform_from_mel_amplitudes(mel)
+            if wl != "riffuse":
+                conv.waveform_from_mel_amplitudes(mel)
             t2 = time.perf_counter()
+            if wl == "roundtrip":
+                conv.mel_amplitudes_from_waveform(wave)
+            t3 = time.perf_counter()
             if it >= warm:
                 t_unet += t1 - t0
                 t_audio += t2 - t1
+                t_fwd += t3 - t2
     t_unet /= steps
     t_audio /= steps
-    sec = n_evals * t_unet * (1 + VAE_DEC_TFLOP / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE)) + t_audio
+    t_fwd /= steps
+    vae_tflop = VAE_DEC_TFLOP + (VAE_ENC_TFLOP if wl in ("riffuse", "roundtrip") else 0.0)
+    sec = n_evals * t_unet * (1 + vae_tflop / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE)) + t_audio + t_fwd
     value = 1.0 / sec
-    sample = (f"{steps} x [1 CFG UNet evaluation ({t_unet:.1f} s, torch-eager fp32 restatement, {unet_threads} threads) "
-              f"extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of torchaudio inverse-mel + "
-              f"Griffin-Lim ({t_audio:.1f} s, {audio_threads} threads)]; host has {cores} cores")
+    sample = (f"{steps} x [1 CFG UNet evaluation ({t_unet:.1f} s, torch-eager fp32 restatement, {unet_threads} threads = fastest of "
+              f"{cand}) extrapolated to {n_evals} evals + VAE {'encode + ' if vae_tflop > VAE_DEC_TFLOP else ''}decode at the same FLOP rate"
+              + (f", plus 1 clip of torchaudio inverse-mel + Griffin-Lim ({t_audio:.1f} s, {audio_threads} threads)" if wl != "riffuse" else "")
+              + (f", plus 1 forward STFT + mel ({t_fwd:.2f} s)" if wl == "roundtrip" else "") + f"]; host has {cores} cores")
     line = {"impl": "reference", "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": clip_config(args.evals, n_evals, args.clips),
+            "dtype": "f32", "data": "synthetic",
+            "config": clip_config(args.evals, n_evals, 1 if wl == "riffuse" else args.clips, wl, args.denoising),
             "cpu_baseline": {"value": value, "unit": "clips/s", "cores": unet_threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

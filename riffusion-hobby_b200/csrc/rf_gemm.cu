@@ -75,8 +75,29 @@ struct TcParams {
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == 1) return v / (1.f + __expf(-v));
+    if (act == 1) return __fdividef(v, 1.f + __expf(-v));
     return v;
+}
+
+// exact-erf GELU  g * Phi(g),  Phi(g) = 0.5 erfc(-g / sqrt 2), branch-free with ONE MUFU op:
+//   0.5 erfc(t) = 2^q(t) on t = |g| / sqrt 2 in [0, 4] (degree-7 fit of -log2 erfc(t) - 1; erfc(4) = 1.5e-8, clamped
+//   beyond), Phi = g < 0 ? h : 1 - h.  |error| <= 7e-7 absolute, <= 4.2e-6 relative (fp32 Horner), i.e. 1 % of an fp16 ulp —
+//   same function as erff's GELU (diffusers GEGLU uses the exact form), not the tanh approximation.  erff() costs ~35
+//   instructions per element on two divergent paths and made the K = 320 GEGLU GEMM epilogue-bound (ALU ~4500 clk per
+//   tile against 2560 clk of MMA).
+__device__ __forceinline__ float gelu_erf_fast(float g) {
+    const float t = fminf(fabsf(g) * 0.70710678118654752f, 4.0f);
+    float q = -2.1777638e-05f;
+    q = fmaf(q, t, 0.0005068331f);
+    q = fmaf(q, t, -0.005339398f);
+    q = fmaf(q, t, 0.034231447f);
+    q = fmaf(q, t, -0.15289085f);
+    q = fmaf(q, t, -0.91675895f);
+    q = fmaf(q, t, -1.6281544f);
+    q = fmaf(q, t, -0.9999938f);
+    float h;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(q));
+    return g * (g < 0.f ? h : 1.f - h);
 }
 
 // Persistent kernel: grid = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
@@ -96,8 +117,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    // BN = 320 (pairs only): two 160-wide MMA instructions per K step share the A operand; the 320 accumulator columns
+    // leave no room for a second set, so the epilogue of a tile does not overlap the next tile's MMAs (NBUF = 1) —
+    // worth it for long K: 56 B/clk of operands per SM instead of 115 (the 1-SM 128 x 160 tile is L2-feed bound).
+    static_assert(BN != 320 || PAIR, "320-wide tiles exist for CTA pairs only");
+    constexpr int UN = BN == 320 ? 160 : BN;        // MMA instruction width
+    constexpr int NI = BN / UN;                     // instructions per K step
+    constexpr int NBUF = BN == 320 ? 1 : 2;         // TMEM accumulator sets
     constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
-    constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM allocations are powers of two
+    constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;   // powers of two
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_TILE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
@@ -131,10 +159,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     }
     if (warp == 1) {
         if constexpr (PAIR) {
-            tc::tmem_alloc_pair(tmem_slot, 2 * ACC_COLS);
+            tc::tmem_alloc_pair(tmem_slot, NBUF * ACC_COLS);
             tc::tmem_relinquish_pair();
         } else {
-            tc::tmem_alloc(tmem_slot, 2 * ACC_COLS);
+            tc::tmem_alloc(tmem_slot, NBUF * ACC_COLS);
             tc::tmem_relinquish();
         }
     }
@@ -160,7 +188,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 ty = (m_blk / p.tiles_x) % p.tiles_y;
                 tb = m_blk / (p.tiles_x * p.tiles_y);
             }
-            const int n0 = n_blk * BN + (PAIR ? rank * (BN / 2) : 0);      // this CTA's rows of the B tile
+            const int n0 = n_blk * BN + ((PAIR && NI == 1) ? rank * (BN / 2) : 0);      // this CTA's rows of the B tile
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t phase = (it / STAGES) & 1;
@@ -173,7 +201,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                     const uint32_t fb = tc::mapa_u32(tc::smem_u32(&full[stage]), 0);
                     if (!p.conv) {
                         tc::tma_load_4d_pair(&mapA0, fb, dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
-                        tc::tma_load_4d_pair(&mapB, fb, dstB, kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)    // instruction i reads rows [i * UN/2, +UN/2) of this CTA's B stage
+                            tc::tma_load_4d_pair(&mapB, fb, static_cast<uint8_t*>(dstB) + i * (UN / 2) * BK * 2, kb * BK,
+                                                 n_blk * BN + i * UN + rank * (UN / 2), b1 * p.b_m1, b2 * p.b_m2);
                     } else {
                         const int kct = p.kc1 + p.kc2;
                         const int tap = kb / kct, kc = kb - tap * kct;
@@ -184,7 +215,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                             tc::tma_load_4d_pair(&mapA0, fb, dstA, kc * BK, x0, y0, tb * p.bb);
                         else
                             tc::tma_load_4d_pair(&mapA1, fb, dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
-                        tc::tma_load_4d_pair(&mapB, fb, dstB, kb * BK, n0, 0, 0);
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)
+                            tc::tma_load_4d_pair(&mapB, fb, static_cast<uint8_t*>(dstB) + i * (UN / 2) * BK * 2, kb * BK,
+                                                 n_blk * BN + i * UN + rank * (UN / 2), 0, 0);
                     }
                 } else {
                     tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
@@ -208,14 +242,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
-        constexpr uint32_t idesc = tc::make_idesc_f16(PAIR ? 2 * BM : BM, BN);
+        constexpr uint32_t idesc = tc::make_idesc_f16(PAIR ? 2 * BM : BM, UN);
         int it = 0, lt = 0;
         for (int unit = unit0; unit < n_tiles; unit += unit_step, ++lt) {
             const int sp = unit % p.splits;
             const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-            const int acc = lt & 1;
-            if (lt >= 2) {                                   // the epilogue must have drained this accumulator
-                tc::mbar_wait(&tmem_empty[acc], ((lt >> 1) - 1) & 1);
+            const int acc = lt % NBUF, use = lt / NBUF;
+            if (use >= 1) {                                  // the epilogue must have drained this accumulator
+                tc::mbar_wait(&tmem_empty[acc], (use - 1) & 1);
                 tc::fence_after_sync();
             }
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -229,9 +263,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
-                    const uint64_t db = tc::make_desc_sw128(b_base + k * 32);
-                    if constexpr (PAIR) tc::mma_f16_pair(d_tmem, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
-                    else tc::mma_f16(d_tmem, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const uint64_t db = tc::make_desc_sw128(b_base + i * (UN / 2) * BK * 2 + k * 32);
+                        if constexpr (PAIR) tc::mma_f16_pair(d_tmem + i * UN, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        else tc::mma_f16(d_tmem + i * UN, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                    }
                 }
                 if constexpr (PAIR) tc::mma_commit_pair(&empty[stage]);
                 else tc::mma_commit(&empty[stage]);
@@ -260,7 +297,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const uint32_t tmem_empty_leader = PAIR ? tc::mapa_u32(tc::smem_u32(&tmem_empty[0]), 0) : 0;
         for (int unit = unit0; unit < n_tiles; unit += unit_step, ++lt) {
             const int tile = unit / p.splits, sp = unit - tile * p.splits;
-            const int acc = lt & 1;
+            const int acc = lt % NBUF;
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
             const int m_row = mn / p.tiles_n, n_blk = mn - m_row * p.tiles_n;
             const int m_blk = PAIR ? 2 * m_row + rank : m_row;
@@ -285,7 +322,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             }
             const int m_glob = m_blk * BM + row;
             const float bias_row = (p.bias_mode == 2 && row_ok) ? __half2float(p.bias[m_glob]) : 0.f;
-            tc::mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+            tc::mbar_wait(&tmem_full[acc], (lt / NBUF) & 1);
             tc::fence_after_sync();
 #pragma unroll 1
             for (int c0 = half_id * 32; c0 < BN; c0 += 32 * EPI_SETS) {   // the warp sets take the 32-column runs round-robin
@@ -360,8 +397,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float g0 = f[16 + 2 * j], g1 = f[17 + 2 * j];
-                        const float y0 = f[2 * j] * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f)));
-                        const float y1 = f[2 * j + 1] * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f)));
+                        const float y0 = f[2 * j] * gelu_erf_fast(g0);
+                        const float y1 = f[2 * j + 1] * gelu_erf_fast(g1);
                         const __half2 h = __floats2half2_rn(y0, y1);
                         pk[j] = *reinterpret_cast<const uint32_t*>(&h);
                     }
@@ -440,8 +477,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     else __syncthreads();
     if (warp == 1) {
         tc::fence_after_sync();
-        if constexpr (PAIR) tc::tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
-        else tc::tmem_dealloc(tmem_base, 2 * ACC_COLS);
+        if constexpr (PAIR) tc::tmem_dealloc_pair(tmem_base, NBUF * ACC_COLS);
+        else tc::tmem_dealloc(tmem_base, NBUF * ACC_COLS);
     }
 }
 
@@ -503,6 +540,7 @@ template <int BN, int STAGES, bool PAIR>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
            cudaStream_t st) {   // `grid` arrives as (tiles_n, tiles_m, batch) and is flattened to a persistent 1-D grid
     const size_t smem = static_cast<size_t>(STAGES) * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024;
+    static_assert(STAGES * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024 <= 232448, "shared memory budget");
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -669,7 +707,7 @@ struct TileCfg {
     int bn;
     bool pair;
 };
-TileCfg pick_cfg(int N, long tiles_m, int nbatch) {
+TileCfg pick_cfg(int N, long tiles_m, int nbatch, int num_kb) {
     const char* env_pair = getenv("RF_GEMM_PAIR");      // read per call: the parity tests flip them inside one process
     const char* env_bn = getenv("RF_GEMM_BN");
     const long tiles_m_total = tiles_m * nbatch;
@@ -679,13 +717,24 @@ TileCfg pick_cfg(int N, long tiles_m, int nbatch) {
     const long rows2 = ((tiles_m + 1) / 2) * nbatch;
     if (env_bn) {                                        // forced pair width
         const int bn = atoi(env_bn);
-        if ((bn == 256 || bn == 160 || bn == 128) && !(bn == 160 && N % 160) && tiles_m_total * ((N + c.bn - 1) / c.bn) >= 2 * sms) {
+        if ((bn == 320 || bn == 256 || bn == 160 || bn == 128) && !(bn == 160 && N % 160) && !(bn == 320 && N % 320) &&
+            tiles_m_total * ((N + c.bn - 1) / c.bn) >= 2 * sms) {
             c.bn = bn;
             c.pair = true;
         }
         return c;
     }
-    if ((N % 256) != 0) return c;
+    if ((N % 256) != 0) {
+        // N = 320 / 640 / 960 ...: 320-wide pair tiles (two instructions, no accumulator double buffering) when K is long
+        // enough to amortise the exposed epilogue
+        const char* env320 = getenv("RF_GEMM_320_MIN_KB");
+        const int min_kb = env320 ? atoi(env320) : 10;
+        if ((N % 320) == 0 && num_kb >= min_kb && tiles_m_total * (N / 160) >= 2 * sms) {
+            c.bn = 320;
+            c.pair = true;
+        }
+        return c;
+    }
     const long t1 = tiles_m_total * ((N + c.bn - 1) / c.bn), t2 = rows2 * (N / 256);
     if (t1 < 2 * sms) return c;
     const double cost1 = static_cast<double>((t1 + sms - 1) / sms) * c.bn;
@@ -696,6 +745,9 @@ TileCfg pick_cfg(int N, long tiles_m, int nbatch) {
     }
     return c;
 }
+
+// rows of B one TMA load brings in: the whole tile (1-SM), this CTA's half (pairs), half of one 160-wide instruction (BN 320)
+int b_box_rows(const TileCfg& c) { return !c.pair ? c.bn : (c.bn == 320 ? 80 : c.bn / 2); }
 
 int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
              int tiles_m, int nbatch, cudaStream_t st) {
@@ -708,6 +760,7 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
         p.kb_per_split = p.num_kb;
         p.ws = nullptr;
         dim3 grid(p.tiles_n, p.tiles_m, nbatch);
+        if (bn == 320) return launch<320, 6, true>(a0, a1, b, p, grid, st);
         if (bn == 256) return launch<256, 6, true>(a0, a1, b, p, grid, st);
         if (bn == 160) return launch<160, 8, true>(a0, a1, b, p, grid, st);
         return launch<128, 8, true>(a0, a1, b, p, grid, st);
@@ -775,11 +828,11 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
         int rc = make_map(&ma, d->A, dims, str, box, es);
         if (rc) return rc;
     }
-    const TileCfg cfg = pick_cfg(d->N, (d->M + BM - 1) / BM, b1 * b2);
+    const TileCfg cfg = pick_cfg(d->N, (d->M + BM - 1) / BM, b1 * b2, (d->K + BK - 1) / BK);
     {
         const long dims[4] = {d->K, d->N, b_m1 ? b1 : 1, b_m2 ? b2 : 1};
         const long str[4] = {1, d->ldb, b_m1 ? d->sb1 : d->ldb, b_m2 ? d->sb2 : d->ldb};
-        const int box[4] = {BK, cfg.pair ? cfg.bn / 2 : cfg.bn, 1, 1};
+        const int box[4] = {BK, b_box_rows(cfg), 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&mb, d->B, dims, str, box, es);
         if (rc) return rc;
@@ -853,11 +906,11 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     const int taps = d->ksize * d->ksize;
     const long Ktot = static_cast<long>(taps) * (d->C1 + C2);
     const long conv_tiles_m = static_cast<long>((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((d->B + bb - 1) / bb);
-    const TileCfg cfg = pick_cfg(d->Cout, conv_tiles_m, 1);
+    const TileCfg cfg = pick_cfg(d->Cout, conv_tiles_m, 1, static_cast<int>(Ktot / BK));
     {
         const long dims[4] = {Ktot, d->Cout, 1, 1};
         const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
-        const int box[4] = {BK, cfg.pair ? cfg.bn / 2 : cfg.bn, 1, 1};
+        const int box[4] = {BK, b_box_rows(cfg), 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&mb, d->w, dims, str, box, es);
         if (rc) return rc;
@@ -900,7 +953,7 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
         CUtensorMap mph;
         const long dims[4] = {Ktot, d->Cout, 1, 1};
         const long str[4] = {1, Ktot, Ktot * d->Cout, Ktot * d->Cout};
-        const int box[4] = {BK, cfg.pair ? cfg.bn / 2 : cfg.bn, 1, 1};
+        const int box[4] = {BK, b_box_rows(cfg), 1, 1};
         const int es[4] = {1, 1, 1, 1};
         int rc = make_map(&mph, static_cast<const __half*>(d->w) + static_cast<long>(ph) * d->Cout * Ktot, dims, str, box, es);
         if (rc) return rc;
