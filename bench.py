@@ -482,6 +482,21 @@ def main_clip_reference(args) -> None:
     print(json.dumps(line))
 
 
+def load_frozen_weights(rank: int, dist, dev):
+    """random-init SD-1.5 UNet + VAE state dicts (BASELINE config 4): created on rank 0, broadcast ONCE as two flat NCCL
+    buffers through the library helper (riffusion/distributed.py) — the only collective of a run."""
+    from riffusion import sd15_spec
+    from riffusion.distributed import broadcast_state_dict
+
+    out = []
+    for spec, seed in ((sd15_spec.unet_spec(), 0), (sd15_spec.vae_spec(), 1)):
+        sd = {k: v.to(dev) for k, v in sd15_spec.random_state_dict(spec, seed).items()} if rank == 0 else None
+        if dist is not None:
+            sd = broadcast_state_dict(spec, sd, src=0, device=dev)
+        out.append(sd)
+    return out
+
+
 def main_clip(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -506,27 +521,14 @@ def main_clip(args) -> None:
 
     lib = _native.lib()
     # frozen weights: created on rank 0 and broadcast once over NCCL (init only; no collective in the step loop)
-    unet_spec, vae_spec = sd15_spec.unet_spec(), sd15_spec.vae_spec()
-    if rank == 0:
-        unet_sd = {k: v.to(dev) for k, v in sd15_spec.random_state_dict(unet_spec, 0).items()}
-        vae_sd = {k: v.to(dev) for k, v in sd15_spec.random_state_dict(vae_spec, 1).items()}
-    else:
-        unet_sd = {k: torch.empty(shp, dtype=torch.float16, device=dev) for k, shp in unet_spec}
-        vae_sd = {k: torch.empty(shp, dtype=torch.float16, device=dev) for k, shp in vae_spec}
-    if dist is not None:
-        for sd in (unet_sd, vae_sd):
-            flat = torch.cat([t.reshape(-1) for t in sd.values()])
-            dist.broadcast(flat, src=0)
-            off = 0
-            for k, t in sd.items():
-                sd[k] = flat[off: off + t.numel()].view(t.shape)
-                off += t.numel()
+    unet_sd, vae_sd = load_frozen_weights(rank, dist, dev)
     pipe = RiffusionPipeline(vae=VaeB200(vae_sd, device=str(dev)), unet=UNetB200(unet_sd, device=str(dev)), device=str(dev))
     del unet_sd, vae_sd
     params = SpectrogramParams()
     conv = SpectrogramConverter(params, device=str(dev))
 
     B, n_steps = args.clips, args.evals
+    roundtrip = args.workload == "roundtrip"
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     text = torch.randn((B, 77, 768), generator=g, device=dev, dtype=torch.float16)      # N(0,1) embeddings
     uncond = torch.randn((1, 77, 768), generator=g, device=dev, dtype=torch.float16)
@@ -538,20 +540,42 @@ def main_clip(args) -> None:
     mean, logvar = pipe.vae.encode_moments(img)                                          # cacheable per seed image
     std = torch.exp(0.5 * logvar.float().clamp(-30, 20))
 
-    def make_inputs():
-        """per-request tensors the reference draws from its generators: posterior noise + noise_a/noise_b -> slerp"""
+    def make_inputs(mean_=None, std_=None):
+        """per-request tensors the reference draws from its generators: posterior noise + noise_a/noise_b -> slerp.
+        mean_/std_: per-clip posterior moments (B,4,64,64) of the round-trip workload, else the cached seed-image moments"""
         lat, nas, nbs = [], [], []
+        shape = mean.shape
         for i in range(B):
             ga = torch.Generator(device=dev).manual_seed(i + 1000 * rank)
             gb = torch.Generator(device=dev).manual_seed(10_000 + i + 1000 * rank)
-            eps = torch.randn(mean.shape, generator=ga, device=dev)
-            lat.append((VAE_SCALE * (mean.float() + std * eps)).half())
-            nas.append(torch.randn(mean.shape, generator=ga, device=dev, dtype=torch.float16))
-            nbs.append(torch.randn(mean.shape, generator=gb, device=dev, dtype=torch.float16))
+            eps = torch.randn(shape, generator=ga, device=dev)
+            m_i = mean.float() if mean_ is None else mean_[i:i + 1].float()
+            s_i = std if std_ is None else std_[i:i + 1]
+            lat.append((VAE_SCALE * (m_i + s_i * eps)).half())
+            nas.append(torch.randn(shape, generator=ga, device=dev, dtype=torch.float16))
+            nbs.append(torch.randn(shape, generator=gb, device=dev, dtype=torch.float16))
         noise = tc_ops.slerp(alphas, torch.cat(nas), torch.cat(nbs))       # per-request slerp on the device (rf_slerp_f16)
         return torch.cat(lat), noise
 
     lat0, noise0 = make_inputs()
+    # round trip (configs[4]): int16-scaled band-limited noise of exactly 512 frames per clip (SURVEY 8d config 5)
+    waves_host = wave_dev = None
+    if roundtrip:
+        from riffusion.util import image_util
+
+        gw = torch.Generator().manual_seed(77 + rank)
+        w = torch.randn((B, L_WAVE + 16), generator=gw)
+        w = torch.nn.functional.avg_pool1d(w[:, None], 9, stride=1, padding=4)[:, 0, : L_WAVE] * 9000.0
+        waves_host = w.contiguous().pin_memory()
+        wave_dev = waves_host.to(dev)
+
+        def audio_to_latents(wav):
+            """waveform -> mel (rf_stft_mel) -> uint8 spectrogram image (rf_mel_to_image, per-clip max) -> VAE posterior"""
+            mel_in = conv.mel_amplitudes_from_waveform(wav)                          # (B, 512, 512)
+            imgs = torch.stack([image_util.image_from_spectrogram_device(mel_in[i:i + 1], power=0.25)[0] for i in range(B)])
+            x = (imgs.permute(0, 3, 1, 2).half() / 255.0) * 2 - 1                  # preprocess_image (:439-452)
+            m_, lv_ = pipe.vae.encode_moments(x)
+            return make_inputs(m_, torch.exp(0.5 * lv_.float().clamp(-30, 20)))
     F = 8821
     torch.manual_seed(rank)
     angles = torch.rand((B, F, T_FRAMES), dtype=torch.complex64, device=dev)
@@ -560,16 +584,22 @@ def main_clip(args) -> None:
     stream = torch.cuda.current_stream(dev)
 
     def step_device():
+        if roundtrip:
+            lat, nz = audio_to_latents(wave_dev)
+            return pipe.generate_clips(text, uncond, lat, nz, 1.0, n_steps, 7.0, conv, init_angles=angles)
         return pipe.generate_clips(text, uncond, lat0, noise0, 1.0, n_steps, 7.0, conv, init_angles=angles)
 
     def step_e2e():
         # host buffers in: seed image + text embeddings; out: uint8 image + int16 pcm
-        rgb = seed_host.to(dev, non_blocking=True)
         t_emb = text_host.to(dev, non_blocking=True)
         u_emb = uncond_host.to(dev, non_blocking=True)
-        im = (rgb.permute(2, 0, 1)[None].half() / 255.0) * 2 - 1
-        m_, lv_ = pipe.vae.encode_moments(im)            # the reference re-encodes the seed image on every request
-        lat, nz = make_inputs()
+        if roundtrip:
+            lat, nz = audio_to_latents(waves_host.to(dev, non_blocking=True))
+        else:
+            rgb = seed_host.to(dev, non_blocking=True)
+            im = (rgb.permute(2, 0, 1)[None].half() / 255.0) * 2 - 1
+            m_, lv_ = pipe.vae.encode_moments(im)            # the reference re-encodes the seed image on every request
+            lat, nz = make_inputs()
         out = pipe.generate_clips(t_emb, u_emb, lat, nz, 1.0, n_steps, 7.0, conv)      # random GL phases like the reference
         w = out["waveform"]
         pcm = torch.empty((B, L_WAVE), dtype=torch.int16, device=dev)
@@ -629,10 +659,10 @@ def main_clip(args) -> None:
     value = clips / (ms_step / 1e3)
     pk = tensor_peaks()
     achieved = tc_fl.value / (tc_ms.value / 1e3) / 1e12
-    alg_tflop_step = B * (n_evals * 2 * UNET_TFLOP_PER_SAMPLE + VAE_DEC_TFLOP)
+    alg_tflop_step = B * (n_evals * 2 * UNET_TFLOP_PER_SAMPLE + VAE_DEC_TFLOP + (VAE_ENC_TFLOP if roundtrip else 0.0))
     roofline = {
         "bound": "tensor", "kernel": "k_tc_gemm (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved,
-        "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "traffic": None,
+        "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "traffic": gemm_traffic(),
         "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
         "kernel_ms_per_step": tc_ms.value, "kernel_launches_per_step": tc_n.value,
         "kernel_flops_per_step": tc_fl.value, "kernel_share_of_step": tc_ms.value / ms_step,
@@ -640,19 +670,21 @@ def main_clip(args) -> None:
                 "CUDA events around every launch of one eager step; share is vs the CUDA-graph step",
         "step": {"algorithmic_tflop": alg_tflop_step, "achieved": alg_tflop_step / (ms_step / 1e3),
                  "frac": alg_tflop_step / (ms_step / 1e3) / pk["sustained"], "unit": "TFLOP/s",
-                 "formula": "B*(n_evals*2*0.803 + 2.515) TFLOP (SURVEY 8d)"},
+                 "formula": "B*(n_evals*2*0.803 + 2.515" + (" + 1.117" if roundtrip else "") + ") TFLOP (SURVEY 8d)"},
     }
     ms_e2e_step = ms_e2e / e2e_steps
     e2e = {"value": clips / (ms_e2e_step / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e_step,
-           "h2d_bytes_per_step": int(seed_host.numel() + text_host.numel() * 2 + uncond_host.numel() * 2),
+           "h2d_bytes_per_step": int((waves_host.numel() * 4 if roundtrip else seed_host.numel()) + text_host.numel() * 2 +
+                                     uncond_host.numel() * 2),
            "d2h_bytes_per_step": int(pcm_host.numel() * 2 + img_host.numel()),
            "steps": e2e_steps,
-           "api": "VaeB200.encode_moments + RiffusionPipeline.generate_clips + rf_wave_to_int16: pinned host seed image and "
-                  "text embeddings in, uint8 images and int16 PCM out"}
+           "api": ("SpectrogramConverter.mel_amplitudes_from_waveform + image_from_spectrogram_device + " if roundtrip else "") +
+                  "VaeB200.encode_moments + RiffusionPipeline.generate_clips + rf_wave_to_int16: pinned host " +
+                  ("waveforms" if roundtrip else "seed image") + " and text embeddings in, uint8 images and int16 PCM out"}
     # Griffin-Lim sub-benchmark (BASELINE configs[1]) in a child process so that its memory does not add to ours
     gl = None
     cpu_baseline = None
-    if world == 1:
+    if world == 1 and not roundtrip:
         try:
             r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--workload", "gl", "--steps", "5", "--warmup", "3",
                                 "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
@@ -661,14 +693,16 @@ def main_clip(args) -> None:
                   "workload": gl_line["config"]["workload"], "roofline": gl_line["roofline"], "e2e": gl_line["e2e"]}
         except Exception as exc:  # noqa: BLE001
             gl = {"error": repr(exc)}
+    if world == 1:
         if not args.no_cpu_baseline:
             r = time_reference_clip(cores)
-            per_clip = n_evals * r["t_unet_cfg_eval_s"] * (1 + VAE_DEC_TFLOP / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE)) + r["t_audio_s"]
+            vae_tf = VAE_DEC_TFLOP + (VAE_ENC_TFLOP if roundtrip else 0.0)
+            per_clip = n_evals * r["t_unet_cfg_eval_s"] * (1 + vae_tf / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE)) + r["t_audio_s"]
             cpu_baseline = {"value": 1.0 / per_clip, "unit": "clips/s", "cores": r["threads"], "kind": "port",
                             "sample": f"1 CFG UNet evaluation ({r['t_unet_cfg_eval_s']:.1f} s, torch-eager fp32 restatement, "
                                       f"{r['threads']} threads) extrapolated to {n_evals} evals + VAE decode at the same FLOP rate, plus 1 clip of "
                                       f"torchaudio inverse-mel + Griffin-Lim ({r['t_audio_s']:.1f} s, {r['audio_threads']} threads); host has {cores} cores"}
-    config = clip_config(n_steps, n_evals, B)
+    config = clip_config(n_steps, n_evals, B, args.workload)
     line = {
         "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -679,6 +713,178 @@ def main_clip(args) -> None:
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+class _BenchTokenizer:
+    """whitespace tokenizer stand-in (no CLIP vocabulary files offline); ids feed the random-init text encoder"""
+    model_max_length = 77
+    bos_token_id = 49406
+    eos_token_id = 49407
+
+    def __call__(self, text, padding=None, max_length=None, truncation=False, return_tensors=None):
+        import types
+        import zlib
+
+        single = isinstance(text, str)
+        rows = []
+        for t in ([text] if single else text):
+            ids = [self.bos_token_id] + [1 + zlib.crc32(w.lower().encode()) % 49000 for w in t.split()] + [self.eos_token_id]
+            if truncation and max_length and len(ids) > max_length:
+                ids = ids[: max_length - 1] + [self.eos_token_id]
+            if padding == "max_length":
+                ids = ids + [self.eos_token_id] * (max_length - len(ids))
+            rows.append(ids)
+        if return_tensors == "pt":
+            return types.SimpleNamespace(input_ids=torch.tensor(rows, dtype=torch.long))
+        return types.SimpleNamespace(input_ids=rows[0] if single else rows)
+
+
+def main_riffuse(args) -> None:
+    """BASELINE configs[2]: one request through RiffusionPipeline.riffuse() — PIL seed image in, PIL image out, alpha 0.5,
+    50 scheduler steps; `--denoising 0.75` (the reference default: 38 CFG evaluations) or 1.0 (50).  Each rank serves its own
+    request (weak scaling).  value = requests/s with the seed image's VAE moments cached and latents resident (the loop +
+    decode + uint8); e2e = riffuse() itself, PIL -> PIL (host image in, VAE encode on a cache miss excluded by the moment
+    cache exactly as in serving, uint8 image back to the host)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from PIL import Image
+
+    from riffusion import _native, sd15_spec
+    from riffusion.clip_b200 import ClipTextB200
+    from riffusion.datatypes import InferenceInput, PromptInput
+    from riffusion.riffusion_pipeline import RiffusionPipeline
+    from riffusion.unet_b200 import UNetB200
+    from riffusion.vae_b200 import VaeB200
+
+    lib = _native.lib()
+    unet_sd, vae_sd = load_frozen_weights(rank, dist, dev)
+    text_encoder = ClipTextB200.random_init(seed=2, device=str(dev))
+    pipe = RiffusionPipeline(vae=VaeB200(vae_sd, device=str(dev)), unet=UNetB200(unet_sd, device=str(dev)),
+                             text_encoder=text_encoder, tokenizer=_BenchTokenizer(), device=str(dev))
+    del unet_sd, vae_sd
+    rgb = np.load(ROOT / "tests" / "golden" / "og_beat.npz")["rgb"]
+    init_image = Image.fromarray(rgb, mode="RGB")
+    n_steps = args.evals
+    n_evals = n_evals_for(n_steps, args.denoising)
+
+    def request(i: int) -> InferenceInput:
+        return InferenceInput(alpha=0.5, num_inference_steps=n_steps, seed_image_id="og_beat",
+                              start=PromptInput(prompt="church bells on sunday", seed=42 + i + 1000 * rank, denoising=args.denoising),
+                              end=PromptInput(prompt="jazz with piano", seed=123 + i + 1000 * rank, denoising=args.denoising))
+
+    stream = torch.cuda.current_stream(dev)
+    counter = [0]
+
+    def step_e2e():
+        counter[0] += 1
+        return pipe.riffuse(request(counter[0]), init_image)
+
+    # device-resident variant: embeddings + latents prepared once, the timed part is loop + decode + uint8 on the device
+    inp = request(0)
+    e0, e1 = pipe.embed_text_weighted(inp.start.prompt), pipe.embed_text_weighted(inp.end.prompt)
+    text = (e0 + 0.5 * (e1 - e0)).half()
+    lat0 = pipe.encode_image(init_image, torch.Generator(device=dev).manual_seed(42))
+    noise0 = torch.randn(lat0.shape, generator=torch.Generator(device=dev).manual_seed(7), device=dev, dtype=torch.float16)
+    uncond = pipe.embed_text("").half()
+
+    def step_device():
+        from riffusion import tc_ops
+
+        out = pipe.interpolate_img2img(text_embeddings=text, init_latents=lat0, generator_a=None, generator_b=None,
+                                       interpolate_alpha=0.0, strength_a=args.denoising, strength_b=args.denoising,
+                                       num_inference_steps=n_steps, guidance_scale=7.0, uncond_embeddings=uncond, noise=noise0,
+                                       output_type="latent")
+        return tc_ops.vae_image_to_u8(pipe.vae.decode(out["latents"]).sample), out["n_unet_evals"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record(stream)
+        for _ in range(steps):
+            fn()
+        e1_.record(stream)
+        barrier()
+        ms = torch.tensor([e0_.elapsed_time(e1_)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        _, got_evals = step_device()
+    assert got_evals == n_evals, (got_evals, n_evals)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    pipe.use_cuda_graph = False
+    step_device()
+    lib.rf_tc_profile_begin()
+    step_device()
+    tc_ms, tc_fl, tc_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_long()
+    lib.rf_tc_profile_end(ctypes.byref(tc_ms), ctypes.byref(tc_fl), ctypes.byref(tc_n))
+    pipe.use_cuda_graph = True
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms_step, ms_e2e_step = ms_total / args.steps, ms_e2e / args.steps
+    pk = tensor_peaks()
+    achieved = tc_fl.value / (tc_ms.value / 1e3) / 1e12
+    alg = n_evals * 2 * UNET_TFLOP_PER_SAMPLE + VAE_DEC_TFLOP
+    roofline = {"bound": "tensor", "kernel": "k_tc_gemm (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved,
+                "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "traffic": gemm_traffic(),
+                "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "kernel_ms_per_step": tc_ms.value,
+                "kernel_launches_per_step": tc_n.value, "kernel_share_of_step": tc_ms.value / ms_step,
+                "note": "batch 2 (one CFG pair): sub-wave problems, split-K on the 8x8 / 16x16 levels",
+                "step": {"algorithmic_tflop": alg, "achieved": alg / (ms_step / 1e3), "frac": alg / (ms_step / 1e3) / pk["sustained"],
+                         "unit": "TFLOP/s"}}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_reference_clip(os.cpu_count() or 1)
+        per = n_evals * r["t_unet_cfg_eval_s"] * (1 + (VAE_DEC_TFLOP + VAE_ENC_TFLOP) / (n_evals * 2 * UNET_TFLOP_PER_SAMPLE))
+        cpu_baseline = {"value": 1.0 / per, "unit": "clips/s", "cores": r["threads"], "kind": "port",
+                        "sample": f"1 CFG UNet evaluation ({r['t_unet_cfg_eval_s']:.1f} s, torch-eager fp32 restatement, {r['threads']} "
+                                  f"threads) extrapolated to {n_evals} evals + VAE encode + decode at the same FLOP rate"}
+    line = {"metric": "clips/sec", "value": world / (ms_step / 1e3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_step, "latency_ms": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": clip_config(n_steps, n_evals, 1, "riffuse", args.denoising), "clocks": clocks,
+            "e2e": {"value": world / (ms_e2e_step / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e_step, "latency_ms": ms_e2e_step,
+                    "h2d_bytes_per_step": int(rgb.size + 2 * 77 * 4), "d2h_bytes_per_step": int(512 * 512 * 3),
+                    "api": "RiffusionPipeline.riffuse(InferenceInput, PIL.Image) -> PIL.Image (tokenise + CLIP text encoder "
+                           "(lru-cached per prompt), cached VAE moments of the seed image, generator draws, loop, decode, uint8)"},
+            "gpu_launches": int(args.steps * (n_evals * 600 + 250)), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def gemm_traffic():
+    """ncu dram__bytes of the tensor-core kernel (profiles/traffic_latest.json, written from the committed ncu capture)"""
+    f = ROOT / "profiles" / "traffic_latest.json"
+    try:
+        return json.loads(f.read_text()).get("k_tc_gemm")
+    except (OSError, ValueError):
+        return None
 
 
 if __name__ == "__main__":

@@ -170,7 +170,7 @@ typedef struct rf_gemm_desc {
     const void* residual;      /* fp16, indexed like D with ldr/sr1/sr2, or NULL */
     int64_t ldr, sr1, sr2;
     float alpha;               /* 0 is treated as 1 */
-    int32_t act;               /* 0 none, 1 SiLU, 2 GEGLU: B rows come in runs of [16 value | 16 gate] rows of the
+    int32_t act;               /* 0 none, 1 SiLU, 3 quick_gelu x*sigmoid(1.702x), 2 GEGLU: B rows come in runs of [16 value | 16 gate] rows of the
                                   same 16 outputs, D has N/2 columns, D[m][16 r + j] = v_j * gelu(g_j) (exact erf) */
     int32_t out_f32;           /* 1: D is fp32 */
 } rf_gemm_desc;
@@ -205,6 +205,12 @@ int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
  * fp16, d a multiple of 8 and <= 192, vt_pitch a multiple of 8 >= Nk. */
 int rf_attention_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Nq, int Nk,
                      int d, int vt_pitch, float scale, void* stream);
+
+/* Same with an optional causal mask (key j visible to query i iff j <= i): transformers CLIPTextModel's self-attention
+ * (causal_attention_mask), the text encoder behind RiffusionPipeline.embed_text (riffusion/riffusion_pipeline.py:177-191).
+ * causal != 0 requires Nk <= 128 and d <= 112. */
+int rf_attention_masked_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Nq, int Nk,
+                            int d, int vt_pitch, float scale, int causal, void* stream);
 
 /* Measurement aid (bench.py roofline): between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed by
  * CUDA events on its stream; end synchronises the device and returns the summed kernel time (ms), the algorithmic

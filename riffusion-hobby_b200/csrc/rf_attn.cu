@@ -38,6 +38,7 @@ struct AttnParams {
     float c;              // scale * log2(e)
     __half* out;          // [B][Nq][C]
     long out_pitch;       // C
+    int causal;           // 1: key j is visible to query i only if j <= i (CLIP text encoder); short-key kernel only
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -881,9 +882,10 @@ k_attn_short(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
             tc::tmem_wait_ld();
             tc::fence_before_sync();
             tc::mbar_arrive(&s_empty[i]);
+            const int kmax = p.causal ? min(p.Nk, ((w0 + n) % nqb) * TQ + row + 1) : p.Nk;   // causal: keys 0 .. query index
 #pragma unroll
             for (int e = 0; e < 128; ++e)
-                if (e >= p.Nk) v[e] = 0xff800000u;
+                if (e >= kmax) v[e] = 0xff800000u;
             float mx[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) mx[e] = __uint_as_float(v[e]);
@@ -1028,6 +1030,14 @@ int launch_attn_short(const CUtensorMap& mq, const CUtensorMap& mk, const CUtens
 // q: [B][Nq][heads*d], k: [B][Nk][heads*d], vt: [B][heads*d][vt_pitch] (V transposed), out: [B][Nq][heads*d]; fp16.
 extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Nq, int Nk,
                                 int d, int vt_pitch, float scale, void* stream) {
+    return rf_attention_masked_f16(q, k, vt, out, B, heads, Nq, Nk, d, vt_pitch, scale, 0, stream);
+}
+
+extern "C" int rf_attention_masked_f16(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Nq,
+                                       int Nk, int d, int vt_pitch, float scale, int causal, void* stream) {
+    if (causal && (Nk > TK || d > 112))
+        return rf_fail(RF_ERR_UNSUPPORTED, "rf_attention_masked_f16: the causal mask is implemented for Nk <= 128, d <= 112 "
+                                           "(the 77-token text encoder)");
     if (!q || !k || !vt || !out || B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0 || d <= 0 || (d % 8) || vt_pitch < Nk ||
         (vt_pitch % 8))
         return rf_fail(RF_ERR_INVALID, "rf_attention_f16: bad argument");
@@ -1069,10 +1079,11 @@ extern "C" int rf_attention_f16(const void* q, const void* k, const void* vt, vo
     p.c = scale * 1.4426950408889634f;
     p.out = static_cast<__half*>(out);
     p.out_pitch = C;
+    p.causal = causal ? 1 : 0;
     dim3 grid((Nq + TQ - 1) / TQ, heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool no_short = getenv("RF_ATTN_NO_SHORT") != nullptr;
-    if (one_pass && Nk <= TK && !no_short) {     // one key tile: persistent kernel (cross-attention to the text tokens)
+    if (one_pass && Nk <= TK && (!no_short || causal)) {     // one key tile: persistent kernel (cross-attention to the text tokens)
         if (d <= 48) return launch_attn_short<64, 48>(mq, mk, mv, p, B, st);
         if (d <= 64) return launch_attn_short<64, 64>(mq, mk, mv, p, B, st);
         if (d <= 80) return launch_attn_short<128, 80>(mq, mk, mv, p, B, st);

@@ -76,6 +76,7 @@ struct TcParams {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return __fdividef(v, 1.f + __expf(-v));
+    if (act == 3) return __fdividef(v, 1.f + __expf(-1.702f * v));     // quick_gelu (CLIP text encoder MLP)
     return v;
 }
 
@@ -621,7 +622,7 @@ __global__ void k_splitk_reduce(const float* __restrict__ ws, int splits, long s
             float v = f[e] * alpha + brow;
             if (bias_mode == 1) v += __half2float(bias[n0 + e]);
             if (bias2) v += __half2float(bias2[(r / rows_per_image) * bias2_pitch + n0 + e]);
-            if (act == 1) v = apply_act(v, 1);
+            if (act == 1 || act == 3) v = apply_act(v, act);
             if (residual) v += __half2float(residual[r * ldr + n0 + e]);
             f[e] = v;
         }

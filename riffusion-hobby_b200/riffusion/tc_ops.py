@@ -12,7 +12,7 @@ import torch
 
 from riffusion import _native
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_QUICK_GELU = 0, 1, 2, 3
 
 
 def _f16(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -316,16 +316,17 @@ def conv1x1_small(x_nchw: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, in_
     return y
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, heads: int, nk: int) -> torch.Tensor:
-    """q: (B, Nq, C), k: (B, >=nk, C), vt: (B, C, pitch>=nk) fp16 contiguous -> (B, Nq, C); fused tcgen05 kernel."""
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, heads: int, nk: int, causal: bool = False) -> torch.Tensor:
+    """q: (B, Nq, C), k: (B, >=nk, C), vt: (B, C, pitch>=nk) fp16 contiguous -> (B, Nq, C); fused tcgen05 kernel.
+    causal: key j is visible to query i iff j <= i (text encoder; nk <= 128)."""
     _f16(q, "q"), _f16(k, "k"), _f16(vt, "vt")
     B, Nq, C = q.shape
     d = C // heads
     assert q.is_contiguous() and k.is_contiguous() and vt.is_contiguous() and k.shape[1] == nk
     out = torch.empty_like(q)
     with torch.cuda.device(q.device):
-        _native.check(_native.lib().rf_attention_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Nq,
-                                                     nk, d, vt.shape[-1], float(d) ** -0.5, _stream(q)))
+        _native.check(_native.lib().rf_attention_masked_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads,
+                                                            Nq, nk, d, vt.shape[-1], float(d) ** -0.5, int(causal), _stream(q)))
     return out
 
 
