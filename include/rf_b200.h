@@ -173,8 +173,11 @@ typedef struct rf_gemm_desc {
     int32_t act;               /* 0 none, 1 SiLU, 3 quick_gelu x*sigmoid(1.702x), 2 GEGLU: B rows come in runs of [16 value | 16 gate] rows of the
                                   same 16 outputs, D has N/2 columns, D[m][16 r + j] = v_j * gelu(g_j) (exact erf) */
     int32_t out_f32;           /* 1: D is fp32 */
+    void* workspace;           /* optional device scratch for split-K (problems with fewer tiles than SMs); NULL: never split */
+    int64_t workspace_bytes;   /* its size; rf_gemm_workspace_bytes(desc) returns what this problem would use (0: none) */
 } rf_gemm_desc;
 int rf_gemm_f16(const rf_gemm_desc* desc, void* stream);
+size_t rf_gemm_workspace_bytes(const rf_gemm_desc* desc);
 
 /* torch.nn.Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2) as an implicit GEMM over NHWC input;
  * the input may be the channel concatenation of two tensors (UNet skip connections,
@@ -195,9 +198,15 @@ typedef struct rf_conv_desc {
     int32_t bias_per_image_pitch; /* row pitch (elements) of bias_per_image; 0 = Cout */
     int32_t pad_mode;          /* 0: symmetric padding ksize/2 (torch padding=1 for 3x3);
                                   1: no left/top padding, implicit zero padding on the right/bottom edge
-                                     (diffusers VAE Downsample2D: F.pad(x, (0,1,0,1)) then conv padding=0) */
+                                     (diffusers VAE Downsample2D: F.pad(x, (0,1,0,1)) then conv padding=0)
+                                  2: nearest-2x upsample fused in (diffusers Upsample2D: F.interpolate(scale 2, nearest) then
+                                     conv 3x3 pad 1): ksize = 2, w = the four sub-pixel phase kernels [4][Cout][2][2][C1]
+                                     (3x3 taps that land on the same input pixel pre-summed), out is [B][2H][2W][Cout] */
+    void* workspace;           /* optional split-K scratch, as in rf_gemm_desc */
+    int64_t workspace_bytes;
 } rf_conv_desc;
 int rf_conv2d_f16(const rf_conv_desc* desc, void* stream);
+size_t rf_conv2d_workspace_bytes(const rf_conv_desc* desc);
 
 /* Fused attention softmax(Q K^T * scale) V per (image, head) — diffusers CrossAttention's baddbmm/softmax/bmm
  * [restated from memory] without materialising the scores.  q [B][Nq][heads*d], k [B][Nk][heads*d],

@@ -641,13 +641,8 @@ __global__ void k_splitk_reduce(const float* __restrict__ ws, int splits, long s
     }
 }
 
-// Split-K workspace: one lazily grown device buffer per process (allocated outside stream capture: the eager warm-up
-// evaluation that precedes every graph capture sizes it).
-struct SplitWs {
-    float* ptr = nullptr;
-    size_t bytes = 0;
-};
-SplitWs g_ws;
+// Split-K workspace: caller-provided scratch (desc.workspace / workspace_bytes, sized by rf_*_workspace_bytes) — the
+// library keeps no mutable state, so concurrent calls on different streams are safe.  Without it split-K is not used.
 constexpr size_t SPLIT_WS_MAX = static_cast<size_t>(192) << 20;
 
 // Number of K splits: a problem with fewer tiles than SMs leaves SMs idle AND streams its weights through too few
@@ -751,11 +746,15 @@ TileCfg pick_cfg(int N, long tiles_m, int nbatch, int num_kb) {
 int b_box_rows(const TileCfg& c) { return !c.pair ? c.bn : (c.bn == 320 ? 80 : c.bn / 2); }
 
 int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
-             int tiles_m, int nbatch, cudaStream_t st) {
+             int tiles_m, int nbatch, cudaStream_t st, void* ws, size_t ws_bytes, size_t* query) {
     // one persistent CTA (or CTA pair) per SM (TPC): 6-8 stage TMA ring, 2 TMEM accumulators
     const int bn = cfg.bn;
     p.tiles_n = (N + bn - 1) / bn;
     if (cfg.pair) {
+        if (query) {
+            *query = 0;
+            return RF_OK;
+        }
         p.tiles_m = (tiles_m + 1) / 2;          // 256-row blocks
         p.splits = 1;
         p.kb_per_split = p.num_kb;
@@ -778,18 +777,20 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
     p.ws_split_stride = rows * N;
     if (p.splits > 1) {
         const size_t need = static_cast<size_t>(p.splits) * rows * N * sizeof(float);
-        if (g_ws.bytes < need) {
-            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-            cudaStreamIsCapturing(st, &cs);
-            if (cs != cudaStreamCaptureStatusNone)
-                return rf_fail(RF_ERR_CUDA, "split-K workspace must be sized by an eager run before stream capture");
-            if (g_ws.ptr) RF_CUDA_TRY(cudaFree(g_ws.ptr));
-            g_ws.ptr = nullptr;
-            g_ws.bytes = 0;
-            RF_CUDA_TRY(cudaMalloc(&g_ws.ptr, need));
-            g_ws.bytes = need;
+        if (query) {
+            *query = need;
+            return RF_OK;
         }
-        p.ws = g_ws.ptr;
+        if (!ws || ws_bytes < need) {          // no (or too small a) workspace: the un-split kernel is always correct
+            p.splits = 1;
+            p.kb_per_split = p.num_kb;
+        } else {
+            p.ws = static_cast<float*>(ws);
+        }
+    }
+    if (query) {
+        *query = 0;
+        return RF_OK;
     }
     dim3 grid(p.tiles_n * p.splits, tiles_m, nbatch);
     int rc;
@@ -813,7 +814,7 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
 }  // namespace
 
 // ------------------------------------------------------------------------------ C-ABI
-extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
+static int gemm_impl(const rf_gemm_desc* d, void* stream, size_t* query) {
     if (!d || !d->A || !d->B || !d->D || d->M <= 0 || d->N <= 0 || d->K <= 0)
         return rf_fail(RF_ERR_INVALID, "rf_gemm_f16: bad argument");
     const int b1 = d->batch1 > 0 ? d->batch1 : 1, b2 = d->batch2 > 0 ? d->batch2 : 1;
@@ -858,10 +859,17 @@ extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) {
                         (reinterpret_cast<uintptr_t>(d->D) & 15)))
         return rf_fail(RF_ERR_UNSUPPORTED, "rf_gemm_f16: GEGLU epilogue needs N % 32 == 0, fp16 output with 16-byte "
                                            "aligned rows and no residual");
-    return dispatch(d->N, cfg, ma, ma, mb, p, (d->M + BM - 1) / BM, b1 * b2, static_cast<cudaStream_t>(stream));
+    return dispatch(d->N, cfg, ma, ma, mb, p, (d->M + BM - 1) / BM, b1 * b2, static_cast<cudaStream_t>(stream), d->workspace,
+                    d->workspace_bytes > 0 ? static_cast<size_t>(d->workspace_bytes) : 0, query);
 }
 
-extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
+extern "C" int rf_gemm_f16(const rf_gemm_desc* d, void* stream) { return gemm_impl(d, stream, nullptr); }
+extern "C" size_t rf_gemm_workspace_bytes(const rf_gemm_desc* d) {
+    size_t need = 0;
+    return gemm_impl(d, nullptr, &need) == RF_OK ? need : 0;
+}
+
+static int conv_impl(const rf_conv_desc* d, void* stream, size_t* query) {
     if (!d || !d->x1 || !d->w || !d->out || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C1 <= 0 || d->Cout <= 0)
         return rf_fail(RF_ERR_INVALID, "rf_conv2d_f16: bad argument");
     const bool up2 = d->pad_mode == 2;      // nearest-2x upsample fused in: four 2x2 sub-pixel convolutions
@@ -941,7 +949,10 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
     p.residual = static_cast<const __half*>(d->residual);
     p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.act = d->act;
-    if (!up2) return dispatch(d->Cout, cfg, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
+    void* ws = d->workspace;
+    const size_t ws_bytes = d->workspace_bytes > 0 ? static_cast<size_t>(d->workspace_bytes) : 0;
+    if (!up2) return dispatch(d->Cout, cfg, m1, m2, mb, p, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream), ws,
+                              ws_bytes, query);
     // conv3x3(pad 1) of the nearest-2x upsampled image == four 2x2 convolutions of the input, one per output parity
     // (py, px): output (2y + py, 2x + px) reads input rows y + py - 1 + {0, 1} and columns x + px - 1 + {0, 1}; the 3x3 taps
     // that fall on the same input pixel are pre-summed in the phase weights w[phase][Cout][2][2][Cin] (9 -> 4 taps: 2.25x
@@ -959,10 +970,17 @@ extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) {
         int rc = make_map(&mph, static_cast<const __half*>(d->w) + static_cast<long>(ph) * d->Cout * Ktot, dims, str, box, es);
         if (rc) return rc;
         TcParams q = p;
-        rc = dispatch(d->Cout, cfg, m1, m2, mph, q, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream));
-        if (rc) return rc;
+        rc = dispatch(d->Cout, cfg, m1, m2, mph, q, p.tiles_x * p.tiles_y * tiles_b, 1, static_cast<cudaStream_t>(stream), nullptr, 0,
+                      query);      // strided outputs: never split
+        if (rc || query) return rc;
     }
     return RF_OK;
+}
+
+extern "C" int rf_conv2d_f16(const rf_conv_desc* d, void* stream) { return conv_impl(d, stream, nullptr); }
+extern "C" size_t rf_conv2d_workspace_bytes(const rf_conv_desc* d) {
+    size_t need = 0;
+    return conv_impl(d, nullptr, &need) == RF_OK ? need : 0;
 }
 
 // Live measurement aid for bench.py: between begin and end every rf_gemm_f16 / rf_conv2d_f16 launch is bracketed

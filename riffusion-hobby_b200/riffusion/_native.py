@@ -46,6 +46,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p), ("bias_mode", C.c_int32),
         ("residual", C.c_void_p), ("ldr", C.c_int64), ("sr1", C.c_int64), ("sr2", C.c_int64),
         ("alpha", C.c_float), ("act", C.c_int32), ("out_f32", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -56,6 +57,7 @@ class ConvDesc(C.Structure):
         ("x1", C.c_void_p), ("x2", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
         ("bias_per_image", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("alpha", C.c_float), ("act", C.c_int32), ("bias_per_image_pitch", C.c_int32), ("pad_mode", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -93,6 +95,8 @@ SIGNATURES = {
     "rf_mel_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rf_gemm_f16": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "rf_conv2d_f16": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "rf_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmDesc)]),
+    "rf_conv2d_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "rf_group_norm_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rf_group_norm_f16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -25,6 +25,16 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _workspace(nbytes: int, desc, device) -> T.Optional[torch.Tensor]:
+    """split-K scratch of one call, from torch's caching allocator (stream-ordered, CUDA-graph safe): the library itself
+    keeps no device state, so calls on different streams never share it"""
+    if not nbytes:
+        return None
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    desc.workspace, desc.workspace_bytes = ws.data_ptr(), int(nbytes)
+    return ws
+
+
 def gemm(
     a: torch.Tensor, b: torch.Tensor, *, bias: T.Optional[torch.Tensor] = None, bias_per_row: bool = False,
     residual: T.Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = ACT_NONE,
@@ -67,7 +77,9 @@ def gemm(
         d.residual, d.ldr, d.sr1, d.sr2 = r4.data_ptr(), r4.stride(2), r4.stride(1), r4.stride(0)
     d.alpha, d.act, d.out_f32 = float(alpha), int(act), int(o4.dtype == torch.float32)
     with torch.cuda.device(a.device):
+        ws = _workspace(_native.lib().rf_gemm_workspace_bytes(C.byref(d)), d, a.device)     # keeps the scratch alive
         _native.check(_native.lib().rf_gemm_f16(C.byref(d), _stream(a)))
+    del ws
     return out
 
 
@@ -119,7 +131,9 @@ def conv2d(
         d.residual = _f16(residual, "residual").data_ptr()
     d.out, d.alpha, d.act, d.pad_mode = out.data_ptr(), 1.0, int(act), int(pad_far_edge_only)
     with torch.cuda.device(x.device):
+        ws = _workspace(_native.lib().rf_conv2d_workspace_bytes(C.byref(d)), d, x.device)
         _native.check(_native.lib().rf_conv2d_f16(C.byref(d), _stream(x)))
+    del ws
     return out
 
 

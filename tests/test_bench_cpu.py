@@ -36,3 +36,22 @@ def test_reference_arm_other_ranks_print_nothing(monkeypatch):
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_workload_configs_and_eval_counts():
+    """the img2img start-point arithmetic bench.py extrapolates with equals the reference's (riffusion_pipeline.py:358-396,
+    SURVEY Appendix B: 38 evaluations at denoising 0.75, 50 at 1.0, 26 at 0.5) and the product scheduler's"""
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "riffusion-hobby_b200"))
+    import bench
+    from riffusion.scheduler_b200 import PNDMSchedulerB200
+
+    assert [bench.n_evals_for(50, s) for s in (0.75, 1.0, 0.5)] == [38, 50, 26]
+    sch = PNDMSchedulerB200()
+    for steps, s in ((50, 0.75), (50, 1.0), (20, 0.7499999999999999), (8, 1.0)):
+        sch.set_timesteps(steps)
+        init = min(int(steps * s) + 1, steps)
+        assert bench.n_evals_for(steps, s) == len(sch.timesteps[max(steps - init + 1, 0):])
+    rt = bench.clip_config(50, 50, 16, "roundtrip")
+    rf = bench.clip_config(50, 38, 1, "riffuse", 0.75)
+    assert "configs[4]" in rt["workload"] and "configs[2]" in rf["workload"] and rt["clips_per_gpu"] == 16
