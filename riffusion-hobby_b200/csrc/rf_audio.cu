@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "rf_common.h"
+#include "rf_generic.cuh"
 #include "rf_gl_phases.cuh"
 #include "rf_plan.h"
 
@@ -50,6 +51,9 @@ struct rf_plan {
     rf_c32* d_wt2_inv = nullptr;
     uint32_t* d_pp2 = nullptr;
     rf_c32* d_ph_odd = nullptr;
+    float* d_window = nullptr;    // generic engine
+    rf_c32* d_roots2 = nullptr;
+    rf_c32* d_rootsN = nullptr;
     bool use_decimation = true;
     std::vector<void*> owned;
 };
@@ -114,6 +118,11 @@ static int rf_plan_upload(rf_plan* p) {
         RF_CUDA_TRY(upload(p, &p->d_wt2_inv, h.wt2_inv.data(), h.wt2_inv.size() / 2));
         RF_CUDA_TRY(upload(p, &p->d_pp2, h.pp2.data(), h.pp2.size()));
         RF_CUDA_TRY(upload(p, &p->d_ph_odd, h.ph_odd.data(), h.ph_odd.size() / 2));
+    }
+    if (h.generic) {
+        RF_CUDA_TRY(upload(p, &p->d_window, h.window.data(), h.window.size()));
+        RF_CUDA_TRY(upload(p, &p->d_roots2, h.roots2.data(), h.roots2.size() / 2));
+        RF_CUDA_TRY(upload(p, &p->d_rootsN, h.rootsN.data(), h.rootsN.size() / 2));
     }
     p->device = dev;
     p->uploaded = true;
@@ -626,6 +635,33 @@ static rf_gl_tables make_tables(const rf_plan* p, int NA = 10) {
     return tb;
 }
 
+static rf_gen_tab make_gen_tab(const rf_plan* p) {
+    rf_gen_tab g{};
+    g.roots2 = p->d_roots2;
+    g.rootsN = p->d_rootsN;
+    g.window = p->d_window;
+    g.bins = p->d_bins;
+    g.N = p->h.N;
+    g.N2 = p->h.N / 2;
+    g.W = p->h.W;
+    g.H = p->h.H;
+    g.lo = (p->h.N - p->h.W) / 2;
+    g.J = p->h.n_live;
+    g.nrad = static_cast<int>(p->h.radices.size());
+    for (int i = 0; i < g.nrad; ++i) g.rad[i] = p->h.radices[i];
+    return g;
+}
+static size_t gen_smem(const rf_plan* p) { return (2 * static_cast<size_t>(p->h.N / 2) + 2) * sizeof(rf_c32); }
+static int gen_smem_attrs(const rf_plan* p) {
+    static rf_dev_once once[2];
+    const int bytes = static_cast<int>(gen_smem(p));
+    if (bytes > 227 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "generic FFT engine: n_fft too large for shared memory");
+    cudaError_t err = rf_set_smem_once(once[0], k_gen_stft, 227 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[1], k_gen_istft, 227 * 1024);
+    if (err != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+    return RF_OK;
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 struct gl_ws {
@@ -653,7 +689,8 @@ static gl_ws gl_layout(const rf_plan* p, int B, int T, void* base) {
     w.R[1] = reinterpret_cast<rf_c32*>(b + off);
     off += align256(bt * 8);
     w.part = reinterpret_cast<float*>(b + off);
-    off += align256(static_cast<size_t>(B) * 2 * w.nchunks * w.PL * 4);
+    if (p->h.generic) off += align256(static_cast<size_t>(B) * T * p->h.W * 4);      // windowed frames [B][T][W]
+    else off += align256(static_cast<size_t>(B) * 2 * w.nchunks * w.PL * 4);
     w.env = reinterpret_cast<float*>(b + off);
     off += align256(static_cast<size_t>(p->h.H) * (T > 0 ? T - 1 : 0) * 4);
     w.part_e = w.xd = nullptr;
@@ -719,9 +756,36 @@ struct gl_prof {
 };
 
 // Griffin-Lim main loop on a prepared workspace (S and initial angles in R[1]).
+// Griffin-Lim on the generic engine: same recurrence and buffer rotation as below, one CTA per frame
+static int gl_loop_generic(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float momentum_in, float* d_wave,
+                           cudaStream_t st) {
+    const rf_plan_host& h = p->h;
+    int rc = gen_smem_attrs(p);
+    if (rc) return rc;
+    const rf_gen_tab g = make_gen_tab(p);
+    const size_t smem = gen_smem(p);
+    const int L = h.H * (T - 1);
+    const int c0 = h.N / 2 - (h.N - h.W) / 2;
+    const float m = static_cast<float>(static_cast<double>(momentum_in) / (1.0 + static_cast<double>(momentum_in)));
+    const dim3 grid_f(T, B), grid_a((L + 255) / 256, B);
+    for (int it = 0; it <= n_iter; ++it) {
+        const rf_c32* cur = it == 0 ? w.R[1] : w.R[(it - 1) & 1];
+        const rf_c32* prev = (it >= 2 && m != 0.f) ? w.R[it & 1] : nullptr;
+        k_gen_istft<<<grid_f, 256, smem, st>>>(g, w.S, cur, prev, it == 0 ? 0 : 1, m, T, w.part);
+        RF_CUDA_LAUNCH_CHECK("k_gen_istft");
+        k_gen_ola<<<grid_a, 256, 0, st>>>(w.part, p->d_win2, T, h.H, h.W, c0, L, d_wave);
+        RF_CUDA_LAUNCH_CHECK("k_gen_ola");
+        if (it == n_iter) break;
+        k_gen_stft<<<grid_f, 256, smem, st>>>(g, d_wave, L, T, w.R[it & 1]);
+        RF_CUDA_LAUNCH_CHECK("k_gen_stft");
+    }
+    return RF_OK;
+}
+
 static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float momentum_in, float* d_wave,
                    cudaStream_t st, gl_prof* prof = nullptr) {
     const rf_plan_host& h = p->h;
+    if (h.generic) return gl_loop_generic(p, w, B, T, n_iter, momentum_in, d_wave, st);
     const rf_gl_tables tb = make_tables(p, 10);
     const int L = h.H * (T - 1);
     // momentum = momentum / (1 + momentum)  (TA/functional/functional.py:300), fp32 like python float->tensor op
@@ -903,6 +967,19 @@ extern "C" int rf_stft_mel(rf_plan* p, const float* d_wave, int B, int L, float*
     if ((rc = set_smem_attrs())) return rc;
     const rf_plan_host& h = p->h;
     const int T = 1 + L / h.H;
+    if (h.generic) {
+        if ((rc = gen_smem_attrs(p))) return rc;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        rf_c32* tmp = nullptr;
+        RF_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), static_cast<size_t>(B) * T * h.n_live * 8, st));
+        k_gen_stft<<<dim3(T, B), 256, gen_smem(p), st>>>(make_gen_tab(p), d_wave, L, T, tmp);
+        RF_CUDA_LAUNCH_CHECK("k_gen_stft");
+        k_gen_mel_from_TJ<<<dim3((T + 127) / 128, h.n_mels, B), 128, 0, st>>>(tmp, T, h.n_live, h.n_mels, p->d_melcol_ptr,
+                                                                             p->d_melcol_j, p->d_melcol_w, d_mel);
+        RF_CUDA_LAUNCH_CHECK("k_gen_mel_from_TJ");
+        RF_CUDA_TRY(cudaFreeAsync(tmp, st));
+        return RF_OK;
+    }
     const size_t xs_n = (RF_PW + h.H) + ((RF_PW + h.H) & 1);
     const size_t smem = 2 * RF_PW * sizeof(rf_c32) + xs_n * 4 + 2 * static_cast<size_t>(h.n_live) * 8;
     if (smem > 227 * 1024) return rf_fail(RF_ERR_UNSUPPORTED, "rf_stft_mel: live band too wide for the fused kernel");
@@ -926,10 +1003,16 @@ extern "C" int rf_stft(rf_plan* p, const float* d_wave, int B, int L, void* d_sp
     rf_c32* tmp = nullptr;
     const size_t n = static_cast<size_t>(B) * T * h.n_live;
     RF_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), n * 8, st));
-    const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
-    dim3 grid_f(((T + 1) / 2) * 2, B);
-    k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(make_tables(p), d_wave, L, T, h.H, tmp);
-    RF_CUDA_LAUNCH_CHECK("k_stft_pair");
+    if (h.generic) {
+        if ((rc = gen_smem_attrs(p))) return rc;
+        k_gen_stft<<<dim3(T, B), 256, gen_smem(p), st>>>(make_gen_tab(p), d_wave, L, T, tmp);
+        RF_CUDA_LAUNCH_CHECK("k_gen_stft");
+    } else {
+        const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
+        dim3 grid_f(((T + 1) / 2) * 2, B);
+        k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(make_tables(p), d_wave, L, T, h.H, tmp);
+        RF_CUDA_LAUNCH_CHECK("k_stft_pair");
+    }
     RF_CUDA_TRY(cudaMemsetAsync(d_spec, 0, static_cast<size_t>(B) * h.F * T * 8, st));
     dim3 grid((h.n_live + 31) / 32, (T + 31) / 32, B), blk(32, 32);
     k_scatter_TJ_to_FT<float2><<<grid, blk, 0, st>>>(reinterpret_cast<const float2*>(tmp), p->d_bins, h.F, T,

@@ -88,12 +88,28 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
     if (d.win_length > d.n_fft) return "rf_plan_create: win_length > n_fft";
     if (d.f_min > d.f_max) return "Require f_min <= f_max";  // TA/transforms/_transforms.py:473
     code = RF_ERR_UNSUPPORTED;
-    if (d.win_length != RF_W || d.n_fft != RF_N)
-        return "rf_plan_create: this build only has the 4410-point prime-factor FFT engine "
-               "(win_length=4410, n_fft=17640: 44.1 kHz / 100 ms window / 400 ms padded); got "
-               "win_length=" + std::to_string(d.win_length) + " n_fft=" + std::to_string(d.n_fft);
-    if (d.hop_length > RF_W || (RF_W % d.hop_length) != 0)
-        return "rf_plan_create: hop_length must divide win_length";
+    // 44.1 kHz defaults (win 4410 = 10*9*49, n_fft 17640, hop | win): the prime-factor engine.  Anything else (other sample
+    // rates: 48 kHz -> 4800 / 19200 / 480, 22.05 kHz -> 2205 / 8820 / 220 where hop does not divide win, custom window or
+    // padding durations) runs on the generic mixed-radix engine.
+    p.generic = d.win_length != RF_W || d.n_fft != RF_N || d.hop_length > RF_W || (RF_W % d.hop_length) != 0;
+    if (p.generic) {
+        if (d.n_fft & 1) return "rf_plan_create: n_fft must be even (generic FFT engine packs two real samples per point)";
+        int n2 = d.n_fft / 2;
+        if (n2 > 14000)
+            return "rf_plan_create: n_fft = " + std::to_string(d.n_fft) + " exceeds the generic engine's shared-memory frame "
+                   "(n_fft <= 28000, i.e. sample rates up to 70 kHz with the default 400 ms padding)";
+        p.radices.clear();
+        const int cand[5] = {4, 2, 3, 5, 7};
+        for (int r : cand)
+            while (n2 % r == 0 && !(r == 2 && n2 % 4 == 0)) {
+                p.radices.push_back(r);
+                n2 /= r;
+            }
+        if (n2 != 1)
+            return "rf_plan_create: n_fft/2 = " + std::to_string(d.n_fft / 2) + " has a prime factor > 7; the generic FFT engine "
+                   "handles 2^a 3^b 5^c 7^d";
+        if (p.radices.size() > 16) return "rf_plan_create: too many FFT stages";
+    }
     p.d = d;
     p.N = d.n_fft;
     p.W = d.win_length;
@@ -135,7 +151,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
         code = RF_ERR_INVALID;
         return "rf_plan_create: mel filterbank is identically zero";
     }
-    std::sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
+    if (!p.generic) std::sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
         const int gx = x.k & 1, gy = y.k & 1;
         if (gx != gy) return gx < gy;
         if (x.r != y.r) return x.r < y.r;
@@ -144,7 +160,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
     // Within each r block, interleave the positions round-robin over (idx mod 16) so that any 16
     // consecutive bins (a half warp of 8-byte shared-memory accesses at V[idx] and at the partner
     // position 4409-idx) fall in 16 distinct bank pairs.
-    {
+    if (!p.generic) {
         std::vector<Ent> out;
         out.reserve(ents.size());
         size_t i0 = 0;
@@ -187,7 +203,23 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
                   (idx2 << 15) | (static_cast<uint32_t>(k & 7) << 28);
     }
 
+    if (p.generic) {
+        const int N2 = p.N / 2;
+        p.roots2.resize(static_cast<size_t>(N2) * 2);
+        for (int n = 0; n < N2; ++n) {
+            const double ang = -2.0 * M_PI * static_cast<double>(n) / N2;
+            p.roots2[2 * n] = static_cast<float>(std::cos(ang));
+            p.roots2[2 * n + 1] = static_cast<float>(std::sin(ang));
+        }
+        p.rootsN.resize(static_cast<size_t>(N2 + 1) * 2);
+        for (int k = 0; k <= N2; ++k) {
+            const double ang = -2.0 * M_PI * static_cast<double>(k) / p.N;
+            p.rootsN[2 * k] = static_cast<float>(std::cos(ang));
+            p.rootsN[2 * k + 1] = static_cast<float>(std::sin(ang));
+        }
+    }
     // ---- modulation x window tables, time-side (Ruritanian) index n'(a,b,c), stored [r][b][c][a]
+    if (!p.generic) {
     p.wt_fwd.assign(static_cast<size_t>(4) * p.W * 2, 0.f);
     p.wt_inv.assign(static_cast<size_t>(4) * p.W * 2, 0.f);
     for (int r = 0; r < 4; ++r)
@@ -205,6 +237,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
                     p.wt_inv[o] = static_cast<float>(w * std::cos(ang) / p.N);
                     p.wt_inv[o + 1] = static_cast<float>(-w * std::sin(ang) / p.N);
                 }
+    }
 
     // ---- time-decimated loop tables.  Eligible when every live bin k satisfies 2k + 800 <= N/2: the spectrum of a
     // windowed frame at distance >= 800 bins from its content is < 4e-8 of the peak (Hann side lobes fall with the
@@ -212,7 +245,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
     // measurable.  Needs an odd hop (frame parities alternate) and an even chunk size.  The full-rate edge strips of the
     // hybrid loop (rf_dec_geom: 3 head pairs, E = W + H, tail chunks from (T-17)/G) are laid out for hop = W/10 = 441,
     // the reference's default step; other odd hops (2205) run the full-rate loop.
-    p.decimate = (p.H == 441) && (RF_CHUNK % 2 == 0) && (2 * p.k_hi + 800 <= p.N / 2) && (p.W == 4410);
+    p.decimate = !p.generic && (p.H == 441) && (RF_CHUNK % 2 == 0) && (2 * p.k_hi + 800 <= p.N / 2) && (p.W == 4410);
     if (p.decimate) {
         const int W2 = 2205, N2 = p.N / 2;
         p.pp2.resize(p.n_live);

@@ -320,3 +320,44 @@ def test_random_init_uses_torch_global_rng(conv):
     torch.manual_seed(8)
     c = conv.waveform_from_mel_amplitudes(mel)
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+@pytest.mark.parametrize("sr,kw", [(48000, {}), (22050, {}), (44100, dict(window_duration_ms=50, padded_duration_ms=200, step_size_ms=5))])
+def test_generic_engine_other_geometries_vs_torchaudio(native_lib, sr, kw):
+    """sample rates / window settings the prime-factor engine does not cover (cli.py:40-52 builds the params from the
+    file's frame rate): 48 kHz (n_fft 19200 = 2 * 2^7 3 5^2), 22.05 kHz (win 2205 odd, hop 220 does not divide it: the
+    overlap-add envelope is not constant), and non-default window / padding / step durations.
+    STFT, STFT+mel, inverse mel and Griffin-Lim against the installed torchaudio transforms with the reference's arguments."""
+    import torchaudio
+
+    from oracle.torchaudio_ref import TorchaudioConverter, griffinlim_with_angles
+    from riffusion.spectrogram_converter import SpectrogramConverter
+    from riffusion.spectrogram_params import SpectrogramParams
+
+    n_iter = 4
+    p = SpectrogramParams(sample_rate=sr, num_griffin_lim_iters=n_iter, **kw)
+    c = SpectrogramConverter(p, device="cuda")
+    t = TorchaudioConverter(sample_rate=sr, n_fft=p.n_fft, win_length=p.win_length, hop_length=p.hop_length, n_iter=n_iter)
+    Fg = p.n_fft // 2 + 1
+    torch.manual_seed(sr)
+    x = torch.randn(2, p.n_fft + 37 * p.hop_length + 11) * 3000
+    ref = t.spectrogram_func(x)
+    got = c.spectrogram_func(x.cuda()).cpu()
+    assert got.shape == ref.shape == (2, Fg, 1 + x.shape[1] // p.hop_length)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 3e-6
+    mel_ref = t.mel_amplitudes_from_waveform(x)
+    mel_got = c.mel_amplitudes_from_waveform(x.cuda()).cpu()
+    assert float((mel_got - mel_ref).abs().max() / mel_ref.abs().max()) < 3e-6
+    T_ = 60
+    mel = (torch.rand(2, 512, T_) ** 4) * 3e7
+    lin_ref = t.inverse_mel_scaler(mel)
+    lin_got = c.inverse_mel_scaler(mel.cuda()).cpu()
+    assert float((lin_got - lin_ref).norm() / lin_ref.norm()) < 1e-5
+    ang = torch.rand(2, Fg, T_, dtype=torch.complex64)
+    gl = torchaudio.transforms.GriffinLim(n_fft=p.n_fft, n_iter=n_iter, win_length=p.win_length, hop_length=p.hop_length, power=1.0,
+                                          momentum=0.99, rand_init=True)
+    wave_ref = griffinlim_with_angles(gl, lin_ref, ang)
+    wave_full = c.inverse_spectrogram_func.forward(lin_ref.cuda(), ang.cuda()).cpu()
+    wave_fused = c.waveform_from_mel_amplitudes(mel.cuda(), ang.cuda()).cpu()
+    assert wave_full.shape == wave_fused.shape == wave_ref.shape == (2, p.hop_length * (T_ - 1))
+    assert _norm_rms(wave_full, wave_ref) < 2e-5 and _norm_rms(wave_fused, wave_ref) < 5e-5

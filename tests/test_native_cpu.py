@@ -48,8 +48,18 @@ def test_unsupported_geometry_is_loud(native_lib):
     from riffusion.spectrogram_converter import get_plan
     from riffusion.spectrogram_params import SpectrogramParams
 
+    # other sample rates run on the generic mixed-radix engine (48 kHz: n_fft 19200 = 2 * 2^7 3 5^2; 22.05 kHz: hop 220
+    # does not divide win 2205) ...
+    for sr, n_fft, win, hop in ((48000, 19200, 4800, 480), (22050, 8820, 2205, 220)):
+        prm = SpectrogramParams(sample_rate=sr)
+        assert (prm.n_fft, prm.win_length, prm.hop_length) == (n_fft, win, hop)
+        plan = get_plan(prm, full_band=False)
+        assert plan.info.n_freq == n_fft // 2 + 1 and plan.info.n_live > 0
+    # ... unless n_fft/2 has a prime factor above 7 (44 kHz: 17600 / 2 = 2^5 5^2 11) or the frame exceeds shared memory
     with pytest.raises(NotImplementedError):
-        get_plan(SpectrogramParams(sample_rate=48000), full_band=False)
+        get_plan(SpectrogramParams(sample_rate=44000), full_band=False)
+    with pytest.raises(NotImplementedError):
+        get_plan(SpectrogramParams(sample_rate=96000), full_band=False)
 
 
 def test_plan_tables(native_lib):
