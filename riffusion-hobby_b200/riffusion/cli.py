@@ -59,10 +59,6 @@ def _run_pool(worker: T.Callable[[Path], None], items: T.Sequence[Path], num_thr
             pass
 
 
-def _random_window(total_ms: int, duration_ms: int) -> int:
-    return int(np.random.randint(0, max(total_ms - duration_ms, 1)))
-
-
 # ------------------------------------------------------------------------------------------------ commands
 def audio_to_image(*, audio: str, image: str, step_size_ms: int = 10, num_frequencies: int = 512,
                    min_frequency: int = 0, max_frequency: int = 10000, window_duration_ms: int = 100,
@@ -149,7 +145,9 @@ def sample_clips_batch(*, audio_dir: str, output_dir: str, num_clips_per_file: i
                        mono: bool = False, extension: str = "mp3", num_threads: T.Optional[int] = None, glob: str = "*",
                        limit: int = -1, seed: int = -1):
     """Sample short clips from a directory of audio files, multi-threaded."""
-    sources = _files_in(audio_dir, pattern=glob, limit=limit)
+    sources = [p for p in _files_in(audio_dir, pattern=glob) if p.suffix != ".json"]      # metadata files never count (:219-220)
+    if limit > 0:
+        sources = sources[:limit]
     if seed >= 0:
         random.seed(seed)
     target = Path(output_dir)
@@ -163,7 +161,10 @@ def sample_clips_batch(*, audio_dir: str, output_dir: str, num_clips_per_file: i
             source = source.set_channels(1)
         total_ms = int(source.duration_seconds * 1000)
         for index in range(num_clips_per_file):
-            begin = _random_window(total_ms, duration_ms)
+            try:        # a source no longer than the clip duration yields nothing, as in the reference (:247-250)
+                begin = int(np.random.randint(0, total_ms - duration_ms))
+            except ValueError:
+                continue
             name = f"{path.stem}_{index}_start_{begin}_ms_dur_{duration_ms}_ms.{extension}"
             source[begin: begin + duration_ms].export(target / name, format=extension)
 
