@@ -722,9 +722,11 @@ TileCfg pick_cfg(int N, long tiles_m, int nbatch, int num_kb) {
     }
     if ((N % 256) != 0) {
         // N = 320 / 640 / 960 ...: 320-wide pair tiles (two instructions, no accumulator double buffering) when K is long
-        // enough to amortise the exposed epilogue
+        // enough to amortise the exposed epilogue (~4000 clk per tile against 640 clk per K slab).  Measured at batch 64
+        // (profiles/r02_tile_configs.md): K >= 2880 (every 3x3 conv) gains 5-30 % (up to 1450 TFLOP/s), K = 1920-2560 is
+        // even, K <= 1280 loses 10-25 % against the 1-SM 128 x 160 tile -> threshold 45 slabs.
         const char* env320 = getenv("RF_GEMM_320_MIN_KB");
-        const int min_kb = env320 ? atoi(env320) : 10;
+        const int min_kb = env320 ? atoi(env320) : 45;
         if ((N % 320) == 0 && num_kb >= min_kb && tiles_m_total * (N / 160) >= 2 * sms) {
             c.bn = 320;
             c.pair = true;

@@ -148,10 +148,15 @@ def test_unet_benchmarked_batch64_matches_oracle_and_graph(sd15):
     emul2 = torch.cat([_emul_hi(ue.unet_forward, oracle, x[i:i + 1], t, ctx[i:i + 1]) for i in idx.tolist()[:2]])
     print(f"two fp16-storage evaluations apart (2 images): {rel_l2(emul2, emul[:2]):.3e}")
     _check_vs_floor(got[idx], ref32, emul, "UNet SD-1.5 CFG batch 64 (subset of 6 images)")
-    # images are independent: the same image evaluated in a batch of 2 gives the same numbers up to tile-shape
-    # dependent accumulation order (different BN / split-K) -> far below the fp16 floor
+    # images are independent, but a batch of 2 takes other tile shapes / split-K than a batch of 64: a different
+    # accumulation order below fp32 rounding, i.e. one more "equally valid fp16 evaluation" — it sits as far from the
+    # batch-64 result as two emulations sit from each other, not closer
     pair = ours(x[[0, 32]].contiguous(), t, encoder_hidden_states=ctx[[0, 32]].contiguous()).sample
-    assert rel_l2(pair, got[[0, 32]]) < 5e-4
+    spread = rel_l2(emul2, emul[:2])
+    e_pair = rel_l2(pair, got[[0, 32]])
+    print(f"same images at batch 2 vs batch 64: {e_pair:.3e} (spread of two fp16-storage evaluations {spread:.3e})")
+    assert e_pair <= 1.25 * spread + 1e-4
+    assert torch.equal(ours(x[[0, 32]].contiguous(), t, encoder_hidden_states=ctx[[0, 32]].contiguous()).sample, pair)   # deterministic
     graphed = GraphedUNet(ours, lat.shape, ctx)
     g = graphed(lat, t).clone()
     assert torch.equal(g, got), "CUDA-graph replay differs from the eager evaluation at full size"
