@@ -322,7 +322,7 @@ def test_random_init_uses_torch_global_rng(conv):
     assert torch.equal(a, b) and not torch.equal(a, c)
 
 
-@pytest.mark.parametrize("sr,kw", [(48000, {}), (22050, {}), (44100, dict(window_duration_ms=50, padded_duration_ms=200, step_size_ms=5))])
+@pytest.mark.parametrize("sr,kw", [(48000, {}), (22050, {}), (44100, dict(window_duration_ms=50, padded_duration_ms=200, step_size_ms=5, num_frequencies=256))])
 def test_generic_engine_other_geometries_vs_torchaudio(native_lib, sr, kw):
     """sample rates / window settings the prime-factor engine does not cover (cli.py:40-52 builds the params from the
     file's frame rate): 48 kHz (n_fft 19200 = 2 * 2^7 3 5^2), 22.05 kHz (win 2205 odd, hop 220 does not divide it: the
@@ -337,7 +337,8 @@ def test_generic_engine_other_geometries_vs_torchaudio(native_lib, sr, kw):
     n_iter = 4
     p = SpectrogramParams(sample_rate=sr, num_griffin_lim_iters=n_iter, **kw)
     c = SpectrogramConverter(p, device="cuda")
-    t = TorchaudioConverter(sample_rate=sr, n_fft=p.n_fft, win_length=p.win_length, hop_length=p.hop_length, n_iter=n_iter)
+    t = TorchaudioConverter(sample_rate=sr, n_fft=p.n_fft, win_length=p.win_length, hop_length=p.hop_length, n_mels=p.num_frequencies,
+                            n_iter=n_iter)
     Fg = p.n_fft // 2 + 1
     torch.manual_seed(sr)
     x = torch.randn(2, p.n_fft + 37 * p.hop_length + 11) * 3000
@@ -349,7 +350,7 @@ def test_generic_engine_other_geometries_vs_torchaudio(native_lib, sr, kw):
     mel_got = c.mel_amplitudes_from_waveform(x.cuda()).cpu()
     assert float((mel_got - mel_ref).abs().max() / mel_ref.abs().max()) < 3e-6
     T_ = 60
-    mel = (torch.rand(2, 512, T_) ** 4) * 3e7
+    mel = (torch.rand(2, p.num_frequencies, T_) ** 4) * 3e7
     lin_ref = t.inverse_mel_scaler(mel)
     lin_got = c.inverse_mel_scaler(mel.cuda()).cpu()
     assert float((lin_got - lin_ref).norm() / lin_ref.norm()) < 1e-5
