@@ -257,7 +257,9 @@ __device__ __forceinline__ void istft_chunk_body(unsigned char* smem_raw, const 
         in.momentum = momentum;
         rf_istft_load<NA>(tid, RF_NT, V, tb, j0, j1, in);
         __syncthreads();
-        rf_pass_c<true, NA>(tid, RF_NT, V);
+        rf_pass_c7<true, NA, 0>(tid, RF_NT, V);
+        __syncthreads();
+        rf_pass_c7<true, NA, 1>(tid, RF_NT, V);
         __syncthreads();
         rf_pass_a<true, NA>(tid, RF_NT, V);
         __syncthreads();
@@ -278,25 +280,31 @@ k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __rest
                          part + ((static_cast<size_t>(b) * 2 + g) * nchunks + chunk) * PL);
 }
 
-// hybrid decimated loop (rf_gl_dec_geom): grid ((nslots + nchunks)*2, B).  The first nslots*2 CTAs redo the chunks
-// that overlap the edge strips at full rate (heaviest CTAs first), the rest produce half-rate partial sums of every
-// chunk.  part_e[b][g][slot][PL], part_h[b][g][chunk][PLh]
+// hybrid decimated loop (rf_gl_dec_geom), two launches with their own footprints:
+//   k_istft_edge: grid (nslots*2, B) — the chunks that overlap the full-rate edge strips, redone at full rate
+//                 (part_e[b][g][slot][PL]; 112 KB of shared memory, 2 CTAs/SM)
+//   k_istft_half: grid (nchunks*2, B) — half-rate partial sums of every chunk (part_h[b][g][chunk][PLh]); 2205-point
+//                 sub-transforms: 57 KB of shared memory and <= 85 registers with the 7-thread radix-49 pass -> 3 CTAs/SM
+// (one merged launch had to give every CTA the full-rate footprint: 2 CTAs/SM for the 91 % of CTAs that are half rate)
 __global__ void __launch_bounds__(RF_NT, 2)
-k_istft_dec(rf_gl_tables tb, rf_gl_tables tb2, const float* __restrict__ S, const rf_c32* __restrict__ cur,
-            const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL, int PLh, int nchunks,
-            int c_tail, int nslots, float* __restrict__ part_e, float* __restrict__ part_h) {
+k_istft_edge(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __restrict__ cur,
+             const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL, int c_tail, int nslots,
+             float* __restrict__ part_e) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int g = blockIdx.x & 1, b = blockIdx.y;
-    int idx = blockIdx.x >> 1;
-    if (idx < nslots) {
-        const int chunk = idx == 0 ? 0 : c_tail + idx - 1;
-        istft_chunk_body<10>(smem_raw, tb, S, cur, prev, mode, momentum, T, G, PL, 2 * tb.off1, b, g, chunk,
-                             part_e + ((static_cast<size_t>(b) * 2 + g) * nslots + idx) * PL);
-    } else {
-        idx -= nslots;
-        istft_chunk_body<5>(smem_raw, tb2, S, cur, prev, mode, momentum, T, G, PLh, 2 * tb2.off1 - 1, b, g, idx,
-                            part_h + ((static_cast<size_t>(b) * 2 + g) * nchunks + idx) * PLh);
-    }
+    const int g = blockIdx.x & 1, b = blockIdx.y, idx = blockIdx.x >> 1;
+    const int chunk = idx == 0 ? 0 : c_tail + idx - 1;
+    istft_chunk_body<10>(smem_raw, tb, S, cur, prev, mode, momentum, T, G, PL, 2 * tb.off1, b, g, chunk,
+                         part_e + ((static_cast<size_t>(b) * 2 + g) * nslots + idx) * PL);
+}
+
+__global__ void __launch_bounds__(RF_NT, 3)
+k_istft_half(rf_gl_tables tb2, const float* __restrict__ S, const rf_c32* __restrict__ cur,
+             const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PLh, int nchunks,
+             float* __restrict__ part_h) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x & 1, b = blockIdx.y, idx = blockIdx.x >> 1;
+    istft_chunk_body<5>(smem_raw, tb2, S, cur, prev, mode, momentum, T, G, PLh, 2 * tb2.off1 - 1, b, g, idx,
+                        part_h + ((static_cast<size_t>(b) * 2 + g) * nchunks + idx) * PLh);
 }
 
 // ---- overlap-add assembly: x[b][i] = sum(parts) / envelope, kept region only --------------
@@ -355,7 +363,9 @@ __device__ __forceinline__ void stft_pair_body(unsigned char* smem_raw, const rf
     __syncthreads();
     rf_pass_a<false, NA>(tid, RF_NT, V);
     __syncthreads();
-    rf_pass_c<false, NA>(tid, RF_NT, V);
+    rf_pass_c7<false, NA, 0>(tid, RF_NT, V);
+    __syncthreads();
+    rf_pass_c7<false, NA, 1>(tid, RF_NT, V);
     __syncthreads();
     const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
     rf_c32* out0 = R + (static_cast<size_t>(b) * T + t0) * tb.n_live;
@@ -370,22 +380,27 @@ k_stft_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int hop,
     stft_pair_body<10>(smem_raw, tb, x + static_cast<size_t>(b) * L, 0, L, T, hop, b, g, pr, R);
 }
 
-// hybrid decimated loop: grid (npairs*2, B); the first n_edge_pairs*2 CTAs are the edge pairs (3 head pairs, then
-// the pairs from pr_tail on) at full rate from the strips of xd, the rest read xo at half rate
+// hybrid decimated loop, two launches: k_stft_edge, grid (n_edge_pairs*2, B): the edge pairs (3 head pairs, then the
+// pairs from pr_tail on) at full rate from the strips of xd; k_stft_half, grid ((npairs - n_edge_pairs)*2, B): the rest
+// from the odd samples xo at half rate (45 KB of shared memory, <= 85 registers: 3 CTAs/SM)
 __global__ void __launch_bounds__(RF_NT, 2)
-k_stft_dec(rf_gl_tables tb, rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E,
-           int pr_tail, int n_edge_pairs, rf_c32* __restrict__ R) {
+k_stft_edge(rf_gl_tables tb, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E, int pr_tail,
+            rf_c32* __restrict__ R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = blockIdx.x & 1, b = blockIdx.y;
     const int idx = blockIdx.x >> 1;
     const float* xb = xd + static_cast<size_t>(b) * (nxo + 2 * E);
-    if (idx < 3) {
-        stft_pair_body<10>(smem_raw, tb, xb + nxo, 0, L, T, hop, b, g, idx, R);
-    } else if (idx < n_edge_pairs) {
-        stft_pair_body<10>(smem_raw, tb, xb + nxo + E, L - E, L, T, hop, b, g, pr_tail + idx - 3, R);
-    } else {
-        stft_pair_body<5>(smem_raw, tb2, xb, 0, L, T, hop, b, g, 3 + idx - n_edge_pairs, R);
-    }
+    if (idx < 3) stft_pair_body<10>(smem_raw, tb, xb + nxo, 0, L, T, hop, b, g, idx, R);
+    else stft_pair_body<10>(smem_raw, tb, xb + nxo + E, L - E, L, T, hop, b, g, pr_tail + idx - 3, R);
+}
+
+__global__ void __launch_bounds__(RF_NT, 3)
+k_stft_half(rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E,
+            rf_c32* __restrict__ R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x & 1, b = blockIdx.y;
+    const float* xb = xd + static_cast<size_t>(b) * (nxo + 2 * E);
+    stft_pair_body<5>(smem_raw, tb2, xb, 0, L, T, hop, b, g, 3 + (blockIdx.x >> 1), R);
 }
 
 // ---- STFT + |.| + mel of one frame pair (both groups in one CTA) -------------------------
@@ -409,7 +424,9 @@ k_stft_mel_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int 
         __syncthreads();
         rf_pass_a<false, 10>(tid, RF_NT, V);
         __syncthreads();
-        rf_pass_c<false, 10>(tid, RF_NT, V);
+        rf_pass_c7<false, 10, 0>(tid, RF_NT, V);
+        __syncthreads();
+        rf_pass_c7<false, 10, 1>(tid, RF_NT, V);
         __syncthreads();
         const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
         rf_stft_post<10>(tid, RF_NT, V, tb, j0, j1, spec0, spec1);
@@ -721,11 +738,13 @@ static int check_T(const rf_plan* p, int T, const char* who) {
 }
 
 static int set_smem_attrs() {
-    static rf_dev_once once[6];
+    static rf_dev_once once[8];
     cudaError_t err = rf_set_smem_once(once[0], k_istft_chunk, 200 * 1024);
-    if (err == cudaSuccess) err = rf_set_smem_once(once[1], k_istft_dec, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[1], k_istft_edge, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[6], k_istft_half, 100 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[7], k_stft_half, 100 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[2], k_stft_pair, 200 * 1024);
-    if (err == cudaSuccess) err = rf_set_smem_once(once[3], k_stft_dec, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[3], k_stft_edge, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[4], k_stft_mel_pair, 227 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[5], k_inverse_mel, 200 * 1024);
     if (err != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
@@ -796,8 +815,10 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const int PLh = ((RF_CHUNK - 1) * h.H + h.W + 1) / 2;
     const size_t smem_i = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(w.PL) * 4;
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
+    const size_t smem_ih = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(PLh) * 4;                       // half-rate CTAs
+    const size_t smem_fh = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(RF_PW / 2 + (h.H + 1) / 2 + 2) * 4;
     const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
-    const dim3 grid_i2((w.nchunks + dg.nslots) * 2, B), grid_a2((dg.nxo + 2 * dg.E + 255) / 256, B);
+    const dim3 grid_a2((dg.nxo + 2 * dg.E + 255) / 256, B);
     k_envelope<<<(L + 255) / 256, 256, 0, st>>>(p->d_win2, T, h.H, h.W, L, w.env);
     RF_CUDA_LAUNCH_CHECK("k_envelope");
     for (int it = 0; it <= n_iter; ++it) {
@@ -815,10 +836,13 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
         const bool last = it == n_iter;
         const bool half = dec && !last;   // the final reconstruction is always full rate
         if (prof) RF_CUDA_TRY(prof->mark(0, 0, st));
-        if (half)
-            k_istft_dec<<<grid_i2, RF_NT, smem_i, st>>>(tb, tb2, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, PLh,
-                                                        w.nchunks, dg.c_tail, dg.nslots, w.part_e, w.part);
-        else
+        if (half) {
+            k_istft_edge<<<dim3(dg.nslots * 2, B), RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL,
+                                                                        dg.c_tail, dg.nslots, w.part_e);
+            RF_CUDA_LAUNCH_CHECK("k_istft_edge");
+            k_istft_half<<<dim3(w.nchunks * 2, B), RF_NT, smem_ih, st>>>(tb2, w.S, cur, prev, mode, m, T, RF_CHUNK, PLh,
+                                                                         w.nchunks, w.part);
+        } else
             k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
                                                          w.part);
         RF_CUDA_LAUNCH_CHECK("k_istft_chunk");
@@ -835,10 +859,13 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
         if (prof) RF_CUDA_TRY(prof->mark(1, 1, st));
         if (last) break;
         if (prof) RF_CUDA_TRY(prof->mark(2, 0, st));
-        if (dec)
-            k_stft_dec<<<grid_f, RF_NT, smem_f, st>>>(tb, tb2, w.xd, L, T, h.H, dg.nxo, dg.E, dg.pr_tail,
-                                                      dg.n_edge_pairs, w.R[it & 1]);
-        else
+        if (dec) {
+            k_stft_edge<<<dim3(dg.n_edge_pairs * 2, B), RF_NT, smem_f, st>>>(tb, w.xd, L, T, h.H, dg.nxo, dg.E, dg.pr_tail,
+                                                                            w.R[it & 1]);
+            RF_CUDA_LAUNCH_CHECK("k_stft_edge");
+            k_stft_half<<<dim3(((T + 1) / 2 - dg.n_edge_pairs) * 2, B), RF_NT, smem_fh, st>>>(tb2, w.xd, L, T, h.H, dg.nxo,
+                                                                                              dg.E, w.R[it & 1]);
+        } else
             k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, h.H, w.R[it & 1]);
         RF_CUDA_LAUNCH_CHECK("k_stft_pair");
         if (prof) RF_CUDA_TRY(prof->mark(2, 1, st));

@@ -80,17 +80,43 @@ RF_HD void rf_pass_a(int tid, int nt, rf_c32* V) {
     }
 }
 
-// radix-49 over c: items (s, ab); lane stride 49 elements (odd: conflict-free for 8-byte words)
-template <bool INV, int NA>
-RF_HD void rf_pass_c(int tid, int nt, rf_c32* V) {
-    for (int it = tid; it < 2 * 9 * NA; it += nt) {
-        rf_c32* p = V + it * 49;  // s*4410 + ab*49 == it*49
-        rf_c32 v[49];
+// radix-49 over c, SEVEN threads per 49-point transform (work item w = transform * 7 + j), two phases with a barrier
+// in between, both in place and free of cross-thread hazards:
+//   column phase (thread j = c2): DFT7 over the stride-7 elements p[7 c1 + j], twiddle w49^(k1 j), back to p[7 k1 + j]
+//   row phase    (thread j = k1): DFT7 over the contiguous row p[7 j + c2], back to p[7 j + k2] = X[j + 7 k2]
+// forward = column phase then row phase: natural time order in, TRANSPOSED spectral order out (X[k] at 7 (k % 7) + k / 7,
+// which is what the plan's position tables pp / pp2 point at: rf_pfa_spec_pos);  inverse = row phase (twiddle after the
+// DFT) then column phase: transposed spectral order in, natural time order out.  One thread per transform (the previous
+// form) kept 49 complex values = 98 registers live and left 166 of 256 threads idle for NA = 5.
+template <bool INV, int NA, int STEP>
+RF_HD void rf_pass_c7(int tid, int nt, rf_c32* V) {
+    const float WC[37] = RF_W49_COS;
+    const float WS[37] = RF_W49_SIN;
+    const float sg = INV ? 1.0f : -1.0f;
+    constexpr bool COLUMN = (STEP == 0) != INV;
+    for (int w = tid; w < 2 * 9 * NA * 7; w += nt) {
+        const int it = w / 7, j = w - it * 7;
+        rf_c32* p = V + it * 49;  // s*W + ab*49 == it*49
+        rf_c32 v[7];
+        if (COLUMN) {
 #pragma unroll
-        for (int c = 0; c < 49; ++c) v[c] = p[c];
-        dft49<INV>(v);
+            for (int i = 0; i < 7; ++i) v[i] = p[7 * i + j];
+        } else {
 #pragma unroll
-        for (int c = 0; c < 49; ++c) p[c] = v[7 * (c % 7) + c / 7];
+            for (int i = 0; i < 7; ++i) v[i] = p[7 * j + i];
+        }
+        dft7<INV>(v[0], v[1], v[2], v[3], v[4], v[5], v[6]);
+        if (STEP == 0) {   // the twiddle sits between the two DFT7 stages: after the first phase in either direction
+#pragma unroll
+            for (int i = 1; i < 7; ++i) v[i] = c_mulk(v[i], WC[i * j], sg * WS[i * j]);
+        }
+        if (COLUMN) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) p[7 * i + j] = v[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) p[7 * j + i] = v[i];
+        }
     }
 }
 

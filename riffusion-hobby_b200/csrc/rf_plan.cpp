@@ -145,7 +145,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
             }
         if (!live) continue;
         const int mm = k >> 2;
-        ents.push_back({k, k & 3, rf_pfa_pos(mm % RF_NA, mm % RF_NB, mm % RF_NC)});
+        ents.push_back({k, k & 3, rf_pfa_spec_pos(mm % RF_NA, mm % RF_NB, mm % RF_NC)});
     }
     if (ents.empty()) {
         code = RF_ERR_INVALID;
@@ -198,7 +198,7 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
         p.k_hi = std::max(p.k_hi, k);
         const int kp = (p.N - k) % p.N;
         const int mp = kp >> 2;
-        const uint32_t idx2 = rf_pfa_pos(mp % RF_NA, mp % RF_NB, mp % RF_NC);
+        const uint32_t idx2 = rf_pfa_spec_pos(mp % RF_NA, mp % RF_NB, mp % RF_NC);
         p.pp[j] = static_cast<uint32_t>(ents[j].r) | (static_cast<uint32_t>(ents[j].idx) << 2) |
                   (idx2 << 15) | (static_cast<uint32_t>(k & 7) << 28);
     }
@@ -253,10 +253,10 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
         for (int j = 0; j < p.n_live; ++j) {
             const int k = p.bins[j];
             const int m = k >> 2;
-            const uint32_t idx = rf_pfa_pos(m % 5, m % RF_NB, m % RF_NC);
+            const uint32_t idx = rf_pfa_spec_pos(m % 5, m % RF_NB, m % RF_NC);
             const int kp = (N2 - k) % N2;
             const int mp = kp >> 2;
-            const uint32_t idx2 = rf_pfa_pos(mp % 5, mp % RF_NB, mp % RF_NC);
+            const uint32_t idx2 = rf_pfa_spec_pos(mp % 5, mp % RF_NB, mp % RF_NC);
             p.pp2[j] = static_cast<uint32_t>(k & 3) | (idx << 2) | (idx2 << 15) | (static_cast<uint32_t>(k & 7) << 28);
             const double ang = -2.0 * M_PI * static_cast<double>(k) / p.N;
             p.ph_odd[2 * j] = static_cast<float>(std::cos(ang));

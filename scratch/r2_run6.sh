@@ -10,3 +10,8 @@ timeout -k 10 900 ncu --profile-from-start off --set full --clock-control none -
 tail -3 gpurun_out/ncu_full.log
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02_clip_launches.csv python bench.py --steps 1 --warmup 3 --evals 1 --clips 32 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 ls -la gpurun_out | tail -8
+# Griffin-Lim after the 7-thread radix-49 pass and the edge / half-rate kernel split
+timeout -k 10 600 python bench.py --workload gl --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_gl.json 2> gpurun_out/bench_gl.err
+cut -c1-1800 gpurun_out/bench_gl.json; tail -2 gpurun_out/bench_gl.err
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:'k_istft_half|k_stft_half|k_istft_edge|k_stft_edge' -s 8 -c 4 -o gpurun_out/r02_gl -f python scratch/prof_gl.py 64 4 > gpurun_out/ncu_gl.log 2>&1
+tail -2 gpurun_out/ncu_gl.log

@@ -62,7 +62,8 @@ void emu_stft_pairs(const rf_plan_host& h, const float* x, int base, int L, int 
             else phase([&](int tid) { rf_stage_x_d2(tid, NT, xs.data(), x, L, t0, h.H); });
             phase([&](int tid) { rf_stft_pass_b<NA>(tid, NT, V.data(), xs.data(), tb, g, has1); });
             phase([&](int tid) { rf_pass_a<false, NA>(tid, NT, V.data()); });
-            phase([&](int tid) { rf_pass_c<false, NA>(tid, NT, V.data()); });
+            phase([&](int tid) { rf_pass_c7<false, NA, 0>(tid, NT, V.data()); });
+            phase([&](int tid) { rf_pass_c7<false, NA, 1>(tid, NT, V.data()); });
             const int j0 = g ? tb.n_even : 0, j1 = g ? tb.n_live : tb.n_even;
             rf_c32* out0 = R + static_cast<size_t>(t0) * tb.n_live;
             phase([&](int tid) {
@@ -104,7 +105,8 @@ void emu_istft_chunk(const rf_plan_host& h, const float* S, const rf_c32* cur, c
         in.mode = mode;
         in.momentum = momentum;
         phase([&](int tid) { rf_istft_load<NA>(tid, NT, V.data(), tb, j0, j1, in); });
-        phase([&](int tid) { rf_pass_c<true, NA>(tid, NT, V.data()); });
+        phase([&](int tid) { rf_pass_c7<true, NA, 0>(tid, NT, V.data()); });
+        phase([&](int tid) { rf_pass_c7<true, NA, 1>(tid, NT, V.data()); });
         phase([&](int tid) { rf_pass_a<true, NA>(tid, NT, V.data()); });
         // device: one call with which=2 (barrier between the real- and imaginary-part adds)
         float* o = ola.data() + pr * pair_stride;

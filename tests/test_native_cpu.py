@@ -80,8 +80,9 @@ def test_plan_tables(native_lib):
         r, idx, idx2, k7 = pp & 3, (pp >> 2) & 8191, (pp >> 15) & 8191, pp >> 28
         assert np.array_equal(r, bins % 4) and np.array_equal(k7, bins % 8)
 
-        def pos(m):
-            return (m % 10) * 441 + (m % 9) * 49 + (m % 49)
+        def pos(m):          # spectral slot: the 7-thread radix-49 pass leaves output c at 7 (c % 7) + c // 7 of its block
+            c = m % 49
+            return (m % 10) * 441 + (m % 9) * 49 + 7 * (c % 7) + c // 7
 
         assert np.array_equal(idx, pos(bins // 4))
         assert np.array_equal(idx2, pos(((N - bins) % N) // 4))
