@@ -217,6 +217,30 @@ struct rf_w49 {
      -0.9953790903091431f}
 
 // in: v[c], c = 7*c1 + c2 ; out: v[c'], c' = c1' + 7*c2'  (natural in / natural out)
+// cos / sin(2 pi m / 49), m = 0..36, for code that indexes the twiddle at run time (the 7-thread radix-49 pass): a
+// __constant__ table on the device (a local array would be copied to the thread's stack and read with LDL), a static one
+// on the host
+#if defined(__CUDACC__)
+__device__ __constant__ float rf_w49_cos_dev[37] = RF_W49_COS;
+__device__ __constant__ float rf_w49_sin_dev[37] = RF_W49_SIN;
+#endif
+static const float rf_w49_cos_host[37] = RF_W49_COS;
+static const float rf_w49_sin_host[37] = RF_W49_SIN;
+RF_HD float rf_w49_cos(int m) {
+#if defined(__CUDA_ARCH__)
+    return rf_w49_cos_dev[m];
+#else
+    return rf_w49_cos_host[m];
+#endif
+}
+RF_HD float rf_w49_sin(int m) {
+#if defined(__CUDA_ARCH__)
+    return rf_w49_sin_dev[m];
+#else
+    return rf_w49_sin_host[m];
+#endif
+}
+
 template <bool INV>
 RF_HD void dft49(rf_c32* v) {
     const float WC[37] = RF_W49_COS;

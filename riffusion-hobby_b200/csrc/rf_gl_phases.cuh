@@ -90,8 +90,6 @@ RF_HD void rf_pass_a(int tid, int nt, rf_c32* V) {
 // form) kept 49 complex values = 98 registers live and left 166 of 256 threads idle for NA = 5.
 template <bool INV, int NA, int STEP>
 RF_HD void rf_pass_c7(int tid, int nt, rf_c32* V) {
-    const float WC[37] = RF_W49_COS;
-    const float WS[37] = RF_W49_SIN;
     const float sg = INV ? 1.0f : -1.0f;
     constexpr bool COLUMN = (STEP == 0) != INV;
     for (int w = tid; w < 2 * 9 * NA * 7; w += nt) {
@@ -108,7 +106,7 @@ RF_HD void rf_pass_c7(int tid, int nt, rf_c32* V) {
         dft7<INV>(v[0], v[1], v[2], v[3], v[4], v[5], v[6]);
         if (STEP == 0) {   // the twiddle sits between the two DFT7 stages: after the first phase in either direction
 #pragma unroll
-            for (int i = 1; i < 7; ++i) v[i] = c_mulk(v[i], WC[i * j], sg * WS[i * j]);
+            for (int i = 1; i < 7; ++i) v[i] = c_mulk(v[i], rf_w49_cos(i * j), sg * rf_w49_sin(i * j));
         }
         if (COLUMN) {
 #pragma unroll
