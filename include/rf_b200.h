@@ -38,7 +38,11 @@ typedef struct rf_plan rf_plan;
 
 /* Mirrors riffusion/spectrogram_params.py:8-81 (SpectrogramParams + derived n_fft /
  * win_length / hop_length) and the MelScale arguments of
- * riffusion/spectrogram_converter.py:75-99. */
+ * riffusion/spectrogram_converter.py:75-99.
+ * Geometry: win 4410 / n_fft 17640 / hop dividing 4410 (44.1 kHz defaults) runs on the prime-factor
+ * engine; any other even n_fft <= 28000 with n_fft/2 = 2^a 3^b 5^c 7^d (48 kHz: 19200, 22.05 kHz: 8820,
+ * custom window / padding / step durations) runs on the generic mixed-radix engine; everything else is
+ * RF_ERR_UNSUPPORTED from rf_plan_create. */
 typedef struct rf_plan_desc {
     int32_t sample_rate;  /* 44100 */
     int32_t n_fft;        /* 17640  (padded_duration_ms) */
