@@ -39,6 +39,7 @@ struct AttnParams {
     __half* out;          // [B][Nq][C]
     long out_pitch;       // C
     int causal;           // 1: key j is visible to query i only if j <= i (CLIP text encoder); short-key kernel only
+    int poly_exp;         // 1: half of the exponentials of the single-pass kernel on the FMA pipe (experiment, RF_ATTN_POLY=1)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -595,6 +596,26 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 #pragma unroll
             for (int c0 = 0; c0 < TKT; c0 += 8) {
                 uint32_t pk[4];
+                if (p.poly_exp && (c0 & 8)) {
+                    // every second group of 8 keys: 2^a on the FMA / ALU pipes instead of MUFU (the exponentials of a key
+                    // tile are the whole MUFU budget of that tile): n = round(a) by the magic-number add, 2^(a - n) by a
+                    // degree-3 polynomial on [-0.5, 0.5] (7.5e-5 relative, below the 4.9e-4 fp16 rounding of P), exponent
+                    // bits of n added to the result.  a <= RESCALE_LOG2; a < -24 is clamped (2^-24 = fp16's smallest).
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        float e[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float a = fmaxf(fmaf(__uint_as_float(v[c0 + i + u]), c, -mc), -24.f);
+                            const float t = a + 12582912.f;
+                            const float f = a - (t - 12582912.f);
+                            const float q = fmaf(fmaf(fmaf(0.05517144f, f, 0.24261071f), f, 0.69326097f), f, 0.99992812f);
+                            e[u] = __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+                        }
+                        const __half2 h = __floats2half2_rn(e[0], e[1]);
+                        pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                } else
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
                     // the argument (<= RESCALE_LOG2) is formed in fp32 and rounded once to fp16; P is fp16 anyway
@@ -1080,6 +1101,13 @@ extern "C" int rf_attention_masked_f16(const void* q, const void* k, const void*
     p.out = static_cast<__half*>(out);
     p.out_pitch = C;
     p.causal = causal ? 1 : 0;
+    {
+        // measured at the benchmarked batch (profiles/README.md, round 2): 73.8 ms per evaluation with the polynomial on,
+        // 71.3 ms off — the softmax warps are FMA/ALU-issue bound before they are MUFU bound, so moving exponentials to
+        // the FMA pipe loses.  Kept as an experiment switch (RF_ATTN_POLY=1), off by default.
+        const char* e = getenv("RF_ATTN_POLY");
+        p.poly_exp = (e && e[0] == '1') ? 1 : 0;
+    }
     dim3 grid((Nq + TQ - 1) / TQ, heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool no_short = getenv("RF_ATTN_NO_SHORT") != nullptr;

@@ -297,7 +297,10 @@ k_istft_edge(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __restr
                          part_e + ((static_cast<size_t>(b) * 2 + g) * nslots + idx) * PL);
 }
 
-__global__ void __launch_bounds__(RF_NT, 3)
+#ifndef RF_GL_HALF_MINB
+#define RF_GL_HALF_MINB 3   // CTAs per SM the half-rate kernels are compiled for (A/B builds: 2)
+#endif
+__global__ void __launch_bounds__(RF_NT, RF_GL_HALF_MINB)
 k_istft_half(rf_gl_tables tb2, const float* __restrict__ S, const rf_c32* __restrict__ cur,
              const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PLh, int nchunks,
              float* __restrict__ part_h) {
@@ -394,7 +397,7 @@ k_stft_edge(rf_gl_tables tb, const float* __restrict__ xd, int L, int T, int hop
     else stft_pair_body<10>(smem_raw, tb, xb + nxo + E, L - E, L, T, hop, b, g, pr_tail + idx - 3, R);
 }
 
-__global__ void __launch_bounds__(RF_NT, 3)
+__global__ void __launch_bounds__(RF_NT, RF_GL_HALF_MINB)
 k_stft_half(rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E,
             rf_c32* __restrict__ R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -741,8 +744,8 @@ static int set_smem_attrs() {
     static rf_dev_once once[8];
     cudaError_t err = rf_set_smem_once(once[0], k_istft_chunk, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[1], k_istft_edge, 200 * 1024);
-    if (err == cudaSuccess) err = rf_set_smem_once(once[6], k_istft_half, 100 * 1024);
-    if (err == cudaSuccess) err = rf_set_smem_once(once[7], k_stft_half, 100 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[6], k_istft_half, 200 * 1024);
+    if (err == cudaSuccess) err = rf_set_smem_once(once[7], k_stft_half, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[2], k_stft_pair, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[3], k_stft_edge, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[4], k_stft_mel_pair, 227 * 1024);
@@ -815,8 +818,12 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const int PLh = ((RF_CHUNK - 1) * h.H + h.W + 1) / 2;
     const size_t smem_i = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(w.PL) * 4;
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
+#if RF_GL_HALF_MINB >= 3
     const size_t smem_ih = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(PLh) * 4;                       // half-rate CTAs
     const size_t smem_fh = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(RF_PW / 2 + (h.H + 1) / 2 + 2) * 4;
+#else       // A/B build: the footprint of the merged launch (2 CTAs per SM)
+    const size_t smem_ih = smem_i, smem_fh = smem_f;
+#endif
     const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
     const dim3 grid_a2((dg.nxo + 2 * dg.E + 255) / 256, B);
     k_envelope<<<(L + 255) / 256, 256, 0, st>>>(p->d_win2, T, h.H, h.W, L, w.env);

@@ -80,7 +80,7 @@ RF_HD void rf_pass_a(int tid, int nt, rf_c32* V) {
     }
 }
 
-// radix-49 over c, SEVEN threads per 49-point transform (work item w = transform * 7 + j), two phases with a barrier
+// radix-49 over c, SEVEN threads per 49-point transform (work item w = j * transforms + transform), two phases with a barrier
 // in between, both in place and free of cross-thread hazards:
 //   column phase (thread j = c2): DFT7 over the stride-7 elements p[7 c1 + j], twiddle w49^(k1 j), back to p[7 k1 + j]
 //   row phase    (thread j = k1): DFT7 over the contiguous row p[7 j + c2], back to p[7 j + k2] = X[j + 7 k2]
@@ -88,12 +88,32 @@ RF_HD void rf_pass_a(int tid, int nt, rf_c32* V) {
 // which is what the plan's position tables pp / pp2 point at: rf_pfa_spec_pos);  inverse = row phase (twiddle after the
 // DFT) then column phase: transposed spectral order in, natural time order out.  One thread per transform (the previous
 // form) kept 49 complex values = 98 registers live and left 166 of 256 threads idle for NA = 5.
+#ifndef RF_GL_PASS7
+#define RF_GL_PASS7 1       // 0: the one-thread-per-transform radix-49 pass (A/B builds, scratch/variants)
+#endif
 template <bool INV, int NA, int STEP>
 RF_HD void rf_pass_c7(int tid, int nt, rf_c32* V) {
+#if !RF_GL_PASS7
+    if (STEP == 0) {
+        for (int it = tid; it < 2 * 9 * NA; it += nt) {
+            rf_c32* p = V + it * 49;
+            rf_c32 v[49];
+#pragma unroll
+            for (int c = 0; c < 49; ++c) v[c] = p[c];
+            dft49<INV>(v);
+#pragma unroll
+            for (int c = 0; c < 49; ++c) p[c] = v[7 * (c % 7) + c / 7];
+        }
+    }
+    return;
+#endif
     const float sg = INV ? 1.0f : -1.0f;
     constexpr bool COLUMN = (STEP == 0) != INV;
-    for (int w = tid; w < 2 * 9 * NA * 7; w += nt) {
-        const int it = w / 7, j = w - it * 7;
+    constexpr int NTR = 2 * 9 * NA;         // 49-point transforms in V
+    for (int w = tid; w < NTR * 7; w += nt) {
+        // lanes run over the transforms (stride 49 elements = 1 mod 16 eight-byte banks: conflict-free in both phases) and
+        // j is uniform over (most of) a warp, so the twiddle reads below are constant-cache broadcasts
+        const int j = w / NTR, it = w - j * NTR;
         rf_c32* p = V + it * 49;  // s*W + ab*49 == it*49
         rf_c32 v[7];
         if (COLUMN) {

@@ -59,6 +59,11 @@ inline int rf_pfa_n_of(int a, int b, int c) { return (441 * a + 490 * b + 90 * c
 inline int rf_pfa_m_of(int a, int b, int c) { return (441 * a + 3430 * b + 540 * c) % RF_W; }
 inline int rf_pfa_pos(int a, int b, int c) { return a * 441 + b * 49 + c; }
 // spectral side: the 7-thread radix-49 pass leaves output c of a 49-block at the transposed slot 7 (c % 7) + c / 7
-inline int rf_pfa_spec_pos(int a, int b, int c) { return a * 441 + b * 49 + 7 * (c % 7) + c / 7; }
+#ifndef RF_GL_PASS7
+#define RF_GL_PASS7 1
+#endif
+inline int rf_pfa_spec_pos(int a, int b, int c) {
+    return RF_GL_PASS7 ? a * 441 + b * 49 + 7 * (c % 7) + c / 7 : a * 441 + b * 49 + c;
+}
 // decimated grid 5 x 9 x 49 (2205 points): time-side index u and the same position formula
 inline int rf_pfa2_u_of(int a, int b, int c) { return (441 * a + 245 * b + 45 * c) % 2205; }
