@@ -113,7 +113,12 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
 // only columns [r * BN/2, +BN/2) of the B tile; the leader (rank 0) issues one 256-row MMA per K step that reads both CTAs'
 // shared memory.  Barriers: the TMA loads of both CTAs credit the leader's full[stage]; the leader's MMA commits are
 // multicast to empty[stage] / tmem_full[acc] of both CTAs; both epilogues arrive on the leader's tmem_empty[acc].
-template <int BN, int STAGES, bool PAIR>
+//
+// SLABS = 64-element K slabs per ring stage.  scratch/mma_bench.cu (profiles/r02_mma_issue_rate.txt): with the operands
+// resident and NO data movement, one full-barrier wait + tcgen05 fence + commit per 4 MMAs already costs ~135 cycles of
+// tensor-pipe idle time per round trip (N = 160: 457 cycles per slab against 320 ideal = 70 %; 8 MMAs per round trip:
+// 82 %; 12: 99 %), so a stage carries two (or three) slabs and the issuer commits once per stage.
+template <int BN, int STAGES, bool PAIR, int SLABS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
@@ -127,9 +132,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     constexpr int NBUF = BN == 320 ? 1 : 2;         // TMEM accumulator sets
     constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
     constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;   // powers of two
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_TILE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    uint8_t* sA = smem;                                      // [STAGES][SLABS][A_TILE_BYTES]
+    uint8_t* sB = smem + STAGES * SLABS * A_TILE_BYTES;      // [STAGES][SLABS][B_TILE_BYTES]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SLABS * (A_TILE_BYTES + B_TILE_BYTES));
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;      // [2]
@@ -190,16 +195,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 tb = m_blk / (p.tiles_x * p.tiles_y);
             }
             const int n0 = n_blk * BN + ((PAIR && NI == 1) ? rank * (BN / 2) : 0);      // this CTA's rows of the B tile
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            for (int kbs = kb0; kbs < kb1; kbs += SLABS, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t phase = (it / STAGES) & 1;
+                const int nsl = min(SLABS, kb1 - kbs);          // slabs of this stage (the last stage of a tile may be short)
                 tc::mbar_wait(&empty[stage], phase ^ 1);
-                void* dstA = sA + stage * A_TILE_BYTES;
-                void* dstB = sB + stage * B_TILE_BYTES;
+                // only the leader posts the byte count: the loads of BOTH CTAs are credited to its barrier
+                if (rank == 0) tc::mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * nsl * (A_TILE_BYTES + B_TILE_BYTES));
+                const uint32_t fb = PAIR ? tc::mapa_u32(tc::smem_u32(&full[stage]), 0) : 0;
+              for (int sl = 0; sl < nsl; ++sl) {
+                const int kb = kbs + sl;
+                void* dstA = sA + (stage * SLABS + sl) * A_TILE_BYTES;
+                void* dstB = sB + (stage * SLABS + sl) * B_TILE_BYTES;
                 if constexpr (PAIR) {
-                    // only the leader posts the byte count: the loads of BOTH CTAs are credited to its barrier
-                    if (rank == 0) tc::mbar_expect_tx(&full[stage], 2 * (A_TILE_BYTES + B_TILE_BYTES));
-                    const uint32_t fb = tc::mapa_u32(tc::smem_u32(&full[stage]), 0);
                     if (!p.conv) {
                         tc::tma_load_4d_pair(&mapA0, fb, dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
 #pragma unroll
@@ -222,7 +230,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                                                  n_blk * BN + i * UN + rank * (UN / 2), 0, 0);
                     }
                 } else {
-                    tc::mbar_expect_tx(&full[stage], A_TILE_BYTES + B_TILE_BYTES);
                     if (!p.conv) {
                         tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
                         tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
@@ -239,6 +246,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                         tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, 0, 0);
                     }
                 }
+              }
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -254,13 +262,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 tc::fence_after_sync();
             }
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            for (int kbs = kb0; kbs < kb1; kbs += SLABS, ++it) {
                 const int stage = it % STAGES;
                 const uint32_t phase = (it / STAGES) & 1;
+                const int nsl = min(SLABS, kb1 - kbs);
                 tc::mbar_wait(&full[stage], phase);
                 tc::fence_after_sync();
-                const uint32_t a_base = tc::smem_u32(sA + stage * A_TILE_BYTES);
-                const uint32_t b_base = tc::smem_u32(sB + stage * B_TILE_BYTES);
+              for (int sl = 0; sl < nsl; ++sl) {
+                const int kb = kbs + sl;
+                const uint32_t a_base = tc::smem_u32(sA + (stage * SLABS + sl) * A_TILE_BYTES);
+                const uint32_t b_base = tc::smem_u32(sB + (stage * SLABS + sl) * B_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
@@ -271,6 +282,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                         else tc::mma_f16(d_tmem + i * UN, da, db, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
                 }
+              }
                 if constexpr (PAIR) tc::mma_commit_pair(&empty[stage]);
                 else tc::mma_commit(&empty[stage]);
             }
@@ -537,11 +549,11 @@ struct TcProfile {
 TcProfile g_prof;
 std::mutex g_prof_mu;
 
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, int SLABS>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
            cudaStream_t st) {   // `grid` arrives as (tiles_n, tiles_m, batch) and is flattened to a persistent 1-D grid
-    const size_t smem = static_cast<size_t>(STAGES) * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024;
-    static_assert(STAGES * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024 <= 232448, "shared memory budget");
+    const size_t smem = static_cast<size_t>(STAGES) * SLABS * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024;
+    static_assert(STAGES * SLABS * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024 <= 232448, "shared memory budget");
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -556,7 +568,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         grid = dim3(static_cast<unsigned>(n_tiles < num_sms ? n_tiles : num_sms));
     }
     static rf_dev_once once;
-    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES, PAIR>, int(smem));
+    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES, PAIR, SLABS>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(aerr));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = g_prof.on;
@@ -578,9 +590,9 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        RF_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, PAIR>, a0, a1, b, p));
+        RF_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, PAIR, SLABS>, a0, a1, b, p));
     } else {
-        k_tc_gemm<BN, STAGES, PAIR><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
+        k_tc_gemm<BN, STAGES, PAIR, SLABS><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
     }
     RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
     if (prof) {
@@ -749,8 +761,10 @@ int b_box_rows(const TileCfg& c) { return !c.pair ? c.bn : (c.bn == 320 ? 80 : c
 
 int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, TcParams& p,
              int tiles_m, int nbatch, cudaStream_t st, void* ws, size_t ws_bytes, size_t* query) {
-    // one persistent CTA (or CTA pair) per SM (TPC): 6-8 stage TMA ring, 2 TMEM accumulators
+    // one persistent CTA (or CTA pair) per SM (TPC): TMA ring of 3-4 stages x 2 K slabs, 2 TMEM accumulators
     const int bn = cfg.bn;
+    const char* env_slabs = getenv("RF_GEMM_SLABS");          // A/B: 1 = one slab per stage (round-1 ring), 3 = three (BN 160)
+    const int slabs = env_slabs ? atoi(env_slabs) : 2;
     p.tiles_n = (N + bn - 1) / bn;
     if (cfg.pair) {
         if (query) {
@@ -762,10 +776,16 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
         p.kb_per_split = p.num_kb;
         p.ws = nullptr;
         dim3 grid(p.tiles_n, p.tiles_m, nbatch);
-        if (bn == 320) return launch<320, 6, true>(a0, a1, b, p, grid, st);
-        if (bn == 256) return launch<256, 6, true>(a0, a1, b, p, grid, st);
-        if (bn == 160) return launch<160, 8, true>(a0, a1, b, p, grid, st);
-        return launch<128, 8, true>(a0, a1, b, p, grid, st);
+        if (slabs == 1) {
+            if (bn == 320) return launch<320, 6, true, 1>(a0, a1, b, p, grid, st);
+            if (bn == 256) return launch<256, 6, true, 1>(a0, a1, b, p, grid, st);
+            if (bn == 160) return launch<160, 8, true, 1>(a0, a1, b, p, grid, st);
+            return launch<128, 8, true, 1>(a0, a1, b, p, grid, st);
+        }
+        if (bn == 320) return launch<320, 3, true, 2>(a0, a1, b, p, grid, st);
+        if (bn == 256) return launch<256, 3, true, 2>(a0, a1, b, p, grid, st);
+        if (bn == 160) return launch<160, 4, true, 2>(a0, a1, b, p, grid, st);
+        return launch<128, 4, true, 2>(a0, a1, b, p, grid, st);
     }
     p.tiles_m = tiles_m;
     // split-K: non-batched, plain or SiLU epilogue, 16-byte aligned fp16/fp32 rows
@@ -796,9 +816,17 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
     }
     dim3 grid(p.tiles_n * p.splits, tiles_m, nbatch);
     int rc;
-    if (bn == 160) rc = launch<160, 6, false>(a0, a1, b, p, grid, st);   // N = 320-type layers: two exact 160-column tiles
-    else if (bn == 128) rc = launch<128, 6, false>(a0, a1, b, p, grid, st);
-    else rc = launch<64, 8, false>(a0, a1, b, p, grid, st);
+    if (slabs == 1) {
+        if (bn == 160) rc = launch<160, 6, false, 1>(a0, a1, b, p, grid, st);   // N = 320-type layers: two exact 160-column tiles
+        else if (bn == 128) rc = launch<128, 6, false, 1>(a0, a1, b, p, grid, st);
+        else rc = launch<64, 8, false, 1>(a0, a1, b, p, grid, st);
+    } else if (slabs == 3 && bn == 160) {
+        rc = launch<160, 2, false, 3>(a0, a1, b, p, grid, st);
+    } else {
+        if (bn == 160) rc = launch<160, 3, false, 2>(a0, a1, b, p, grid, st);
+        else if (bn == 128) rc = launch<128, 3, false, 2>(a0, a1, b, p, grid, st);
+        else rc = launch<64, 4, false, 2>(a0, a1, b, p, grid, st);
+    }
     if (rc || p.splits == 1) return rc;
     const long work = rows * (N / 8);
     const unsigned blocks = static_cast<unsigned>(std::min<long>((work + 255) / 256, 8L * num_sms_cached()));

@@ -73,14 +73,14 @@ void run(const char* name) {
 // Same MMA stream, but driven through the real kernel's producer/consumer barrier ring WITHOUT any data movement: a
 // "producer" thread waits empty[s] and arrives full[s]; the issuer waits full[s], issues 4 MMAs, commits to empty[s].
 // Cycles per K slab above 4 * N/2 are the cost of the synchronisation structure itself.
-template <int N, int STAGES>
+template <int N, int STAGES, int SLABS, bool RING>
 __global__ void __launch_bounds__(128, 1) k_ring(int iters, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full[STAGES], empty[STAGES], done;
     __shared__ uint32_t slot;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * 16384;
-    for (int i = threadIdx.x; i < (STAGES * (16384 + N * 128)) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    uint8_t* sB = smem + STAGES * SLABS * 16384;
+    for (int i = threadIdx.x; i < (STAGES * SLABS * (16384 + N * 128)) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(&done, 1);
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128, 1) k_ring(int iters, long long* out) {
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = slot;
-    if (threadIdx.x == 64) {            // producer (no TMA)
+    if (threadIdx.x == 64 && RING) {            // producer (no TMA)
         for (int it = 0; it < iters; ++it) {
             const int st = it % STAGES;
             tc::mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
@@ -103,12 +103,17 @@ __global__ void __launch_bounds__(128, 1) k_ring(int iters, long long* out) {
         long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
             const int st = it % STAGES;
-            tc::mbar_wait(&full[st], (it / STAGES) & 1);
-            tc::fence_after_sync();
-            const uint32_t a = tc::smem_u32(sA + st * 16384), b = tc::smem_u32(sB + st * N * 128);
+            if (RING) {
+                tc::mbar_wait(&full[st], (it / STAGES) & 1);
+                tc::fence_after_sync();
+            }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                tc::mma_f16(tmem, tc::make_desc_sw128(a + k * 32), tc::make_desc_sw128(b + k * 32), idesc, 1u);
+            for (int sl = 0; sl < SLABS; ++sl) {
+                const uint32_t a = tc::smem_u32(sA + (st * SLABS + sl) * 16384), b = tc::smem_u32(sB + (st * SLABS + sl) * N * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::mma_f16(tmem, tc::make_desc_sw128(a + k * 32), tc::make_desc_sw128(b + k * 32), idesc, 1u);
+            }
             tc::mma_commit(&empty[st]);
         }
         tc::mma_commit(&done);
@@ -120,26 +125,34 @@ __global__ void __launch_bounds__(128, 1) k_ring(int iters, long long* out) {
     if (threadIdx.x < 32) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int N, int STAGES>
+template <int N, int STAGES, int SLABS = 1, bool RING = true>
 void run_ring() {
     long long* d;
     cudaMalloc(&d, 16);
-    const size_t smem = STAGES * (16384 + N * 128) + 1024;
-    cudaFuncSetAttribute(k_ring<N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int rep = 0; rep < 2; ++rep) k_ring<N, STAGES><<<148, 128, smem>>>(4000, d);
+    const size_t smem = STAGES * SLABS * (16384 + N * 128) + 1024;
+    cudaFuncSetAttribute(k_ring<N, STAGES, SLABS, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; ++rep) k_ring<N, STAGES, SLABS, RING><<<148, 128, smem>>>(4000, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2] = {0, 0};
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("barrier ring, no data movement  N=%3d stages=%d : %7.1f cyc per K slab (4 MMAs, ideal %5.1f) -> %5.1f %% of peak [%s]\n", N, STAGES,
-           double(h[0]) / h[1], 2.0 * N, 100.0 * 2.0 * N / (double(h[0]) / h[1]), cudaGetErrorString(e));
+    printf("%s, no data movement  N=%3d stages=%d, %d MMAs per stage : %7.1f cyc per stage (ideal %6.1f) -> %5.1f %% of peak [%s]\n",
+           RING ? "barrier ring" : "commit only ", N, STAGES, 4 * SLABS, double(h[0]) / h[1], 2.0 * N * SLABS,
+           100.0 * 2.0 * N * SLABS / (double(h[0]) / h[1]), cudaGetErrorString(e));
     cudaFree(d);
 }
 
 int main() {
     run_ring<160, 6>();
+    run_ring<160, 6, 1, false>();
+    run_ring<160, 3, 2>();
+    run_ring<160, 2, 3>();
     run_ring<128, 6>();
+    run_ring<128, 3, 2>();
+    run_ring<128, 6, 1, false>();
     run_ring<256, 4>();
     run_ring<160, 2>();
+    run_ring<160, 3>();
+    run_ring<160, 4>();
     run<128, 1>("single accumulator");
     run<128, 2>("two accumulators");
     run<160, 1>("single accumulator");
