@@ -298,7 +298,8 @@ def main() -> None:
     clips = B * world
     value = clips / (ms_step / 1e3)
     pk = peaks()
-    names = ["k_istft_chunk", "k_ola_assemble", "k_stft_pair"]
+    names = ["k_istft_chunk", "k_ola_assemble", "k_stft_pair"]     # kernel classes: iSTFT (k_istft_edge + k_istft_half in the loop,
+    # k_istft_chunk for the last full-rate pass), overlap-add assembly, STFT (k_stft_edge + k_stft_half)
     per_launch_bytes = [B * 12.0 * F_LIVE * T_FRAMES + B * 4.0 * L_WAVE, 0.0, B * 24.0 * F_LIVE * T_FRAMES + B * 4.0 * L_WAVE]
     dom = int(np.argmax(acc))
     dom_ms = acc[dom] / max(launches[dom], 1)
@@ -663,6 +664,7 @@ def main_clip(args) -> None:
     roofline = {
         "bound": "tensor", "kernel": "k_tc_gemm (tcgen05 GEMM / implicit-GEMM conv)", "achieved": achieved,
         "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "traffic": gemm_traffic(),
+        "traffic_detail": gemm_traffic(detail=True),
         "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
         "kernel_ms_per_step": tc_ms.value, "kernel_launches_per_step": tc_n.value,
         "kernel_flops_per_step": tc_fl.value, "kernel_share_of_step": tc_ms.value / ms_step,
@@ -707,7 +709,7 @@ def main_clip(args) -> None:
         "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * (n_evals * 590 + 400)), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "gpu_launches": int(args.steps * (n_evals * 442 + 400)), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "griffinlim": gl,
     }
     print(json.dumps(line))
@@ -872,19 +874,24 @@ def main_riffuse(args) -> None:
                     "h2d_bytes_per_step": int(rgb.size + 2 * 77 * 4), "d2h_bytes_per_step": int(512 * 512 * 3),
                     "api": "RiffusionPipeline.riffuse(InferenceInput, PIL.Image) -> PIL.Image (tokenise + CLIP text encoder "
                            "(lru-cached per prompt), cached VAE moments of the seed image, generator draws, loop, decode, uint8)"},
-            "gpu_launches": int(args.steps * (n_evals * 600 + 250)), "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "gpu_launches": int(args.steps * (n_evals * 460 + 250)), "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
-def gemm_traffic():
-    """ncu dram__bytes of the tensor-core kernel (profiles/traffic_latest.json, written from the committed ncu capture)"""
+def gemm_traffic(detail: bool = False):
+    """ncu dram__bytes_read + dram__bytes_write of the tensor-core kernel, average per launch over the 236 launches of one
+    CFG evaluation at the benchmarked batch (profiles/traffic_latest.json, from profiles/r02_eval32_launches_dram.csv);
+    detail=True: the whole record (bytes per evaluation, algorithmic bytes)"""
     f = ROOT / "profiles" / "traffic_latest.json"
     try:
-        return json.loads(f.read_text()).get("k_tc_gemm")
+        rec = json.loads(f.read_text()).get("k_tc_gemm")
     except (OSError, ValueError):
         return None
+    if not isinstance(rec, dict):
+        return rec
+    return rec if detail else rec.get("dram_bytes_per_launch_avg")
 
 
 if __name__ == "__main__":
