@@ -118,7 +118,13 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
 // resident and NO data movement, one full-barrier wait + tcgen05 fence + commit per 4 MMAs already costs ~135 cycles of
 // tensor-pipe idle time per round trip (N = 160: 457 cycles per slab against 320 ideal = 70 %; 8 MMAs per round trip:
 // 82 %; 12: 99 %), so a stage carries two (or three) slabs and the issuer commits once per stage.
-template <int BN, int STAGES, bool PAIR, int SLABS>
+//
+// BRES = true (1-SM, K <= BRES_KB slabs, non-batched): B-stationary.  A CTA stays on ONE column block, loads all K slabs of
+// its B tile into shared memory once and streams only A through the ring while it walks the row blocks.  For the K = N = 320
+// projections of the 64x64 level (35 launches per evaluation) the weight tile (100 KB) was re-fetched from L2 for every
+// 128-row block: 180 KB of operands per 1600 cycles of MMA, L2-feed bound at 440-450 TFLOP/s; resident B leaves 80 KB.
+constexpr int BRES_KB = 5;
+template <int BN, int STAGES, bool PAIR, int SLABS, bool BRES = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
@@ -132,21 +138,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     constexpr int NBUF = BN == 320 ? 1 : 2;         // TMEM accumulator sets
     constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
     constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;   // powers of two
+    static_assert(!BRES || !PAIR, "B-stationary mode is a 1-SM mode");
     uint8_t* sA = smem;                                      // [STAGES][SLABS][A_TILE_BYTES]
-    uint8_t* sB = smem + STAGES * SLABS * A_TILE_BYTES;      // [STAGES][SLABS][B_TILE_BYTES]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SLABS * (A_TILE_BYTES + B_TILE_BYTES));
+    uint8_t* sB = smem + STAGES * SLABS * A_TILE_BYTES;      // [STAGES][SLABS][B_TILE_BYTES], BRES: [BRES_KB][B_TILE_BYTES] resident
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * SLABS * A_TILE_BYTES +
+                                                 (BRES ? BRES_KB : STAGES * SLABS) * B_TILE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;      // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* b_full = tmem_empty + 2;         // BRES: the resident B tile has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // PAIR: tiles_m counts 256-row blocks (the host passes ceil(tiles_m / 2)); work units are walked by the pair
     const int tiles_mn = p.tiles_n * p.tiles_m;
     const int n_tiles = tiles_mn * p.batch1 * p.batch2 * p.splits;   // work units (== tiles when splits == 1)
     const int rank = PAIR ? static_cast<int>(tc::cluster_ctarank()) : 0;
-    const int unit0 = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-    const int unit_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+    // BRES: the CTA owns column block nb_fixed and walks row blocks unit = blockIdx.x / tiles_n, + gridDim.x / tiles_n, ...
+    const int nb_fixed = BRES ? static_cast<int>(blockIdx.x) % p.tiles_n : 0;
+    const int unit0 = BRES ? static_cast<int>(blockIdx.x) / p.tiles_n : (PAIR ? blockIdx.x >> 1 : blockIdx.x);
+    const int unit_step = BRES ? static_cast<int>(gridDim.x) / p.tiles_n : (PAIR ? gridDim.x >> 1 : gridDim.x);
+    const int n_units = BRES ? p.tiles_m : n_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -157,6 +169,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             tc::mbar_init(&tmem_full[i], 1);
             tc::mbar_init(&tmem_empty[i], (PAIR ? 2 : 1) * 4 * EPI_SETS);   // one arrival per epilogue warp (of both CTAs)
         }
+        tc::mbar_init(b_full, 1);
         tc::fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -181,8 +194,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------ TMA producer
         int it = 0;
-        for (int unit = unit0; unit < n_tiles; unit += unit_step) {
-            const int tile = unit / p.splits, sp = unit - tile * p.splits;
+        if constexpr (BRES) {      // the whole K extent of this CTA's B tile, once
+            tc::mbar_expect_tx(b_full, p.num_kb * B_TILE_BYTES);
+            for (int kb = 0; kb < p.num_kb; ++kb)
+                tc::tma_load_4d(&mapB, b_full, sB + kb * B_TILE_BYTES, kb * BK, nb_fixed * BN, 0, 0);
+        }
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+            const int tile = BRES ? unit * p.tiles_n + nb_fixed : unit / p.splits, sp = BRES ? 0 : unit - (unit / p.splits) * p.splits;
             const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
             const int m_row = mn / p.tiles_n, n_blk = mn - m_row * p.tiles_n;
@@ -201,7 +219,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 const int nsl = min(SLABS, kb1 - kbs);          // slabs of this stage (the last stage of a tile may be short)
                 tc::mbar_wait(&empty[stage], phase ^ 1);
                 // only the leader posts the byte count: the loads of BOTH CTAs are credited to its barrier
-                if (rank == 0) tc::mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * nsl * (A_TILE_BYTES + B_TILE_BYTES));
+                if (rank == 0)
+                    tc::mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * nsl * (A_TILE_BYTES + (BRES ? 0 : B_TILE_BYTES)));
                 const uint32_t fb = PAIR ? tc::mapa_u32(tc::smem_u32(&full[stage]), 0) : 0;
               for (int sl = 0; sl < nsl; ++sl) {
                 const int kb = kbs + sl;
@@ -232,7 +251,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 } else {
                     if (!p.conv) {
                         tc::tma_load_4d(&mapA0, &full[stage], dstA, kb * BK, m_blk * BM, b1 * p.a_m1, b2 * p.a_m2);
-                        tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
+                        if (!BRES) tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
                     } else {
                         const int kct = p.kc1 + p.kc2;
                         const int tap = kb / kct, kc = kb - tap * kct;
@@ -243,7 +262,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                             tc::tma_load_4d(&mapA0, &full[stage], dstA, kc * BK, x0, y0, tb * p.bb);
                         else
                             tc::tma_load_4d(&mapA1, &full[stage], dstA, (kc - p.kc1) * BK, x0, y0, tb * p.bb);
-                        tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, 0, 0);
+                        if (!BRES) tc::tma_load_4d(&mapB, &full[stage], dstB, kb * BK, n0, 0, 0);
                     }
                 }
               }
@@ -253,8 +272,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
         constexpr uint32_t idesc = tc::make_idesc_f16(PAIR ? 2 * BM : BM, UN);
         int it = 0, lt = 0;
-        for (int unit = unit0; unit < n_tiles; unit += unit_step, ++lt) {
-            const int sp = unit % p.splits;
+        if constexpr (BRES) {
+            tc::mbar_wait(b_full, 0);
+            tc::fence_after_sync();
+        }
+        for (int unit = unit0; unit < n_units; unit += unit_step, ++lt) {
+            const int sp = BRES ? 0 : unit % p.splits;
             const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             const int acc = lt % NBUF, use = lt / NBUF;
             if (use >= 1) {                                  // the epilogue must have drained this accumulator
@@ -271,7 +294,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
               for (int sl = 0; sl < nsl; ++sl) {
                 const int kb = kbs + sl;
                 const uint32_t a_base = tc::smem_u32(sA + (stage * SLABS + sl) * A_TILE_BYTES);
-                const uint32_t b_base = tc::smem_u32(sB + (stage * SLABS + sl) * B_TILE_BYTES);
+                const uint32_t b_base = tc::smem_u32(sB + (BRES ? kb : stage * SLABS + sl) * B_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = tc::make_desc_sw128(a_base + k * 32);
@@ -308,8 +331,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         };
         int lt = 0;
         const uint32_t tmem_empty_leader = PAIR ? tc::mapa_u32(tc::smem_u32(&tmem_empty[0]), 0) : 0;
-        for (int unit = unit0; unit < n_tiles; unit += unit_step, ++lt) {
-            const int tile = unit / p.splits, sp = unit - tile * p.splits;
+        for (int unit = unit0; unit < n_units; unit += unit_step, ++lt) {
+            const int tile = BRES ? unit * p.tiles_n + nb_fixed : unit / p.splits, sp = BRES ? 0 : unit - (unit / p.splits) * p.splits;
             const int acc = lt % NBUF;
             const int z = tile / tiles_mn, mn = tile - z * tiles_mn;
             const int m_row = mn / p.tiles_n, n_blk = mn - m_row * p.tiles_n;
@@ -549,11 +572,12 @@ struct TcProfile {
 TcProfile g_prof;
 std::mutex g_prof_mu;
 
-template <int BN, int STAGES, bool PAIR, int SLABS>
+template <int BN, int STAGES, bool PAIR, int SLABS, bool BRES = false>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid,
            cudaStream_t st) {   // `grid` arrives as (tiles_n, tiles_m, batch) and is flattened to a persistent 1-D grid
-    const size_t smem = static_cast<size_t>(STAGES) * SLABS * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024;
-    static_assert(STAGES * SLABS * (A_TILE_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024 <= 232448, "shared memory budget");
+    constexpr size_t smem = static_cast<size_t>(STAGES) * SLABS * A_TILE_BYTES +
+                            static_cast<size_t>(BRES ? BRES_KB : STAGES * SLABS) * ((PAIR ? BN / 2 : BN) * BK * 2) + 1024;
+    static_assert(smem <= 232448, "shared memory budget");
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -564,11 +588,13 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     if (PAIR) {   // one CTA pair per TPC
         const int pairs = num_sms / 2;
         grid = dim3(static_cast<unsigned>(2 * (n_tiles < pairs ? n_tiles : pairs)));
+    } else if (BRES) {   // every CTA is bound to one column block: a multiple of tiles_n CTAs
+        grid = dim3(static_cast<unsigned>((num_sms / p.tiles_n) * p.tiles_n));
     } else {
         grid = dim3(static_cast<unsigned>(n_tiles < num_sms ? n_tiles : num_sms));
     }
     static rf_dev_once once;
-    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES, PAIR, SLABS>, int(smem));
+    const cudaError_t aerr = rf_set_smem_once(once, k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(aerr));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = g_prof.on;
@@ -590,9 +616,9 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        RF_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, PAIR, SLABS>, a0, a1, b, p));
+        RF_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES>, a0, a1, b, p));
     } else {
-        k_tc_gemm<BN, STAGES, PAIR, SLABS><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
+        k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
     }
     RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
     if (prof) {
@@ -604,7 +630,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         const double m = p.conv ? static_cast<double>(p.Bn) * p.Ho * p.Wo : static_cast<double>(p.M) * p.batch1 * p.batch2;
         g_prof.flops += 2.0 * m * p.N * p.K;
         g_prof.recs.push_back({p.conv, p.conv ? p.Bn * p.Ho * p.Wo : p.M, p.N, p.K, p.batch1 * p.batch2, p.splits,
-                               PAIR ? -BN : BN});
+                               PAIR ? -BN : (BRES ? 1000 + BN : BN)});
     }
     return RF_OK;
 }
@@ -816,6 +842,11 @@ int dispatch(int N, const TileCfg cfg, const CUtensorMap& a0, const CUtensorMap&
     }
     dim3 grid(p.tiles_n * p.splits, tiles_m, nbatch);
     int rc;
+    const char* env_bres = getenv("RF_GEMM_BRES");
+    if (bn == 160 && nbatch == 1 && p.splits == 1 && p.num_kb <= BRES_KB && p.tiles_n <= 8 &&
+        static_cast<long>(tiles_m) * p.tiles_n >= 4L * num_sms_cached() && !(env_bres && env_bres[0] == '0')) {
+        return launch<160, 3, false, 2, true>(a0, a1, b, p, grid, st);       // B-stationary (K <= 320, N = 160 k)
+    }
     if (slabs == 1) {
         if (bn == 160) rc = launch<160, 6, false, 1>(a0, a1, b, p, grid, st);   // N = 320-type layers: two exact 160-column tiles
         else if (bn == 128) rc = launch<128, 6, false, 1>(a0, a1, b, p, grid, st);

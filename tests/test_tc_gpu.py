@@ -278,3 +278,40 @@ def test_fused_upsample_conv_matches_torch(native_lib, B, H, W, Cin, Cout):
     _close(got, ref, tol=3e-3)             # + one fp16 rounding of the pre-summed phase weights
     unfused = ops.conv2d(ops.upsample2x(x), ops.pack_conv_weight(w), bias=bias)
     assert float((got.float() - unfused.float()).norm() / unfused.float().norm()) < 1e-3
+
+
+def test_b_stationary_gemm_matches_torch_and_streaming_kernel(native_lib):
+    """K <= 320, N = 320 / 480 problems with many row blocks run B-stationary (the CTA keeps its weight tile in shared
+    memory and streams only A): GEMM with bias / residual / SiLU, ragged M, K = 192 (3 slabs), and a 1x1 convolution;
+    vs torch and vs the streaming kernel (RF_GEMM_BRES=0)"""
+    import os
+
+    import torch.nn.functional as F
+
+    from riffusion import tc_ops as ops
+
+    try:
+        for (M, N, K) in ((128 * 300 + 77, 320, 320), (45000, 480, 192), (128 * 296, 320, 256)):
+            torch.manual_seed(M + N + K)
+            a = (torch.randn(M, K, device="cuda") * 0.5).half()
+            b = (torch.randn(N, K, device="cuda") * 0.5).half()
+            bias = torch.randn(N, device="cuda").half()
+            res = torch.randn(M, N, device="cuda").half()
+            ref = a.float() @ b.float().t()
+            os.environ.pop("RF_GEMM_BRES", None)
+            g1 = ops.gemm(a, b, bias=bias, residual=res).reshape(M, N)
+            g2 = ops.gemm(a, b, bias=bias, act=ops.ACT_SILU).reshape(M, N)
+            _close(g1, ref + bias.float() + res.float())
+            _close(g2, F.silu(ref + bias.float()))
+            os.environ["RF_GEMM_BRES"] = "0"
+            s1 = ops.gemm(a, b, bias=bias, residual=res).reshape(M, N)
+            assert torch.equal(g1, s1), (M, N, K)            # same slab order, same accumulation
+        os.environ.pop("RF_GEMM_BRES", None)
+        x = (torch.randn(10, 64, 64, 320, device="cuda") * 0.5).half()
+        w = (torch.randn(320, 320, 1, 1, device="cuda") * 320 ** -0.5).half()
+        bias = torch.randn(320, device="cuda").half()
+        ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias.float()).permute(0, 2, 3, 1)
+        got = ops.conv2d(x, ops.pack_conv_weight(w), bias=bias)
+        _close(got, ref)
+    finally:
+        os.environ.pop("RF_GEMM_BRES", None)
