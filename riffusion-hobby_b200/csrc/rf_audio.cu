@@ -13,6 +13,7 @@
 #include "rf_generic.cuh"
 #include "rf_gl_phases.cuh"
 #include "rf_plan.h"
+#include "rf_tc.cuh"
 
 // ---------------------------------------------------------------------------------------
 // error plumbing
@@ -34,9 +35,15 @@ struct rf_plan {
     std::mutex mu;
     bool uploaded = false;
     int device = -1;
-    rf_c32* d_wt_fwd = nullptr;
-    rf_c32* d_wt_inv = nullptr;
-    uint32_t* d_pp = nullptr;
+    struct dev_tabs {              // device copies of rf_bin_tabs
+        rf_f4* wg_fwd = nullptr;
+        rf_f4* wg_inv = nullptr;
+        uint32_t* bt = nullptr;
+        rf_f4* ab_inv = nullptr;
+        rf_f4* ab_fwd = nullptr;
+        uint16_t* zpos = nullptr;
+    } d10, d5;
+    float* d_zero_row = nullptr;   // [n_live] zeros                     // d5: decimated-loop tables (null when not eligible)
     int32_t* d_bins = nullptr;
     int32_t* d_jofk = nullptr;
     float* d_win2 = nullptr;
@@ -47,10 +54,6 @@ struct rf_plan {
     int32_t* d_binrow_m = nullptr;
     float* d_binrow_w = nullptr;
     double* d_thomas = nullptr;  // [3][n_mels]: sub, cprime, inv_den
-    rf_c32* d_wt2_fwd = nullptr;  // decimated-loop tables (null when not eligible)
-    rf_c32* d_wt2_inv = nullptr;
-    uint32_t* d_pp2 = nullptr;
-    rf_c32* d_ph_odd = nullptr;
     float* d_window = nullptr;    // generic engine
     rf_c32* d_roots2 = nullptr;
     rf_c32* d_rootsN = nullptr;
@@ -64,6 +67,16 @@ static cudaError_t upload(rf_plan* p, T** dst, const void* src, size_t count) {
     if (e != cudaSuccess) return e;
     p->owned.push_back(*dst);
     if (count) e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static cudaError_t upload_tabs(rf_plan* p, rf_plan::dev_tabs* d, const rf_bin_tabs& t) {
+    cudaError_t e = upload(p, &d->wg_fwd, t.wg_fwd.data(), t.wg_fwd.size() / 4);
+    if (e == cudaSuccess) e = upload(p, &d->wg_inv, t.wg_inv.data(), t.wg_inv.size() / 4);
+    if (e == cudaSuccess) e = upload(p, &d->bt, t.bt.data(), t.bt.size());
+    if (e == cudaSuccess) e = upload(p, &d->ab_inv, t.ab_inv.data(), t.ab_inv.size() / 4);
+    if (e == cudaSuccess) e = upload(p, &d->ab_fwd, t.ab_fwd.data(), t.ab_fwd.size() / 4);
+    if (e == cudaSuccess) e = upload(p, &d->zpos, t.zpos.data(), t.zpos.size());
     return e;
 }
 
@@ -92,9 +105,11 @@ static int rf_plan_upload(rf_plan* p) {
         return rf_fail(RF_ERR_CUDA, std::string("rf_b200: kernels are built for sm_100a only; device is ") +
                                         prop.name);
     const rf_plan_host& h = p->h;
-    RF_CUDA_TRY(upload(p, &p->d_wt_fwd, h.wt_fwd.data(), h.wt_fwd.size() / 2));
-    RF_CUDA_TRY(upload(p, &p->d_wt_inv, h.wt_inv.data(), h.wt_inv.size() / 2));
-    RF_CUDA_TRY(upload(p, &p->d_pp, h.pp.data(), h.pp.size()));
+    RF_CUDA_TRY(upload_tabs(p, &p->d10, h.t10));
+    {
+        const std::vector<float> zr(h.n_live, 0.f);
+        RF_CUDA_TRY(upload(p, &p->d_zero_row, zr.data(), zr.size()));
+    }
     RF_CUDA_TRY(upload(p, &p->d_bins, h.bins.data(), h.bins.size()));
     RF_CUDA_TRY(upload(p, &p->d_jofk, h.jofk.data(), h.jofk.size()));
     std::vector<float> w2(h.W);
@@ -113,12 +128,7 @@ static int rf_plan_upload(rf_plan* p) {
         th[2 * h.n_mels + i] = h.thomas[h.n_mels + i];  // inv_den
     }
     RF_CUDA_TRY(upload(p, &p->d_thomas, th.data(), th.size()));
-    if (h.decimate) {
-        RF_CUDA_TRY(upload(p, &p->d_wt2_fwd, h.wt2_fwd.data(), h.wt2_fwd.size() / 2));
-        RF_CUDA_TRY(upload(p, &p->d_wt2_inv, h.wt2_inv.data(), h.wt2_inv.size() / 2));
-        RF_CUDA_TRY(upload(p, &p->d_pp2, h.pp2.data(), h.pp2.size()));
-        RF_CUDA_TRY(upload(p, &p->d_ph_odd, h.ph_odd.data(), h.ph_odd.size() / 2));
-    }
+    if (h.decimate) RF_CUDA_TRY(upload_tabs(p, &p->d5, h.t5));
     if (h.generic) {
         RF_CUDA_TRY(upload(p, &p->d_window, h.window.data(), h.window.size()));
         RF_CUDA_TRY(upload(p, &p->d_roots2, h.roots2.data(), h.roots2.size() / 2));
@@ -184,6 +194,13 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
     else if (s == "pp2") { src = h.pp2.data(); n = h.pp2.size() * 4; }
     else if (s == "wt2_fwd") { src = h.wt2_fwd.data(); n = h.wt2_fwd.size() * 4; }
     else if (s == "wt2_inv") { src = h.wt2_inv.data(); n = h.wt2_inv.size() * 4; }
+    else if (s == "bt") { src = h.t10.bt.data(); n = h.t10.bt.size() * 4; }
+    else if (s == "ab_inv") { src = h.t10.ab_inv.data(); n = h.t10.ab_inv.size() * 4; }
+    else if (s == "ab_fwd") { src = h.t10.ab_fwd.data(); n = h.t10.ab_fwd.size() * 4; }
+    else if (s == "bt2") { src = h.t5.bt.data(); n = h.t5.bt.size() * 4; }
+    else if (s == "ab2_inv") { src = h.t5.ab_inv.data(); n = h.t5.ab_inv.size() * 4; }
+    else if (s == "ab2_fwd") { src = h.t5.ab_fwd.data(); n = h.t5.ab_fwd.size() * 4; }
+    else if (s == "ph_odd") { src = h.ph_odd.data(); n = h.ph_odd.size() * 4; }
     else if (s == "pinv") {
         // dense min-norm operator P = fb (fb^T fb)^{-1}, built column by column with the
         // same Thomas factors the kernel uses (fp64), for tests
@@ -243,16 +260,16 @@ __device__ __forceinline__ void istft_chunk_body(unsigned char* smem_raw, const 
     for (int pr = 0; 2 * pr < nf; ++pr) {
         const int t0 = f0 + 2 * pr;
         const bool has1 = (2 * pr + 1) < nf;
-        rf_istft_zero<NA>(tid, RF_NT, V);
-        __syncthreads();
+        rf_istft_zero<NA>(tid, RF_NT, V, tb, g);
+        if (NA == 10) __syncthreads();   // NA = 5 clears only slots the load below does not write
         rf_istft_in in;
         const size_t o0 = (static_cast<size_t>(b) * T + t0) * row;
         in.S0 = S + o0;
         in.cur0 = cur + o0;
         in.prev0 = prev ? prev + o0 : nullptr;
-        in.S1 = has1 ? S + o0 + row : nullptr;
-        in.cur1 = cur + o0 + row;
-        in.prev1 = prev ? prev + o0 + row : nullptr;
+        in.S1 = has1 ? S + o0 + row : tb.zero_row;        // no second frame: zero magnitudes on frame t0's own rows
+        in.cur1 = cur + o0 + (has1 ? row : 0);
+        in.prev1 = prev ? prev + o0 + (has1 ? row : 0) : nullptr;
         in.mode = mode;
         in.momentum = momentum;
         rf_istft_load<NA>(tid, RF_NT, V, tb, j0, j1, in);
@@ -347,6 +364,31 @@ __global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float
     }
 }
 
+// 1-D TMA bulk copy of n floats starting at src (any 4-byte alignment) into shared memory: the copy starts at the enclosing
+// 16-byte boundary and is rounded up to 16 bytes — the caller guarantees those few extra bytes are readable — and lands at
+// xs_al (16-byte aligned).  Returns the shared-memory address of src[0].  Ends with every thread past the mbarrier wait.
+__device__ __forceinline__ float* stage_bulk(float* xs_al, uint64_t* bar, const float* src, int n) {
+    const uint64_t a = reinterpret_cast<uint64_t>(src);
+    const uint32_t shift = static_cast<uint32_t>(a & 15u);
+    const uint32_t nbytes = (shift + static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc::mbar_expect_tx(bar, nbytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         tc::smem_u32(xs_al)),
+                     "l"(a - shift), "r"(nbytes), "r"(tc::smem_u32(bar))
+                     : "memory");
+    }
+    __syncthreads();   // the initialised barrier is visible to every thread before it waits
+    tc::mbar_wait(bar, 0);
+    return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xs_al) + shift);
+}
+// staging area of the half-rate STFT CTAs: W/2 + (hop+1)/2 samples + up to 3 floats of alignment slack, rounded to 16 bytes;
+// the mbarrier sits behind it
+constexpr int RF_XS_HALF_BYTES = ((RF_PW / 2 + (441 + 1) / 2 + 3) * 4 + 15) / 16 * 16;
+
 // ---- STFT of one frame pair, one r-group ------------------------------------------------
 // x_full: waveform holding samples [base, ...) (reflect padding applied on the fly); NA = 5: xo odd samples
 template <int NA>
@@ -359,9 +401,22 @@ __device__ __forceinline__ void stft_pair_body(unsigned char* smem_raw, const rf
     const int tid = threadIdx.x;
     const int t0 = 2 * pr;
     const bool has1 = t0 + 1 < T;
-    if (NA == 10) rf_stage_x(tid, RF_NT, xs, x, L, t0, hop, base);
-    else rf_stage_x_d2(tid, RF_NT, xs, x, L, t0, hop);
-    __syncthreads();
+    if (NA == 10) {
+        rf_stage_x(tid, RF_NT, xs, x, L, t0, hop, base);
+        __syncthreads();
+    } else {
+        // half-rate pairs: the staged samples are nv consecutive odd samples xo[vo0 ..) unless the frame touches the reflect
+        // padding (which the hybrid loop gives to the full-rate edge kernel) -> one 1-D TMA bulk copy instead of a load loop
+        constexpr int nv = RF_PW / 2 + (441 + 1) / 2;
+        const int vo0 = (t0 * hop - RF_PW / 2 - 1) >> 1;
+        if (hop == 441 && vo0 >= 0 && vo0 + nv <= (L - 1) / 2) {
+            uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * W * sizeof(rf_c32) + RF_XS_HALF_BYTES);
+            xs = stage_bulk(xs, bar, x + vo0, nv);
+        } else {
+            rf_stage_x_d2(tid, RF_NT, xs, x, L, t0, hop);
+            __syncthreads();
+        }
+    }
     rf_stft_pass_b<NA>(tid, RF_NT, V, xs, tb, g, has1);
     __syncthreads();
     rf_pass_a<false, NA>(tid, RF_NT, V);
@@ -637,19 +692,18 @@ __global__ void k_wave_to_int16(const float* __restrict__ w, int C, int L, const
 // ---------------------------------------------------------------------------------------
 static rf_gl_tables make_tables(const rf_plan* p, int NA = 10) {
     rf_gl_tables tb;
-    if (NA == 10) {
-        tb.wt_fwd = p->d_wt_fwd;
-        tb.wt_inv = p->d_wt_inv;
-        tb.pp = p->d_pp;
-        tb.ph_odd = nullptr;
-        tb.off1 = p->h.H;
-    } else {
-        tb.wt_fwd = p->d_wt2_fwd;
-        tb.wt_inv = p->d_wt2_inv;
-        tb.pp = p->d_pp2;
-        tb.ph_odd = p->d_ph_odd;
-        tb.off1 = (p->h.H + 1) / 2;
-    }
+    const rf_plan::dev_tabs& d = NA == 10 ? p->d10 : p->d5;
+    const rf_bin_tabs& t = NA == 10 ? p->h.t10 : p->h.t5;
+    tb.wg_fwd = d.wg_fwd;
+    tb.wg_inv = d.wg_inv;
+    tb.bt = d.bt;
+    tb.ab_inv = d.ab_inv;
+    tb.ab_fwd = d.ab_fwd;
+    tb.zpos = d.zpos;
+    tb.nz0 = t.nz[0];
+    tb.nz1 = t.nz[1];
+    tb.zero_row = p->d_zero_row;
+    tb.off1 = NA == 10 ? p->h.H : (p->h.H + 1) / 2;
     tb.n_live = p->h.n_live;
     tb.n_even = p->h.n_even;
     return tb;
@@ -812,7 +866,7 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const int L = h.H * (T - 1);
     // momentum = momentum / (1 + momentum)  (TA/functional/functional.py:300), fp32 like python float->tensor op
     const float m = static_cast<float>(static_cast<double>(momentum_in) / (1.0 + static_cast<double>(momentum_in)));
-    const bool dec = h.decimate && p->use_decimation && p->d_pp2 != nullptr && w.xd != nullptr;
+    const bool dec = h.decimate && p->use_decimation && p->d5.bt != nullptr && w.xd != nullptr;
     const rf_gl_tables tb2 = dec ? make_tables(p, 5) : tb;
     const rf_gl_dec_geom dg = rf_dec_geom(T, RF_CHUNK, h.H, h.W);
     const int PLh = ((RF_CHUNK - 1) * h.H + h.W + 1) / 2;
@@ -820,7 +874,7 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
 #if RF_GL_HALF_MINB >= 3
     const size_t smem_ih = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(PLh) * 4;                       // half-rate CTAs
-    const size_t smem_fh = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(RF_PW / 2 + (h.H + 1) / 2 + 2) * 4;
+    const size_t smem_fh = 2 * (RF_PW / 2) * sizeof(rf_c32) + RF_XS_HALF_BYTES + 16;   // + mbarrier of the bulk copy
 #else       // A/B build: the footprint of the merged launch (2 CTAs per SM)
     const size_t smem_ih = smem_i, smem_fh = smem_f;
 #endif

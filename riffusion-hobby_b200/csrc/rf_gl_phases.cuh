@@ -41,26 +41,36 @@ template <int NA> struct rf_geom {
     static constexpr int B_ITERS = (B_ITEMS + RF_NT - 1) / RF_NT;
 };
 
+struct alignas(16) rf_f4 {
+    float x, y, z, w;
+};
+
+// Tables of one prime-factor grid (rf_bin_tabs in rf_plan.h holds the host copies and the exact definitions)
 struct rf_gl_tables {
-    const rf_c32* wt_fwd;  // [2 parities][4][9][49][NA]  window x modulation, index (par*4 + r)*W + b*49*NA + c*NA + a
-    const rf_c32* wt_inv;  // same layout (parity 1 only exists for NA = 5)
-    const uint32_t* pp;    // [n_live] r | idx<<2 | idx2<<15 | (k&7)<<28  (positions for this NA)
-    const rf_c32* ph_odd;  // NA = 5: exp(-2 pi i k/N) per live bin (the odd-sample frame of a pair), else null
+    const rf_f4* wg_fwd;   // [2 groups][9][49][NA][NP]  window x modulation of the group's two r: (w_r0, w_r1), per sample parity
+    const rf_f4* wg_inv;   // same layout (NP = 2 parities for NA = 5, else 1)
+    const uint32_t* bt;    // [n_live] V offset of the bin | V offset of its Hermitian partner << 14 | self-paired << 31
+    const rf_f4* ab_inv;   // [n_live] (alpha, beta):  Z[k] = alpha C0 + beta C1,  Z[N-k] = conj(alpha C0 - beta C1)
+    const rf_f4* ab_fwd;   // [n_live] (gamma, delta): X_t[k] = gamma (Z[k] + conj Z[N-k]),  X_t+1[k] = delta (Z[k] - conj Z[N-k])
+    const uint16_t* zpos;  // V offsets that no bin of the group writes: nz0 entries of group 0, then nz1 of group 1
+    const float* zero_row; // [n_live] zeros: the magnitudes of a frame that does not exist (odd frame count)
+    int nz0, nz1;
     int n_live;
     int n_even;
     int off1;              // offset of frame t0+1 in the staged sample buffer: hop (NA = 10) or (hop+1)/2 (NA = 5)
 };
 
-// phase factor exp(-2 pi i * 3k/8) (frame offset (N-W)/2 = 3N/8), from k & 7, branch-free
-RF_HD rf_c32 rf_phase8(int k7) {
-    const float h = 0.70710678118654752440f;
-    const int q = (3 * k7) & 7;  // angle = -pi q / 4
-    const float mc = (q & 1) ? h : ((q & 2) ? 0.f : 1.f);
-    const float ms = (q & 1) ? h : ((q & 2) ? 1.f : 0.f);
-    const bool neg_c = ((q - 3) & 7) < 3;  // q in {3,4,5}
-    const bool neg_s = q >= 5;             // q in {5,6,7}
-    return c_make(neg_c ? -mc : mc, neg_s ? ms : -ms);
+// streaming (evict-first) loads for the spectra, which are read once per launch: the per-bin tables stay in L1
+#if defined(__CUDA_ARCH__)
+RF_HD float rf_ld_stream(const float* p) { return __ldcs(p); }
+RF_HD rf_c32 rf_ld_stream(const rf_c32* p) {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    return c_make(v.x, v.y);
 }
+#else
+RF_HD float rf_ld_stream(const float* p) { return *p; }
+RF_HD rf_c32 rf_ld_stream(const rf_c32* p) { return *p; }
+#endif
 
 // ------------------------------------------------------------------ shared passes
 // radix-10 over a: items (s, b, c); lanes run over consecutive positions
@@ -145,12 +155,9 @@ template <int NA>
 RF_HD void rf_stft_pass_b(int tid, int nt, rf_c32* V, const float* xs, const rf_gl_tables& tb, int g,
                           bool has1) {
     constexpr int W = rf_geom<NA>::W, SB = rf_geom<NA>::SB, SC = rf_geom<NA>::SC;
-    const int r0 = g ? 1 : 0, r1 = g ? 3 : 2;
-    // frame t0 uses the parity-0 tables, frame t0+1 the parity-1 tables (identical for NA = 10)
-    const rf_c32* w00 = tb.wt_fwd + r0 * W;
-    const rf_c32* w01 = tb.wt_fwd + r1 * W;
-    const rf_c32* w10 = tb.wt_fwd + ((NA == 5 ? 4 : 0) + r0) * W;
-    const rf_c32* w11 = tb.wt_fwd + ((NA == 5 ? 4 : 0) + r1) * W;
+    constexpr int NP = NA == 5 ? 2 : 1;
+    // frame t0 uses the parity-0 entries, frame t0+1 the parity-1 entries (one parity for NA = 10)
+    const rf_f4* wg = tb.wg_fwd + static_cast<size_t>(g) * W * NP;
     for (int tau = tid; tau < rf_geom<NA>::B_ITEMS; tau += nt) {
         const int c = tau / NA;
         const int a = tau - c * NA;
@@ -164,12 +171,13 @@ RF_HD void rf_stft_pass_b(int tid, int nt, rf_c32* V, const float* xs, const rf_
             const int ti = b * (49 * NA) + tau;
             if (NA == 10) {
                 const rf_c32 z = c_make(x0, x1);
-                u0[b] = c_mul(z, w00[ti]);
-                u1[b] = c_mul(z, w01[ti]);
+                const rf_f4 f = wg[ti];
+                u0[b] = c_mul(z, c_make(f.x, f.y));
+                u1[b] = c_mul(z, c_make(f.z, f.w));
             } else {   // the two frames of the pair sit on different sample parities: separate window tables
-                const rf_c32 f00 = w00[ti], f01 = w01[ti], f10 = w10[ti], f11 = w11[ti];
-                u0[b] = c_make(x0 * f00.x - x1 * f10.y, x0 * f00.y + x1 * f10.x);   // x0*f00 + i*x1*f10
-                u1[b] = c_make(x0 * f01.x - x1 * f11.y, x0 * f01.y + x1 * f11.x);
+                const rf_f4 f0 = wg[2 * ti], f1 = wg[2 * ti + 1];
+                u0[b] = c_make(x0 * f0.x - x1 * f1.y, x0 * f0.y + x1 * f1.x);   // x0*f00 + i*x1*f10
+                u1[b] = c_make(x0 * f0.z - x1 * f1.w, x0 * f0.w + x1 * f1.z);
             }
         }
         dft9<false>(u0);
@@ -185,41 +193,56 @@ RF_HD void rf_stft_pass_b(int tid, int nt, rf_c32* V, const float* xs, const rf_
 
 // Unpack the pair: X_t[k] and X_{t+1}[k] for the live bins j in [j0, j1) of this group.
 // out0/out1: rows of the [T][n_live] spectrum for frames t0, t0+1 (out1 may be null).
-template <int NA>
-RF_HD void rf_stft_post(int tid, int nt, const rf_c32* V, const rf_gl_tables& tb, int j0, int j1,
-                        rf_c32* out0, rf_c32* out1) {
-    constexpr int W = rf_geom<NA>::W;
-    for (int jb = j0 + tid; jb < j1; jb += nt * RF_LOAD_UNROLL) {
-        uint32_t pw[RF_LOAD_UNROLL];
-        rf_c32 po[RF_LOAD_UNROLL];
+//   X_t[k]   = ph (Z[k] + conj Z[N-k]) / 2 = gamma u,   X_t+1[k] = ph po (Z[k] - conj Z[N-k]) / 2i = delta v
+// (ph = exp(-2 pi i 3k/8): frame offset; po = exp(-2 pi i k/N): the odd-sample frame of a decimated pair)
+template <int NA, bool F1, int U>
+RF_HD void rf_stft_post_batch(int jb, int nt, const rf_c32* V, const rf_gl_tables& tb, rf_c32* out0, rf_c32* out1) {
+    const uint32_t* pbt = tb.bt + jb;
+    const rf_f4* pgd = tb.ab_fwd + jb;
+    rf_c32* o0 = out0 + jb;
+    rf_c32* o1 = F1 ? out1 + jb : nullptr;
+    uint32_t pw[U];
+    rf_f4 gd[U];
 #pragma unroll
-        for (int u = 0; u < RF_LOAD_UNROLL; ++u) {
-            const int j = jb + u * nt;
-            pw[u] = (j < j1) ? tb.pp[j] : 0u;
-            if (NA == 5) po[u] = (j < j1) ? tb.ph_odd[j] : c_make(1.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < RF_LOAD_UNROLL; ++u) {
-            const int j = jb + u * nt;
-            if (j >= j1) continue;
-            const uint32_t p = pw[u];
-            const int r = p & 3, idx = (p >> 2) & 8191, idx2 = (p >> 15) & 8191, k7 = p >> 28;
-            const int s = r >> 1, s2 = ((4 - r) & 3) >> 1;
-            const rf_c32 zk = V[s * W + idx];
-            const rf_c32 zp = V[s2 * W + idx2];
-            const rf_c32 ph = rf_phase8(k7);
-            const rf_c32 g0 = c_make(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-            const rf_c32 g1 = c_make(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
-            out0[j] = c_mul(ph, g0);
-            if (out1) out1[j] = (NA == 5) ? c_mul(c_mul(ph, po[u]), g1) : c_mul(ph, g1);
-        }
+    for (int u = 0; u < U; ++u) {
+        pw[u] = pbt[u * nt];
+        gd[u] = pgd[u * nt];
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const rf_c32 zk = V[pw[u] & 16383u];
+        const rf_c32 zp = V[(pw[u] >> 14) & 16383u];
+        o0[u * nt] = c_mul(c_make(gd[u].x, gd[u].y), c_make(zk.x + zp.x, zk.y - zp.y));
+        if (F1) o1[u * nt] = c_mul(c_make(gd[u].z, gd[u].w), c_make(zk.x - zp.x, zk.y + zp.y));
+    }
+}
+template <int NA, bool F1>
+RF_HD void rf_stft_post_t(int tid, int nt, const rf_c32* V, const rf_gl_tables& tb, int j0, int j1, rf_c32* out0,
+                          rf_c32* out1) {
+    int jb = j0 + tid;
+    for (; jb + 3 * nt < j1; jb += 4 * nt) rf_stft_post_batch<NA, F1, 4>(jb, nt, V, tb, out0, out1);
+    for (; jb + nt < j1; jb += 2 * nt) rf_stft_post_batch<NA, F1, 2>(jb, nt, V, tb, out0, out1);
+    if (jb < j1) rf_stft_post_batch<NA, F1, 1>(jb, nt, V, tb, out0, out1);
+}
+template <int NA>
+RF_HD void rf_stft_post(int tid, int nt, const rf_c32* V, const rf_gl_tables& tb, int j0, int j1, rf_c32* out0,
+                        rf_c32* out1) {
+    if (out1) rf_stft_post_t<NA, true>(tid, nt, V, tb, j0, j1, out0, out1);
+    else rf_stft_post_t<NA, false>(tid, nt, V, tb, j0, j1, out0, out1);
 }
 
 // ------------------------------------------------------------------ inverse (iSTFT)
+// NA = 10: clear V (a barrier must follow).  NA = 5: the live bins and their partners cover all but a few hundred of the
+// 4410 slots, so only the uncovered slots (zpos) are cleared — disjoint from what rf_istft_load writes: no barrier in between.
 template <int NA>
-RF_HD void rf_istft_zero(int tid, int nt, rf_c32* V) {
-    for (int i = tid; i < 2 * rf_geom<NA>::W; i += nt) V[i] = c_make(0.f, 0.f);
+RF_HD void rf_istft_zero(int tid, int nt, rf_c32* V, const rf_gl_tables& tb, int g) {
+    if (NA == 5) {
+        const uint16_t* z = tb.zpos + (g ? tb.nz0 : 0);
+        const int n = g ? tb.nz1 : tb.nz0;
+        for (int i = tid; i < n; i += nt) V[z[i]] = c_make(0.f, 0.f);
+    } else {
+        for (int i = tid; i < 2 * rf_geom<NA>::W; i += nt) V[i] = c_make(0.f, 0.f);
+    }
 }
 
 // Griffin-Lim phase update fused into the load:
@@ -230,15 +253,18 @@ RF_HD void rf_istft_zero(int tid, int nt, rf_c32* V) {
 // own complex abs() is a hypot with a rounding of its own, so neither form is bit-identical to the reference, and a
 // 1-ulp change of a unit phasor is the same size as the rounding differences between any two FFT implementations.
 // |A| < 1e-15 (a bin with no energy) is clamped instead of adding 1e-16: the product with S is noise either way.
-RF_HD rf_c32 rf_gl_coef(int mode, bool use_prev, float S, rf_c32 a, rf_c32 q, float momentum) {
-    if (mode) {
-        if (use_prev) {
+template <int MODE, bool UP>
+RF_HD rf_c32 rf_gl_coef(float S, rf_c32 a, rf_c32 q, float momentum) {
+    if (MODE) {
+        if (UP) {
             a.x = fmaf(-momentum, q.x, a.x);
             a.y = fmaf(-momentum, q.y, a.y);
         }
         const float n2 = fmaxf(fmaf(a.x, a.x, a.y * a.y), 1e-30f);
 #if defined(__CUDA_ARCH__)
-        S *= rsqrtf(n2);
+        float rs;   // n2 >= 1e-30 is a normal number: the flush-to-zero form needs no denormal pre-scaling
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+        S *= rs;
 #else
         S *= 1.0f / sqrtf(n2);
 #endif
@@ -248,7 +274,7 @@ RF_HD rf_c32 rf_gl_coef(int mode, bool use_prev, float S, rf_c32 a, rf_c32 q, fl
 
 struct rf_istft_in {
     const float* S0;      // magnitudes, frame t0   [n_live]
-    const float* S1;      // frame t0+1 or null
+    const float* S1;      // frame t0+1; a chunk that ends on a single frame passes tb.zero_row here (and frame t0's cur / prev rows)
     const rf_c32* cur0;   // R (or A0) rows
     const rf_c32* cur1;
     const rf_c32* prev0;  // previous R rows or null
@@ -257,55 +283,71 @@ struct rf_istft_in {
     float momentum;
 };
 
-// All global loads of a batch of RF_LOAD_UNROLL bins are issued before any is used, so one
-// DRAM latency is paid per batch instead of per bin.
-template <int NA>
-RF_HD void rf_istft_load(int tid, int nt, rf_c32* V, const rf_gl_tables& tb, int j0, int j1,
-                         const rf_istft_in& in) {
-    constexpr int W = rf_geom<NA>::W;
-    const bool f1 = in.S1 != nullptr;
-    const bool up = in.prev0 != nullptr;
-    for (int jb = j0 + tid; jb < j1; jb += nt * RF_LOAD_UNROLL) {
-        uint32_t pw[RF_LOAD_UNROLL];
-        float s0[RF_LOAD_UNROLL], s1[RF_LOAD_UNROLL];
-        rf_c32 a0[RF_LOAD_UNROLL], a1[RF_LOAD_UNROLL], q0[RF_LOAD_UNROLL], q1[RF_LOAD_UNROLL], po[RF_LOAD_UNROLL];
+// Coefficients of the packed pair, per live bin k of the group (C0, C1 = the two frames' Griffin-Lim coefficients):
+//   Z[k] = conj(ph) (C0 + i C1') = alpha C0 + beta C1,   Z[N-k] = ph (conj C0 + i conj C1') = conj(alpha C0 - beta C1)
+// with C1' = C1 conj(po); alpha, beta are per-bin constants (rf_bin_tabs), so the phase factors cost two complex products.
+// All global loads of a batch of RF_LOAD_UNROLL bins are issued before any is used, so one DRAM latency is paid per
+// batch instead of per bin.  MODE / UP (update mode, momentum term present) are uniform over a launch and compiled out.
+template <int NA, int MODE, bool UP, int U>
+RF_HD void rf_istft_load_batch(int jb, int nt, rf_c32* V, const rf_gl_tables& tb, const rf_istft_in& in) {
+    // bins jb, jb + nt, ..: one base pointer per array, the slots are constant offsets from it
+    const uint32_t* pbt = tb.bt + jb;
+    const rf_f4* pab = tb.ab_inv + jb;
+    const float* pS0 = in.S0 + jb;
+    const rf_c32* pA0 = in.cur0 + jb;
+    const rf_c32* pQ0 = UP ? in.prev0 + jb : nullptr;
+    const float* pS1 = in.S1 + jb;
+    const rf_c32* pA1 = in.cur1 + jb;
+    const rf_c32* pQ1 = UP ? in.prev1 + jb : nullptr;
+    const float mom = in.momentum;
+    uint32_t pw[U];
+    rf_f4 ab[U];
+    float s0[U], s1[U];
+    rf_c32 a0[U], a1[U], q0[U], q1[U];
 #pragma unroll
-        for (int u = 0; u < RF_LOAD_UNROLL; ++u) {
-            const int j = jb + u * nt;
-            const bool ok = j < j1;
-            pw[u] = ok ? tb.pp[j] : 0u;
-            if (NA == 5) po[u] = (ok && f1) ? tb.ph_odd[j] : c_make(1.f, 0.f);
-            s0[u] = ok ? in.S0[j] : 0.f;
-            a0[u] = ok ? in.cur0[j] : c_make(0.f, 0.f);
-            q0[u] = (ok && up) ? in.prev0[j] : c_make(0.f, 0.f);
-            s1[u] = (ok && f1) ? in.S1[j] : 0.f;
-            a1[u] = (ok && f1) ? in.cur1[j] : c_make(0.f, 0.f);
-            q1[u] = (ok && f1 && up) ? in.prev1[j] : c_make(0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < RF_LOAD_UNROLL; ++u) {
-            const int j = jb + u * nt;
-            if (j >= j1) continue;
-            const uint32_t p = pw[u];
-            const int r = p & 3, idx = (p >> 2) & 8191, idx2 = (p >> 15) & 8191, k7 = p >> 28;
-            const int rp = (4 - r) & 3;
-            const int s = r >> 1, s2 = rp >> 1;
-            rf_c32 c0 = rf_gl_coef(in.mode, up, s0[u], a0[u], q0[u], in.momentum);
-            rf_c32 c1 = c_make(0.f, 0.f);
-            if (f1) c1 = rf_gl_coef(in.mode, up, s1[u], a1[u], q1[u], in.momentum);
-            if (NA == 5) c1 = c_mul(c1, c_conj(po[u]));   // odd-sample frame: exp(+2 pi i k/N)
-            const bool selfp = (idx2 == idx) && (rp == r);
-            if (selfp) {  // DC / Nyquist: irfft ignores the imaginary part
-                c0.y = 0.f;
-                c1.y = 0.f;
-            }
-            const rf_c32 ph = rf_phase8(k7);
-            // Z[k] = conj(ph) * (C0 + i C1)
-            V[s * W + idx] = c_mul(c_conj(ph), c_make(c0.x - c1.y, c0.y + c1.x));
-            // Z[N-k] = ph * (conj(C0) + i conj(C1))
-            if (!selfp) V[s2 * W + idx2] = c_mul(ph, c_make(c0.x + c1.y, c1.x - c0.y));
-        }
+    for (int u = 0; u < U; ++u) {
+        pw[u] = pbt[u * nt];
+        ab[u] = pab[u * nt];
+        s0[u] = rf_ld_stream(pS0 + u * nt);
+        a0[u] = rf_ld_stream(pA0 + u * nt);
+        if (UP) q0[u] = rf_ld_stream(pQ0 + u * nt);
+        s1[u] = rf_ld_stream(pS1 + u * nt);
+        a1[u] = rf_ld_stream(pA1 + u * nt);
+        if (UP) q1[u] = rf_ld_stream(pQ1 + u * nt);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t p = pw[u];
+        const rf_c32 c0 = rf_gl_coef<MODE, UP>(s0[u], a0[u], UP ? q0[u] : c_make(0.f, 0.f), mom);
+        const rf_c32 c1 = rf_gl_coef<MODE, UP>(s1[u], a1[u], UP ? q1[u] : c_make(0.f, 0.f), mom);
+        const rf_c32 al = c_make(ab[u].x, ab[u].y), be = c_make(ab[u].z, ab[u].w);
+        rf_c32* vk = V + (p & 16383u);
+        if (static_cast<int32_t>(p) < 0) {   // self-paired bin (DC / Nyquist, rarely live): irfft ignores the imaginary part
+            const rf_c32 P = c_mul(al, c_make(c0.x, 0.f)), Q = c_mul(be, c_make(c1.x, 0.f));
+            *vk = c_make(P.x + Q.x, P.y + Q.y);
+            continue;
+        }
+        const rf_c32 P = c_mul(al, c0);
+        const rf_c32 Q = c_mul(be, c1);
+        rf_c32* vp = V + ((p >> 14) & 16383u);
+        *vk = c_make(P.x + Q.x, P.y + Q.y);
+        *vp = c_make(P.x - Q.x, Q.y - P.y);
+    }
+}
+
+template <int NA, int MODE, bool UP>
+RF_HD void rf_istft_load_t(int tid, int nt, rf_c32* V, const rf_gl_tables& tb, int j0, int j1, const rf_istft_in& in) {
+    int jb = j0 + tid;
+    for (; jb + 3 * nt < j1; jb += 4 * nt) rf_istft_load_batch<NA, MODE, UP, 4>(jb, nt, V, tb, in);
+    for (; jb + nt < j1; jb += 2 * nt) rf_istft_load_batch<NA, MODE, UP, 2>(jb, nt, V, tb, in);
+    if (jb < j1) rf_istft_load_batch<NA, MODE, UP, 1>(jb, nt, V, tb, in);
+}
+
+template <int NA>
+RF_HD void rf_istft_load(int tid, int nt, rf_c32* V, const rf_gl_tables& tb, int j0, int j1, const rf_istft_in& in) {
+    if (in.mode == 0) rf_istft_load_t<NA, 0, false>(tid, nt, V, tb, j0, j1, in);
+    else if (in.prev0 != nullptr) rf_istft_load_t<NA, 1, true>(tid, nt, V, tb, j0, j1, in);
+    else rf_istft_load_t<NA, 1, false>(tid, nt, V, tb, j0, j1, in);
 }
 
 // Last inverse pass: radix-9 over b for both sub-FFTs, demodulate, window (x 1/N), overlap-add.
@@ -321,11 +363,8 @@ RF_HD void rf_istft_pass_b(int tid, int nt, const rf_c32* V, float* ola, const r
                            bool has1, int which) {
     constexpr int W = rf_geom<NA>::W, SB = rf_geom<NA>::SB, SC = rf_geom<NA>::SC;
     constexpr int ITERS = rf_geom<NA>::B_ITERS;
-    const int r0 = g ? 1 : 0, r1 = g ? 3 : 2;
-    const rf_c32* w00 = tb.wt_inv + r0 * W;
-    const rf_c32* w01 = tb.wt_inv + r1 * W;
-    const rf_c32* w10 = tb.wt_inv + ((NA == 5 ? 4 : 0) + r0) * W;
-    const rf_c32* w11 = tb.wt_inv + ((NA == 5 ? 4 : 0) + r1) * W;
+    constexpr int NP = NA == 5 ? 2 : 1;
+    const rf_f4* wg = tb.wg_inv + static_cast<size_t>(g) * W * NP;
     float re[ITERS][9], im[ITERS][9];
     int base_n[ITERS];
 #pragma unroll
@@ -348,14 +387,14 @@ RF_HD void rf_istft_pass_b(int tid, int nt, const rf_c32* V, float* ola, const r
             for (int b = 0; b < 9; ++b) {
                 const int ti = b * (49 * NA) + tau;
                 if (NA == 10) {
-                    const rf_c32 z = c_add(c_mul(u0[b], w00[ti]), c_mul(u1[b], w01[ti]));
+                    const rf_f4 f = wg[ti];
+                    const rf_c32 z = c_add(c_mul(u0[b], c_make(f.x, f.y)), c_mul(u1[b], c_make(f.z, f.w)));
                     re[itn][b] = z.x;
                     im[itn][b] = z.y;
                 } else {   // frame t0 = Re(z with parity-0 tables), frame t0+1 = Im(z with parity-1 tables)
-                    const rf_c32 z0 = c_add(c_mul(u0[b], w00[ti]), c_mul(u1[b], w01[ti]));
-                    const rf_c32 z1 = c_add(c_mul(u0[b], w10[ti]), c_mul(u1[b], w11[ti]));
-                    re[itn][b] = z0.x;
-                    im[itn][b] = z1.y;
+                    const rf_f4 f0 = wg[2 * ti], f1 = wg[2 * ti + 1];
+                    re[itn][b] = (u0[b].x * f0.x - u0[b].y * f0.y) + (u1[b].x * f0.z - u1[b].y * f0.w);
+                    im[itn][b] = (u0[b].x * f1.y + u0[b].y * f1.x) + (u1[b].x * f1.w + u1[b].y * f1.z);
                 }
             }
         }

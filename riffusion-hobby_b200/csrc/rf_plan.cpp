@@ -78,6 +78,78 @@ std::vector<float> melscale_fbanks_f32(int n_freqs, float f_min, float f_max, in
     return fb;
 }
 
+// kernel-side forms of the per-bin / per-sample tables (rf_bin_tabs) for one prime-factor grid
+void build_bin_tabs(const rf_plan_host& p, int NA, const std::vector<uint32_t>& pp, const std::vector<float>* ph_odd,
+                    const std::vector<float>& wt_fwd, const std::vector<float>& wt_inv, rf_bin_tabs& t) {
+    const int W = NA * 441;
+    const int J = p.n_live;
+    t.bt.resize(J);
+    t.ab_inv.resize(static_cast<size_t>(J) * 4);
+    t.ab_fwd.resize(static_cast<size_t>(J) * 4);
+    std::vector<char> hit[2] = {std::vector<char>(2 * W, 0), std::vector<char>(2 * W, 0)};
+    for (int j = 0; j < J; ++j) {
+        const uint32_t q = pp[j];
+        const int r = q & 3, idx = (q >> 2) & 8191, idx2 = (q >> 15) & 8191, k7 = q >> 28;
+        const int rp = (4 - r) & 3;
+        const int off = (r >> 1) * W + idx, off2 = (rp >> 1) * W + idx2;
+        const bool self = idx2 == idx && rp == r;
+        t.bt[j] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(off2) << 14) | (self ? 1u << 31 : 0u);
+        const int g = j < p.n_even ? 0 : 1;
+        hit[g][off] = hit[g][off2] = 1;
+        // ph = exp(-2 pi i 3k/8) (frame offset (N-W)/2 = 3N/8), po = exp(-2 pi i k/N) (odd-sample frame, NA = 5 only)
+        const double a_ph = -2.0 * M_PI * ((3 * k7) & 7) / 8.0;
+        const double phx = std::cos(a_ph), phy = std::sin(a_ph);
+        double pox = 1.0, poy = 0.0;
+        if (ph_odd) {
+            const double a_po = -2.0 * M_PI * static_cast<double>(p.bins[j]) / p.N;
+            pox = std::cos(a_po);
+            poy = std::sin(a_po);
+        }
+        // e = ph * po
+        const double ex = phx * pox - phy * poy, ey = phx * poy + phy * pox;
+        float* ai = &t.ab_inv[static_cast<size_t>(j) * 4];
+        ai[0] = static_cast<float>(phx);      // alpha = conj(ph)
+        ai[1] = static_cast<float>(-phy);
+        ai[2] = static_cast<float>(ey);       // beta = i conj(e) = (ey, ex)
+        ai[3] = static_cast<float>(ex);
+        float* af = &t.ab_fwd[static_cast<size_t>(j) * 4];
+        af[0] = static_cast<float>(0.5 * phx);   // gamma = ph / 2
+        af[1] = static_cast<float>(0.5 * phy);
+        af[2] = static_cast<float>(0.5 * ey);    // delta = -i e / 2 = (ey, -ex) / 2
+        af[3] = static_cast<float>(-0.5 * ex);
+    }
+    t.zpos.clear();
+    for (int g = 0; g < 2; ++g) {
+        t.nz[g] = 0;
+        for (int i = 0; i < 2 * W; ++i)
+            if (!hit[g][i]) {
+                t.zpos.push_back(static_cast<uint16_t>(i));
+                ++t.nz[g];
+            }
+    }
+    // window x modulation tables regrouped per CTA group: entry (g, ti) = for each parity (w_r0, w_r1)
+    const int NP = NA == 5 ? 2 : 1;
+    t.wg_fwd.assign(static_cast<size_t>(2) * W * NP * 4, 0.f);
+    t.wg_inv.assign(static_cast<size_t>(2) * W * NP * 4, 0.f);
+    for (int g = 0; g < 2; ++g) {
+        const int r0 = g ? 1 : 0, r1 = g ? 3 : 2;
+        for (int ti = 0; ti < W; ++ti)
+            for (int par = 0; par < NP; ++par) {
+                const size_t o = ((static_cast<size_t>(g) * W + ti) * NP + par) * 4;
+                const size_t s0 = ((static_cast<size_t>(par) * 4 + r0) * W + ti) * 2;
+                const size_t s1 = ((static_cast<size_t>(par) * 4 + r1) * W + ti) * 2;
+                t.wg_fwd[o] = wt_fwd[s0];
+                t.wg_fwd[o + 1] = wt_fwd[s0 + 1];
+                t.wg_fwd[o + 2] = wt_fwd[s1];
+                t.wg_fwd[o + 3] = wt_fwd[s1 + 1];
+                t.wg_inv[o] = wt_inv[s0];
+                t.wg_inv[o + 1] = wt_inv[s0 + 1];
+                t.wg_inv[o + 2] = wt_inv[s1];
+                t.wg_inv[o + 3] = wt_inv[s1 + 1];
+            }
+    }
+}
+
 }  // namespace
 
 std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const float* fb_in,
@@ -281,6 +353,9 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
                             p.wt2_inv[o + 1] = static_cast<float>(-w * std::sin(ang) / p.N);
                         }
     }
+
+    if (!p.generic) build_bin_tabs(p, 10, p.pp, nullptr, p.wt_fwd, p.wt_inv, p.t10);
+    if (p.decimate) build_bin_tabs(p, 5, p.pp2, &p.ph_odd, p.wt2_fwd, p.wt2_inv, p.t5);
 
     // ---- sparse filterbank
     p.melcol_ptr.assign(p.n_mels + 1, 0);

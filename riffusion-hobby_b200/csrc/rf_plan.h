@@ -13,6 +13,18 @@ constexpr int RF_N = 4 * RF_W;
 constexpr int RF_NA = 10, RF_NB = 9, RF_NC = 49;
 constexpr int RF_CHUNK = 16;  // frames per overlap-add chunk in the iSTFT kernel (even)
 
+// Per-bin and per-sample tables in the form the kernels consume them, one set per prime-factor grid (NA = 10: full rate,
+// NA = 5: time-decimated loop).  Derived from pp / ph_odd / wt_* below, which stay as the readable (and tested) source.
+struct rf_bin_tabs {
+    std::vector<uint32_t> bt;      // [n_live] V offset of bin k (s*W + idx) | V offset of its Hermitian partner << 14 | self-paired << 31
+    std::vector<float> ab_inv;     // [n_live][4] alpha = conj(ph), beta = i conj(ph) conj(po):  Z[k] = alpha C0 + beta C1
+    std::vector<float> ab_fwd;     // [n_live][4] gamma = ph/2, delta = -i ph po/2:  X_t = gamma (Zk + conj Zp), X_t+1 = delta (Zk - conj Zp)
+    std::vector<float> wg_fwd;     // [2 groups][W][NP][4]: (w_r0, w_r1) of parity 0 (then parity 1 for NA = 5), r0/r1 = the group's two r
+    std::vector<float> wg_inv;
+    std::vector<uint16_t> zpos;    // V offsets no live bin or partner of the group writes: [nz[0] entries of group 0 | nz[1] of group 1]
+    int nz[2] = {0, 0};
+};
+
 struct rf_plan_host {
     rf_plan_desc d{};
     int N = 0, W = 0, H = 0, F = 0, n_mels = 0;
@@ -31,6 +43,7 @@ struct rf_plan_host {
     std::vector<float> wt2_fwd;   // [2 parities][4][9][49][5][2]  2 * w[2u+par] * exp(-2 pi i r u/8820)
     std::vector<float> wt2_inv;   // same layout,                  w[2u+par]/N * exp(+2 pi i r u/8820)
     std::vector<float> ph_odd;    // [n_live][2]  exp(-2 pi i k/N)
+    rf_bin_tabs t10, t5;          // kernel-side forms (t5 empty unless `decimate`)
     // mel filterbank in sparse forms over the private bin order
     std::vector<int32_t> melcol_ptr;  // [n_mels+1]  CSR by mel column: entries (j, w)
     std::vector<int32_t> melcol_j;

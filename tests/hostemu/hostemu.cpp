@@ -9,6 +9,7 @@
 //
 // Build: g++ -O2 -shared -fPIC -I../../riffusion-hobby_b200/csrc hostemu.cpp \
 //            ../../riffusion-hobby_b200/csrc/rf_plan.cpp -o librf_hostemu.so
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -28,19 +29,19 @@ void phase(F f) {
 
 rf_gl_tables tables(const rf_plan_host& h, int NA) {
     rf_gl_tables tb;
-    if (NA == 10) {
-        tb.wt_fwd = reinterpret_cast<const rf_c32*>(h.wt_fwd.data());
-        tb.wt_inv = reinterpret_cast<const rf_c32*>(h.wt_inv.data());
-        tb.pp = h.pp.data();
-        tb.ph_odd = nullptr;
-        tb.off1 = h.H;
-    } else {
-        tb.wt_fwd = reinterpret_cast<const rf_c32*>(h.wt2_fwd.data());
-        tb.wt_inv = reinterpret_cast<const rf_c32*>(h.wt2_inv.data());
-        tb.pp = h.pp2.data();
-        tb.ph_odd = reinterpret_cast<const rf_c32*>(h.ph_odd.data());
-        tb.off1 = (h.H + 1) / 2;
-    }
+    const rf_bin_tabs& t = NA == 10 ? h.t10 : h.t5;
+    tb.wg_fwd = reinterpret_cast<const rf_f4*>(t.wg_fwd.data());
+    tb.wg_inv = reinterpret_cast<const rf_f4*>(t.wg_inv.data());
+    tb.bt = t.bt.data();
+    tb.ab_inv = reinterpret_cast<const rf_f4*>(t.ab_inv.data());
+    tb.ab_fwd = reinterpret_cast<const rf_f4*>(t.ab_fwd.data());
+    tb.zpos = t.zpos.data();
+    tb.nz0 = t.nz[0];
+    tb.nz1 = t.nz[1];
+    static std::vector<float> zero_row;
+    if (static_cast<int>(zero_row.size()) < h.n_live) zero_row.assign(h.n_live, 0.f);
+    tb.zero_row = zero_row.data();
+    tb.off1 = NA == 10 ? h.H : (h.H + 1) / 2;
     tb.n_live = h.n_live;
     tb.n_even = h.n_even;
     return tb;
@@ -85,7 +86,7 @@ void emu_istft_chunk(const rf_plan_host& h, const float* S, const rf_c32* cur, c
     constexpr int W = rf_geom<NA>::W;
     const int G = RF_CHUNK;
     const int pair_stride = NA == 10 ? 2 * tb.off1 : 2 * tb.off1 - 1;
-    std::vector<rf_c32> V(2 * W);
+    std::vector<rf_c32> V(2 * W, c_make(NAN, NAN));   // shared memory starts out as garbage on the device
     std::vector<float> ola(PL, 0.f);
     const int f0 = chunk * G;
     const int nf = std::min(G, T - f0);
@@ -93,15 +94,15 @@ void emu_istft_chunk(const rf_plan_host& h, const float* S, const rf_c32* cur, c
     for (int pr = 0; 2 * pr < nf; ++pr) {
         const int t0 = f0 + 2 * pr;
         const bool has1 = (2 * pr + 1) < nf;
-        phase([&](int tid) { rf_istft_zero<NA>(tid, NT, V.data()); });
+        phase([&](int tid) { rf_istft_zero<NA>(tid, NT, V.data(), tb, g); });
         rf_istft_in in;
         const size_t o0 = static_cast<size_t>(t0) * tb.n_live;
         in.S0 = S + o0;
         in.cur0 = cur + o0;
         in.prev0 = prev ? prev + o0 : nullptr;
-        in.S1 = has1 ? S + o0 + tb.n_live : nullptr;
-        in.cur1 = cur + o0 + tb.n_live;
-        in.prev1 = prev ? prev + o0 + tb.n_live : nullptr;
+        in.S1 = has1 ? S + o0 + tb.n_live : tb.zero_row;
+        in.cur1 = cur + o0 + (has1 ? tb.n_live : 0);
+        in.prev1 = prev ? prev + o0 + (has1 ? tb.n_live : 0) : nullptr;
         in.mode = mode;
         in.momentum = momentum;
         phase([&](int tid) { rf_istft_load<NA>(tid, NT, V.data(), tb, j0, j1, in); });

@@ -89,6 +89,27 @@ def test_plan_tables(native_lib):
         # bank-aware order: 16 consecutive bins of one r block hit 16 distinct 8-byte bank pairs
         blk = slice(0, 16 * 40)
         assert all(len(set((idx[blk][i:i + 16] % 16).tolist())) == 16 for i in range(0, 16 * 40 - 16))
+        # kernel-side per-bin tables derived from pp: V offsets of the bin and its Hermitian partner, phase constants
+        bt = plan.table("bt", np.uint32, (n_live,))
+        rp = (4 - r) % 4
+        assert np.array_equal(bt & 16383, (r >> 1) * W + idx) and np.array_equal((bt >> 14) & 16383, (rp >> 1) * W + idx2)
+        assert np.array_equal(bt >> 31, ((idx == idx2) & (r == rp)).astype(np.uint32))
+        ph = np.exp(-2j * np.pi * 3 * bins / 8)
+        ai = plan.table("ab_inv", np.float32, (n_live, 4)).astype(np.float64)
+        af = plan.table("ab_fwd", np.float32, (n_live, 4)).astype(np.float64)
+        assert np.abs(ai[:, 0] + 1j * ai[:, 1] - np.conj(ph)).max() < 1e-7
+        assert np.abs(ai[:, 2] + 1j * ai[:, 3] - 1j * np.conj(ph)).max() < 1e-7
+        assert np.abs(af[:, 0] + 1j * af[:, 1] - ph / 2).max() < 1e-7
+        assert np.abs(af[:, 2] + 1j * af[:, 3] - (-1j) * ph / 2).max() < 1e-7
+        if i.k_hi * 2 + 800 <= N // 2:    # decimated loop eligible: odd-sample frame carries exp(-2 pi i k/N)
+            po = np.exp(-2j * np.pi * bins / N)
+            pp2 = plan.table("pp2", np.uint32, (n_live,))
+            bt2 = plan.table("bt2", np.uint32, (n_live,))
+            assert np.array_equal(bt2 & 16383, ((pp2 & 3) >> 1) * (W // 2) + ((pp2 >> 2) & 8191))
+            a2 = plan.table("ab2_inv", np.float32, (n_live, 4)).astype(np.float64)
+            f2 = plan.table("ab2_fwd", np.float32, (n_live, 4)).astype(np.float64)
+            assert np.abs(a2[:, 2] + 1j * a2[:, 3] - 1j * np.conj(ph * po)).max() < 1e-7
+            assert np.abs(f2[:, 2] + 1j * f2[:, 3] - (-1j) * ph * po / 2).max() < 1e-7
         fb = plan.table("fb", np.float32, (F, 512))
         assert np.array_equal(fb, mel_filterbank(F, float(params.min_frequency), float(params.max_frequency),
                                                  512, 44100).numpy())
