@@ -38,6 +38,7 @@ struct rf_plan {
     struct dev_tabs {              // device copies of rf_bin_tabs
         rf_f4* wg_fwd = nullptr;
         rf_f4* wg_inv = nullptr;
+        uint32_t* items = nullptr;
         uint32_t* bt = nullptr;
         rf_f4* ab_inv = nullptr;
         rf_f4* ab_fwd = nullptr;
@@ -73,6 +74,7 @@ static cudaError_t upload(rf_plan* p, T** dst, const void* src, size_t count) {
 static cudaError_t upload_tabs(rf_plan* p, rf_plan::dev_tabs* d, const rf_bin_tabs& t) {
     cudaError_t e = upload(p, &d->wg_fwd, t.wg_fwd.data(), t.wg_fwd.size() / 4);
     if (e == cudaSuccess) e = upload(p, &d->wg_inv, t.wg_inv.data(), t.wg_inv.size() / 4);
+    if (e == cudaSuccess) e = upload(p, &d->items, t.items.data(), t.items.size());
     if (e == cudaSuccess) e = upload(p, &d->bt, t.bt.data(), t.bt.size());
     if (e == cudaSuccess) e = upload(p, &d->ab_inv, t.ab_inv.data(), t.ab_inv.size() / 4);
     if (e == cudaSuccess) e = upload(p, &d->ab_fwd, t.ab_fwd.data(), t.ab_fwd.size() / 4);
@@ -240,6 +242,11 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
 // kernels
 // ---------------------------------------------------------------------------------------
 
+#ifndef RF_GL_PREFETCH
+#define RF_GL_PREFETCH 1    // 0: no L2 prefetch of the next pair's rows (A/B builds)
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- iSTFT of one overlap-add chunk (G frames) of one clip, one r-group ------------------
 // Output: dst[PL] partial overlap-add sums of the chunk (NA = 10 full rate, NA = 5 odd samples only).
 template <int NA>
@@ -273,6 +280,23 @@ __device__ __forceinline__ void istft_chunk_body(unsigned char* smem_raw, const 
         in.mode = mode;
         in.momentum = momentum;
         rf_istft_load<NA>(tid, RF_NT, V, tb, j0, j1, in);
+#if RF_GL_PREFETCH
+        // the rows of the NEXT pair go to L2 now: its load phase, four FFT passes from here, then waits on L2 instead of HBM
+        // (ncu: 37 % of this kernel's samples sat in the load phase, 60 % of them on the long scoreboard)
+        if (2 * pr + 2 < nf) {
+            const size_t o2 = o0 + 2 * row + j0;
+            const int nb4 = (j1 - j0) * 4;   // bytes of a float row segment; the complex rows are twice that
+            const int nfr = (2 * pr + 3 < nf) ? 2 : 1;
+            for (int f = 0; f < nfr; ++f) {
+                const size_t o = o2 + f * row;
+                for (int i = tid * 128; i < nb4; i += RF_NT * 128) prefetch_l2(reinterpret_cast<const char*>(S + o) + i);
+                for (int i = tid * 128; i < 2 * nb4; i += RF_NT * 128) {
+                    prefetch_l2(reinterpret_cast<const char*>(cur + o) + i);
+                    if (prev) prefetch_l2(reinterpret_cast<const char*>(prev + o) + i);
+                }
+            }
+        }
+#endif
         __syncthreads();
         rf_pass_c7<true, NA, 0>(tid, RF_NT, V);
         __syncthreads();
@@ -366,28 +390,25 @@ __global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float
 
 // 1-D TMA bulk copy of n floats starting at src (any 4-byte alignment) into shared memory: the copy starts at the enclosing
 // 16-byte boundary and is rounded up to 16 bytes — the caller guarantees those few extra bytes are readable — and lands at
-// xs_al (16-byte aligned).  Returns the shared-memory address of src[0].  Ends with every thread past the mbarrier wait.
-__device__ __forceinline__ float* stage_bulk(float* xs_al, uint64_t* bar, const float* src, int n) {
+// xs_al (16-byte aligned); src[0] ends up bulk_shift(src) bytes behind xs_al.  One thread issues; completion on `bar`.
+__device__ __forceinline__ uint32_t bulk_shift(const float* src) {
+    return static_cast<uint32_t>(reinterpret_cast<uint64_t>(src) & 15u);
+}
+__device__ __forceinline__ void bulk_issue(float* xs_al, uint64_t* bar, const float* src, int n) {
     const uint64_t a = reinterpret_cast<uint64_t>(src);
     const uint32_t shift = static_cast<uint32_t>(a & 15u);
     const uint32_t nbytes = (shift + static_cast<uint32_t>(n) * 4u + 15u) & ~15u;
-    if (threadIdx.x == 0) {
-        tc::mbar_init(bar, 1);
-        tc::fence_barrier_init();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc::mbar_expect_tx(bar, nbytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         tc::smem_u32(xs_al)),
-                     "l"(a - shift), "r"(nbytes), "r"(tc::smem_u32(bar))
-                     : "memory");
-    }
-    __syncthreads();   // the initialised barrier is visible to every thread before it waits
-    tc::mbar_wait(bar, 0);
-    return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xs_al) + shift);
+    tc::mbar_expect_tx(bar, nbytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(xs_al)),
+                 "l"(a - shift), "r"(nbytes), "r"(tc::smem_u32(bar))
+                 : "memory");
 }
-// staging area of the half-rate STFT CTAs: W/2 + (hop+1)/2 samples + up to 3 floats of alignment slack, rounded to 16 bytes;
-// the mbarrier sits behind it
-constexpr int RF_XS_HALF_BYTES = ((RF_PW / 2 + (441 + 1) / 2 + 3) * 4 + 15) / 16 * 16;
+// staging buffer of the half-rate STFT CTAs: W/2 + (hop+1)/2 samples + up to 3 floats of alignment slack, rounded to 16
+// bytes.  Two of them (double buffering over the CTA's pairs), then the two mbarriers.
+constexpr int RF_XS_HALF_N = RF_PW / 2 + (441 + 1) / 2;
+constexpr int RF_XS_HALF_BYTES = ((RF_XS_HALF_N + 3) * 4 + 15) / 16 * 16;
+constexpr int RF_STFT_HALF_PAIRS = 4;    // consecutive frame pairs per half-rate STFT CTA
 
 // ---- STFT of one frame pair, one r-group ------------------------------------------------
 // x_full: waveform holding samples [base, ...) (reflect padding applied on the fly); NA = 5: xo odd samples
@@ -401,22 +422,9 @@ __device__ __forceinline__ void stft_pair_body(unsigned char* smem_raw, const rf
     const int tid = threadIdx.x;
     const int t0 = 2 * pr;
     const bool has1 = t0 + 1 < T;
-    if (NA == 10) {
-        rf_stage_x(tid, RF_NT, xs, x, L, t0, hop, base);
-        __syncthreads();
-    } else {
-        // half-rate pairs: the staged samples are nv consecutive odd samples xo[vo0 ..) unless the frame touches the reflect
-        // padding (which the hybrid loop gives to the full-rate edge kernel) -> one 1-D TMA bulk copy instead of a load loop
-        constexpr int nv = RF_PW / 2 + (441 + 1) / 2;
-        const int vo0 = (t0 * hop - RF_PW / 2 - 1) >> 1;
-        if (hop == 441 && vo0 >= 0 && vo0 + nv <= (L - 1) / 2) {
-            uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * W * sizeof(rf_c32) + RF_XS_HALF_BYTES);
-            xs = stage_bulk(xs, bar, x + vo0, nv);
-        } else {
-            rf_stage_x_d2(tid, RF_NT, xs, x, L, t0, hop);
-            __syncthreads();
-        }
-    }
+    if (NA == 10) rf_stage_x(tid, RF_NT, xs, x, L, t0, hop, base);
+    else rf_stage_x_d2(tid, RF_NT, xs, x, L, t0, hop);
+    __syncthreads();
     rf_stft_pass_b<NA>(tid, RF_NT, V, xs, tb, g, has1);
     __syncthreads();
     rf_pass_a<false, NA>(tid, RF_NT, V);
@@ -452,13 +460,53 @@ k_stft_edge(rf_gl_tables tb, const float* __restrict__ xd, int L, int T, int hop
     else stft_pair_body<10>(smem_raw, tb, xb + nxo + E, L - E, L, T, hop, b, g, pr_tail + idx - 3, R);
 }
 
+// Half-rate pairs never touch the reflect padding (the hybrid loop gives those to k_stft_edge), so the samples of a pair
+// are RF_XS_HALF_N consecutive odd samples xo[vo0 ..): ONE 1-D TMA bulk copy per pair instead of a load loop, and a CTA takes
+// RF_STFT_HALF_PAIRS consecutive pairs [pr_lo + P i, ..) < pr_hi so that the copy of the next pair flies during the four
+// passes of the current one (two staging buffers, one mbarrier each).
 __global__ void __launch_bounds__(RF_NT, RF_GL_HALF_MINB)
-k_stft_half(rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E,
+k_stft_half(rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E, int pr_lo, int pr_hi,
             rf_c32* __restrict__ R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int g = blockIdx.x & 1, b = blockIdx.y;
-    const float* xb = xd + static_cast<size_t>(b) * (nxo + 2 * E);
-    stft_pair_body<5>(smem_raw, tb2, xb, 0, L, T, hop, b, g, 3 + (blockIdx.x >> 1), R);
+    constexpr int W = rf_geom<5>::W;
+    const int g = blockIdx.x & 1, b = blockIdx.y, tid = threadIdx.x;
+    const float* xo = xd + static_cast<size_t>(b) * (nxo + 2 * E);
+    rf_c32* V = reinterpret_cast<rf_c32*>(smem_raw);
+    unsigned char* xbuf = smem_raw + 2 * W * sizeof(rf_c32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + 2 * RF_XS_HALF_BYTES);
+    const int first = pr_lo + (blockIdx.x >> 1) * RF_STFT_HALF_PAIRS;
+    const int npr = min(RF_STFT_HALF_PAIRS, pr_hi - first);
+    auto src_of = [&](int pr) { return xo + ((2 * pr * hop - RF_PW / 2 - 1) >> 1); };
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulk_issue(reinterpret_cast<float*>(xbuf), &bars[0], src_of(first), RF_XS_HALF_N);
+    }
+    __syncthreads();   // the initialised barriers are visible to every thread before it waits
+    const int j0 = g ? tb2.n_even : 0, j1 = g ? tb2.n_live : tb2.n_even;
+    for (int i = 0; i < npr; ++i) {
+        const int pr = first + i, t0 = 2 * pr;
+        const bool has1 = t0 + 1 < T;
+        // buffer (i+1)&1 was last read by the radix-9 pass of pair i-1, which every thread left at least one barrier ago
+        if (tid == 0 && i + 1 < npr)
+            bulk_issue(reinterpret_cast<float*>(xbuf + ((i + 1) & 1) * RF_XS_HALF_BYTES), &bars[(i + 1) & 1], src_of(pr + 1),
+                       RF_XS_HALF_N);
+        tc::mbar_wait(&bars[i & 1], (i >> 1) & 1);
+        const float* xs = reinterpret_cast<const float*>(xbuf + (i & 1) * RF_XS_HALF_BYTES + bulk_shift(src_of(pr)));
+        rf_stft_pass_b<5>(tid, RF_NT, V, xs, tb2, g, has1);
+        __syncthreads();
+        rf_pass_a<false, 5>(tid, RF_NT, V);
+        __syncthreads();
+        rf_pass_c7<false, 5, 0>(tid, RF_NT, V);
+        __syncthreads();
+        rf_pass_c7<false, 5, 1>(tid, RF_NT, V);
+        __syncthreads();
+        rf_c32* out0 = R + (static_cast<size_t>(b) * T + t0) * tb2.n_live;
+        rf_stft_post<5>(tid, RF_NT, V, tb2, j0, j1, out0, has1 ? out0 + tb2.n_live : nullptr);
+        __syncthreads();   // V is rewritten by the next pair
+    }
 }
 
 // ---- STFT + |.| + mel of one frame pair (both groups in one CTA) -------------------------
@@ -696,6 +744,7 @@ static rf_gl_tables make_tables(const rf_plan* p, int NA = 10) {
     const rf_bin_tabs& t = NA == 10 ? p->h.t10 : p->h.t5;
     tb.wg_fwd = d.wg_fwd;
     tb.wg_inv = d.wg_inv;
+    tb.items = d.items;
     tb.bt = d.bt;
     tb.ab_inv = d.ab_inv;
     tb.ab_fwd = d.ab_fwd;
@@ -874,7 +923,7 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const size_t smem_f = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(RF_PW + h.H) * 4;
 #if RF_GL_HALF_MINB >= 3
     const size_t smem_ih = 2 * (RF_PW / 2) * sizeof(rf_c32) + static_cast<size_t>(PLh) * 4;                       // half-rate CTAs
-    const size_t smem_fh = 2 * (RF_PW / 2) * sizeof(rf_c32) + RF_XS_HALF_BYTES + 16;   // + mbarrier of the bulk copy
+    const size_t smem_fh = 2 * (RF_PW / 2) * sizeof(rf_c32) + 2 * RF_XS_HALF_BYTES + 16;   // two staging buffers + mbarriers
 #else       // A/B build: the footprint of the merged launch (2 CTAs per SM)
     const size_t smem_ih = smem_i, smem_fh = smem_f;
 #endif
@@ -924,8 +973,9 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
             k_stft_edge<<<dim3(dg.n_edge_pairs * 2, B), RF_NT, smem_f, st>>>(tb, w.xd, L, T, h.H, dg.nxo, dg.E, dg.pr_tail,
                                                                             w.R[it & 1]);
             RF_CUDA_LAUNCH_CHECK("k_stft_edge");
-            k_stft_half<<<dim3(((T + 1) / 2 - dg.n_edge_pairs) * 2, B), RF_NT, smem_fh, st>>>(tb2, w.xd, L, T, h.H, dg.nxo,
-                                                                                              dg.E, w.R[it & 1]);
+            // the half-rate pairs [3, pr_tail): RF_STFT_HALF_PAIRS consecutive pairs per CTA
+            k_stft_half<<<dim3((dg.pr_tail - 3 + RF_STFT_HALF_PAIRS - 1) / RF_STFT_HALF_PAIRS * 2, B), RF_NT, smem_fh, st>>>(
+                tb2, w.xd, L, T, h.H, dg.nxo, dg.E, 3, dg.pr_tail, w.R[it & 1]);
         } else
             k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, h.H, w.R[it & 1]);
         RF_CUDA_LAUNCH_CHECK("k_stft_pair");

@@ -47,8 +47,10 @@ struct alignas(16) rf_f4 {
 
 // Tables of one prime-factor grid (rf_bin_tabs in rf_plan.h holds the host copies and the exact definitions)
 struct rf_gl_tables {
-    const rf_f4* wg_fwd;   // [2 groups][9][49][NA][NP]  window x modulation of the group's two r: (w_r0, w_r1), per sample parity
-    const rf_f4* wg_inv;   // same layout (NP = 2 parities for NA = 5, else 1)
+    const rf_f4* wg_fwd;   // [9][49 NA] per (b, item): (w0, w1, cos t, -sin t): windows of frames t0 / t0+1 (sample parities for
+                           // NA = 5) and the modulation exp(-i t) of r = 1 at that sample; r = 2, 3 are derived from it
+    const rf_f4* wg_inv;   // same layout: (w0/N, w1/N, cos t, sin t)
+    const uint32_t* items; // [49 NA] radix-9 pass item of slot tau: V position a*441 + c | first sample index n'(a, b=0, c) << 12
     const uint32_t* bt;    // [n_live] V offset of the bin | V offset of its Hermitian partner << 14 | self-paired << 31
     const rf_f4* ab_inv;   // [n_live] (alpha, beta):  Z[k] = alpha C0 + beta C1,  Z[N-k] = conj(alpha C0 - beta C1)
     const rf_f4* ab_fwd;   // [n_live] (gamma, delta): X_t[k] = gamma (Z[k] + conj Z[N-k]),  X_t+1[k] = delta (Z[k] - conj Z[N-k])
@@ -154,35 +156,29 @@ RF_HD void rf_pass_c7(int tid, int nt, rf_c32* V) {
 template <int NA>
 RF_HD void rf_stft_pass_b(int tid, int nt, rf_c32* V, const float* xs, const rf_gl_tables& tb, int g,
                           bool has1) {
-    constexpr int W = rf_geom<NA>::W, SB = rf_geom<NA>::SB, SC = rf_geom<NA>::SC;
-    constexpr int NP = NA == 5 ? 2 : 1;
-    // frame t0 uses the parity-0 entries, frame t0+1 the parity-1 entries (one parity for NA = 10)
-    const rf_f4* wg = tb.wg_fwd + static_cast<size_t>(g) * W * NP;
+    constexpr int W = rf_geom<NA>::W, SB = rf_geom<NA>::SB;
+    // sub-transform r of the group sees z[n'] exp(-2 pi i r n'/N):  r0 = g, r1 = g + 2, so with y = (x0 w0) + i (x1 w1) and
+    // c = exp(-i t):  u0 = y c^g,  u1 = u0 c^2.  Items (a, c) are assigned to slots tau by the plan (bank-conflict-free order).
     for (int tau = tid; tau < rf_geom<NA>::B_ITEMS; tau += nt) {
-        const int c = tau / NA;
-        const int a = tau - c * NA;
-        const int base = (441 * a + SC * c) % W;
+        const uint32_t item = tb.items[tau];
+        const int base = item >> 12;
         rf_c32 u0[9], u1[9];
 #pragma unroll
         for (int b = 0; b < 9; ++b) {
             int n = base + SB * b;
             if (n >= W) n -= W;
             const float x0 = xs[n], x1 = has1 ? xs[tb.off1 + n] : 0.f;
-            const int ti = b * (49 * NA) + tau;
-            if (NA == 10) {
-                const rf_c32 z = c_make(x0, x1);
-                const rf_f4 f = wg[ti];
-                u0[b] = c_mul(z, c_make(f.x, f.y));
-                u1[b] = c_mul(z, c_make(f.z, f.w));
-            } else {   // the two frames of the pair sit on different sample parities: separate window tables
-                const rf_f4 f0 = wg[2 * ti], f1 = wg[2 * ti + 1];
-                u0[b] = c_make(x0 * f0.x - x1 * f1.y, x0 * f0.y + x1 * f1.x);   // x0*f00 + i*x1*f10
-                u1[b] = c_make(x0 * f0.z - x1 * f1.w, x0 * f0.w + x1 * f1.z);
-            }
+            const rf_f4 f = tb.wg_fwd[b * (49 * NA) + tau];
+            rf_c32 y = c_make(x0 * f.x, x1 * f.y);
+            const rf_c32 c1 = c_make(f.z, f.w);
+            const rf_c32 c2 = c_make(f.z * f.z - f.w * f.w, 2.f * f.z * f.w);
+            if (g) y = c_mul(y, c1);
+            u0[b] = y;
+            u1[b] = c_mul(y, c2);
         }
         dft9<false>(u0);
         dft9<false>(u1);
-        rf_c32* p = V + a * 441 + c;
+        rf_c32* p = V + (item & 4095u);
 #pragma unroll
         for (int b = 0; b < 9; ++b) {
             p[49 * b] = u0[b];
@@ -361,20 +357,17 @@ RF_HD void rf_istft_load(int tid, int nt, rf_c32* V, const rf_gl_tables& tb, int
 template <int NA>
 RF_HD void rf_istft_pass_b(int tid, int nt, const rf_c32* V, float* ola, const rf_gl_tables& tb, int g,
                            bool has1, int which) {
-    constexpr int W = rf_geom<NA>::W, SB = rf_geom<NA>::SB, SC = rf_geom<NA>::SC;
+    constexpr int W = rf_geom<NA>::W, SB = rf_geom<NA>::SB;
     constexpr int ITERS = rf_geom<NA>::B_ITERS;
-    constexpr int NP = NA == 5 ? 2 : 1;
-    const rf_f4* wg = tb.wg_inv + static_cast<size_t>(g) * W * NP;
     float re[ITERS][9], im[ITERS][9];
     int base_n[ITERS];
 #pragma unroll
     for (int itn = 0; itn < ITERS; ++itn) {
         const int tau = tid + itn * nt;
         if (tau < rf_geom<NA>::B_ITEMS) {
-            const int c = tau / NA;
-            const int a = tau - c * NA;
-            base_n[itn] = (441 * a + SC * c) % W;
-            const rf_c32* p = V + a * 441 + c;
+            const uint32_t item = tb.items[tau];
+            base_n[itn] = item >> 12;
+            const rf_c32* p = V + (item & 4095u);
             rf_c32 u0[9], u1[9];
 #pragma unroll
             for (int b = 0; b < 9; ++b) {
@@ -385,17 +378,14 @@ RF_HD void rf_istft_pass_b(int tid, int nt, const rf_c32* V, float* ola, const r
             dft9<true>(u1);
 #pragma unroll
             for (int b = 0; b < 9; ++b) {
-                const int ti = b * (49 * NA) + tau;
-                if (NA == 10) {
-                    const rf_f4 f = wg[ti];
-                    const rf_c32 z = c_add(c_mul(u0[b], c_make(f.x, f.y)), c_mul(u1[b], c_make(f.z, f.w)));
-                    re[itn][b] = z.x;
-                    im[itn][b] = z.y;
-                } else {   // frame t0 = Re(z with parity-0 tables), frame t0+1 = Im(z with parity-1 tables)
-                    const rf_f4 f0 = wg[2 * ti], f1 = wg[2 * ti + 1];
-                    re[itn][b] = (u0[b].x * f0.x - u0[b].y * f0.y) + (u1[b].x * f0.z - u1[b].y * f0.w);
-                    im[itn][b] = (u0[b].x * f1.y + u0[b].y * f1.x) + (u1[b].x * f1.w + u1[b].y * f1.z);
-                }
+                // z = (w/N) e^g (u0 + u1 e^2), e = exp(+i t): frame t0 = w0 Re z, frame t0+1 = w1 Im z
+                const rf_f4 f = tb.wg_inv[b * (49 * NA) + tau];
+                const rf_c32 e1 = c_make(f.z, f.w);
+                const rf_c32 e2 = c_make(f.z * f.z - f.w * f.w, 2.f * f.z * f.w);
+                rf_c32 t = c_add(u0[b], c_mul(u1[b], e2));
+                if (g) t = c_mul(t, e1);
+                re[itn][b] = f.x * t.x;
+                im[itn][b] = f.y * t.y;
             }
         }
     }

@@ -78,9 +78,11 @@ std::vector<float> melscale_fbanks_f32(int n_freqs, float f_min, float f_max, in
     return fb;
 }
 
+#include "rf_pass_b_perm.inc"
+
 // kernel-side forms of the per-bin / per-sample tables (rf_bin_tabs) for one prime-factor grid
 void build_bin_tabs(const rf_plan_host& p, int NA, const std::vector<uint32_t>& pp, const std::vector<float>* ph_odd,
-                    const std::vector<float>& wt_fwd, const std::vector<float>& wt_inv, rf_bin_tabs& t) {
+                    rf_bin_tabs& t) {
     const int W = NA * 441;
     const int J = p.n_live;
     t.bt.resize(J);
@@ -127,26 +129,32 @@ void build_bin_tabs(const rf_plan_host& p, int NA, const std::vector<uint32_t>& 
                 ++t.nz[g];
             }
     }
-    // window x modulation tables regrouped per CTA group: entry (g, ti) = for each parity (w_r0, w_r1)
-    const int NP = NA == 5 ? 2 : 1;
-    t.wg_fwd.assign(static_cast<size_t>(2) * W * NP * 4, 0.f);
-    t.wg_inv.assign(static_cast<size_t>(2) * W * NP * 4, 0.f);
-    for (int g = 0; g < 2; ++g) {
-        const int r0 = g ? 1 : 0, r1 = g ? 3 : 2;
-        for (int ti = 0; ti < W; ++ti)
-            for (int par = 0; par < NP; ++par) {
-                const size_t o = ((static_cast<size_t>(g) * W + ti) * NP + par) * 4;
-                const size_t s0 = ((static_cast<size_t>(par) * 4 + r0) * W + ti) * 2;
-                const size_t s1 = ((static_cast<size_t>(par) * 4 + r1) * W + ti) * 2;
-                t.wg_fwd[o] = wt_fwd[s0];
-                t.wg_fwd[o + 1] = wt_fwd[s0 + 1];
-                t.wg_fwd[o + 2] = wt_fwd[s1];
-                t.wg_fwd[o + 3] = wt_fwd[s1 + 1];
-                t.wg_inv[o] = wt_inv[s0];
-                t.wg_inv[o + 1] = wt_inv[s0 + 1];
-                t.wg_inv[o + 2] = wt_inv[s1];
-                t.wg_inv[o + 3] = wt_inv[s1 + 1];
-            }
+    // radix-9 pass: item (a, c) of slot tau, and per (b, slot) the two windows and the r = 1 modulation at that sample
+    const uint16_t* perm = rf_pass_b_perm(NA);
+    const int n_items = 49 * NA;
+    t.items.resize(n_items);
+    t.wg_fwd.assign(static_cast<size_t>(W) * 4, 0.f);
+    t.wg_inv.assign(static_cast<size_t>(W) * 4, 0.f);
+    for (int tau = 0; tau < n_items; ++tau) {
+        const int a = perm[tau] / 49, c = perm[tau] % 49;
+        const int base = (441 * a + (W / 49) * c) % W;
+        t.items[tau] = static_cast<uint32_t>(a * 441 + c) | (static_cast<uint32_t>(base) << 12);
+        for (int bq = 0; bq < 9; ++bq) {
+            const int u = (base + (W / 9) * bq) % W;            // sample index within the (decimated) frame
+            const double ang = 2.0 * M_PI * static_cast<double>(u) / (NA == 5 ? p.N / 2 : p.N);
+            const double w0 = NA == 5 ? p.window[2 * u] : p.window[u];
+            const double w1 = NA == 5 ? p.window[2 * u + 1] : p.window[u];
+            const double fs = NA == 5 ? 2.0 : 1.0;              // half the samples carry the same spectrum at half the level
+            const size_t o = (static_cast<size_t>(bq) * n_items + tau) * 4;
+            t.wg_fwd[o] = static_cast<float>(fs * w0);
+            t.wg_fwd[o + 1] = static_cast<float>(fs * w1);
+            t.wg_fwd[o + 2] = static_cast<float>(std::cos(ang));
+            t.wg_fwd[o + 3] = static_cast<float>(-std::sin(ang));
+            t.wg_inv[o] = static_cast<float>(w0 / p.N);
+            t.wg_inv[o + 1] = static_cast<float>(w1 / p.N);
+            t.wg_inv[o + 2] = static_cast<float>(std::cos(ang));
+            t.wg_inv[o + 3] = static_cast<float>(std::sin(ang));
+        }
     }
 }
 
@@ -354,8 +362,8 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
                         }
     }
 
-    if (!p.generic) build_bin_tabs(p, 10, p.pp, nullptr, p.wt_fwd, p.wt_inv, p.t10);
-    if (p.decimate) build_bin_tabs(p, 5, p.pp2, &p.ph_odd, p.wt2_fwd, p.wt2_inv, p.t5);
+    if (!p.generic) build_bin_tabs(p, 10, p.pp, nullptr, p.t10);
+    if (p.decimate) build_bin_tabs(p, 5, p.pp2, &p.ph_odd, p.t5);
 
     // ---- sparse filterbank
     p.melcol_ptr.assign(p.n_mels + 1, 0);

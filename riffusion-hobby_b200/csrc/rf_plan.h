@@ -19,8 +19,10 @@ struct rf_bin_tabs {
     std::vector<uint32_t> bt;      // [n_live] V offset of bin k (s*W + idx) | V offset of its Hermitian partner << 14 | self-paired << 31
     std::vector<float> ab_inv;     // [n_live][4] alpha = conj(ph), beta = i conj(ph) conj(po):  Z[k] = alpha C0 + beta C1
     std::vector<float> ab_fwd;     // [n_live][4] gamma = ph/2, delta = -i ph po/2:  X_t = gamma (Zk + conj Zp), X_t+1 = delta (Zk - conj Zp)
-    std::vector<float> wg_fwd;     // [2 groups][W][NP][4]: (w_r0, w_r1) of parity 0 (then parity 1 for NA = 5), r0/r1 = the group's two r
-    std::vector<float> wg_inv;
+    std::vector<uint32_t> items;   // [49 NA] radix-9 pass: item (a, c) of slot tau as  a*441 + c | n'(a, 0, c) << 12  (rf_pass_b_perm)
+    std::vector<float> wg_fwd;     // [9][49 NA][4] per (b, slot): (w0, w1, cos t, -sin t), t = 2 pi n'/N; w0 / w1 = window at the
+                                   // sample of frame t0 / t0+1 (NA = 5: the two sample parities, times 2)
+    std::vector<float> wg_inv;     // same layout: (w0/N, w1/N, cos t, sin t)
     std::vector<uint16_t> zpos;    // V offsets no live bin or partner of the group writes: [nz[0] entries of group 0 | nz[1] of group 1]
     int nz[2] = {0, 0};
 };

@@ -32,6 +32,7 @@ rf_gl_tables tables(const rf_plan_host& h, int NA) {
     const rf_bin_tabs& t = NA == 10 ? h.t10 : h.t5;
     tb.wg_fwd = reinterpret_cast<const rf_f4*>(t.wg_fwd.data());
     tb.wg_inv = reinterpret_cast<const rf_f4*>(t.wg_inv.data());
+    tb.items = t.items.data();
     tb.bt = t.bt.data();
     tb.ab_inv = reinterpret_cast<const rf_f4*>(t.ab_inv.data());
     tb.ab_fwd = reinterpret_cast<const rf_f4*>(t.ab_fwd.data());
