@@ -377,14 +377,17 @@ __global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float
     const int b = blockIdx.y;
     if (v >= nxo + 2 * E) return;
     float* dst = xd + static_cast<size_t>(b) * (nxo + 2 * E);
+    // the decimated loop only exists for hop 441 / win 4410 / 16-frame chunks (rf_plan_build_host): compile-time
+    // constants turn the index divisions below into multiplies
+    (void)G, (void)H, (void)W;
     if (v < nxo) {
-        dst[v] = rf_ola_sample_d2(v, part_h + static_cast<size_t>(b) * 2 * nchunks * PLh, env[2 * v + 1], G, PLh,
-                                  nchunks, H, W);
+        dst[v] = rf_ola_sample_d2(v, part_h + static_cast<size_t>(b) * 2 * nchunks * PLh, env[2 * v + 1], RF_CHUNK, PLh,
+                                  nchunks, 441, RF_PW);
     } else {
         const int e = v - nxo;
         const int i = e < E ? e : L - 2 * E + e;
-        dst[v] = rf_ola_sample_edge(i, part_e + static_cast<size_t>(b) * 2 * nslots * PL, env[i], T, G, PL, c_tail,
-                                    nslots, H, W);
+        dst[v] = rf_ola_sample_edge(i, part_e + static_cast<size_t>(b) * 2 * nslots * PL, env[i], T, RF_CHUNK, PL, c_tail,
+                                    nslots, 441, RF_PW);
     }
 }
 
@@ -907,33 +910,6 @@ static int gl_loop_generic(rf_plan* p, const gl_ws& w, int B, int T, int n_iter,
     return RF_OK;
 }
 
-// Second stream of the hybrid decimated loop: the full-rate edge CTAs (112 KB of shared memory, 1.3 waves at 2 CTAs/SM: a
-// launch that is mostly tail) run BESIDE the half-rate launch instead of in front of it.  Fork / join through two events
-// per call; nothing outlives the call (stream and event destruction is deferred by the runtime until their work is done).
-struct gl_side {
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    cudaError_t init() {
-        cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
-        return e;
-    }
-    cudaError_t begin(cudaStream_t main) {   // side stream continues from here
-        cudaError_t e = cudaEventRecord(fork, main);
-        return e == cudaSuccess ? cudaStreamWaitEvent(s, fork, 0) : e;
-    }
-    cudaError_t end(cudaStream_t main) {     // main stream waits for what the side stream has been given
-        cudaError_t e = cudaEventRecord(join, s);
-        return e == cudaSuccess ? cudaStreamWaitEvent(main, join, 0) : e;
-    }
-    ~gl_side() {
-        if (fork) cudaEventDestroy(fork);
-        if (join) cudaEventDestroy(join);
-        if (s) cudaStreamDestroy(s);
-    }
-};
-
 static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float momentum_in, float* d_wave,
                    cudaStream_t st, gl_prof* prof = nullptr) {
     const rf_plan_host& h = p->h;
@@ -956,8 +932,6 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
 #endif
     const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
     const dim3 grid_a2((dg.nxo + 2 * dg.E + 255) / 256, B);
-    gl_side side;
-    if (dec && n_iter > 0) RF_CUDA_TRY(side.init());
     k_envelope<<<(L + 255) / 256, 256, 0, st>>>(p->d_win2, T, h.H, h.W, L, w.env);
     RF_CUDA_LAUNCH_CHECK("k_envelope");
     for (int it = 0; it <= n_iter; ++it) {
@@ -976,14 +950,12 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
         const bool half = dec && !last;   // the final reconstruction is always full rate
         if (prof) RF_CUDA_TRY(prof->mark(0, 0, st));
         if (half) {
-            RF_CUDA_TRY(side.begin(st));
-            k_istft_edge<<<dim3(dg.nslots * 2, B), RF_NT, smem_i, side.s>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL,
-                                                                            dg.c_tail, dg.nslots, w.part_e);
+            k_istft_edge<<<dim3(dg.nslots * 2, B), RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL,
+                                                                        dg.c_tail, dg.nslots, w.part_e);
             RF_CUDA_LAUNCH_CHECK("k_istft_edge");
             k_istft_half<<<dim3(w.nchunks * 2, B), RF_NT, smem_ih, st>>>(tb2, w.S, cur, prev, mode, m, T, RF_CHUNK, PLh,
                                                                          w.nchunks, w.part);
             RF_CUDA_LAUNCH_CHECK("k_istft_half");
-            RF_CUDA_TRY(side.end(st));
         } else
             k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
                                                          w.part);
@@ -1002,15 +974,13 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
         if (last) break;
         if (prof) RF_CUDA_TRY(prof->mark(2, 0, st));
         if (dec) {
-            RF_CUDA_TRY(side.begin(st));
-            k_stft_edge<<<dim3(dg.n_edge_pairs * 2, B), RF_NT, smem_f, side.s>>>(tb, w.xd, L, T, h.H, dg.nxo, dg.E,
-                                                                                dg.pr_tail, w.R[it & 1]);
+            k_stft_edge<<<dim3(dg.n_edge_pairs * 2, B), RF_NT, smem_f, st>>>(tb, w.xd, L, T, h.H, dg.nxo, dg.E, dg.pr_tail,
+                                                                            w.R[it & 1]);
             RF_CUDA_LAUNCH_CHECK("k_stft_edge");
             // the half-rate pairs [3, pr_tail): RF_STFT_HALF_PAIRS consecutive pairs per CTA
             k_stft_half<<<dim3((dg.pr_tail - 3 + RF_STFT_HALF_PAIRS - 1) / RF_STFT_HALF_PAIRS * 2, B), RF_NT, smem_fh, st>>>(
                 tb2, w.xd, L, T, h.H, dg.nxo, dg.E, 3, dg.pr_tail, w.R[it & 1]);
             RF_CUDA_LAUNCH_CHECK("k_stft_half");
-            RF_CUDA_TRY(side.end(st));
         } else
             k_stft_pair<<<grid_f, RF_NT, smem_f, st>>>(tb, d_wave, L, T, h.H, w.R[it & 1]);
         RF_CUDA_LAUNCH_CHECK("k_stft_pair");
