@@ -508,7 +508,8 @@ RF_HD float rf_ola_sample_d2(int v, const float* part, float env, int G, int PLh
 // therefore keeps two full-rate edge strips [0, E) and [L-E, L), E = W + H:
 //   * forward STFT: the first 3 frame pairs (frames 0..5) and the pairs from pr_tail = (T-6)/2 on read the strips at
 //     full rate, every other pair reads the odd-sample waveform xo;
-//   * inverse STFT: the frames that overlap the strips are chunk 0 (frames <= 15) and chunks >= c_tail = (T-17)/G;
+//   * inverse STFT: the frames that overlap the strips are frames <= 15 (chunk 0) and frames >= T-16 (frame t covers
+//     samples [tH - W/2, tH + W/2) and the tail strip starts at (T-1)H - W - H), i.e. chunks >= c_tail = (T-16)/G;
 //     those chunks are ALSO evaluated at full rate into `nslots` extra partial-sum slots (slot 0 = chunk 0, slot s =
 //     chunk c_tail + s - 1).
 struct rf_gl_dec_geom {
@@ -519,7 +520,7 @@ RF_HD rf_gl_dec_geom rf_dec_geom(int T, int G, int H, int W) {
     const int nchunks = (T + G - 1) / G;
     d.E = W + H;
     d.pr_tail = (T - 6) / 2;
-    d.c_tail = (T - 17) / G;
+    d.c_tail = (T - 16) / G;
     d.nslots = 1 + nchunks - d.c_tail;
     d.n_edge_pairs = 3 + (T + 1) / 2 - d.pr_tail;
     d.nxo = (H * (T - 1) - 1) / 2;
