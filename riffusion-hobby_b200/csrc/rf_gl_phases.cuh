@@ -191,8 +191,8 @@ RF_HD void rf_stft_pass_b(int tid, int nt, rf_c32* V, const float* xs, const rf_
 // out0/out1: rows of the [T][n_live] spectrum for frames t0, t0+1 (out1 may be null).
 //   X_t[k]   = ph (Z[k] + conj Z[N-k]) / 2 = gamma u,   X_t+1[k] = ph po (Z[k] - conj Z[N-k]) / 2i = delta v
 // (ph = exp(-2 pi i 3k/8): frame offset; po = exp(-2 pi i k/N): the odd-sample frame of a decimated pair)
-template <int NA, bool F1, int U>
-RF_HD void rf_stft_post_batch(int jb, int nt, const rf_c32* V, const rf_gl_tables& tb, rf_c32* out0, rf_c32* out1) {
+template <int NA, bool F1, int U, bool TAIL>
+RF_HD void rf_stft_post_batch(int jb, int j1, int nt, const rf_c32* V, const rf_gl_tables& tb, rf_c32* out0, rf_c32* out1) {
     const uint32_t* pbt = tb.bt + jb;
     const rf_f4* pgd = tb.ab_fwd + jb;
     rf_c32* o0 = out0 + jb;
@@ -201,11 +201,13 @@ RF_HD void rf_stft_post_batch(int jb, int nt, const rf_c32* V, const rf_gl_table
     rf_f4 gd[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        pw[u] = pbt[u * nt];
-        gd[u] = pgd[u * nt];
+        const int o = TAIL ? ((jb + u * nt < j1) ? u * nt : 0) : u * nt;
+        pw[u] = pbt[o];
+        gd[u] = pgd[o];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+        if (TAIL && u > 0 && jb + u * nt >= j1) continue;
         const rf_c32 zk = V[pw[u] & 16383u];
         const rf_c32 zp = V[(pw[u] >> 14) & 16383u];
         o0[u * nt] = c_mul(c_make(gd[u].x, gd[u].y), c_make(zk.x + zp.x, zk.y - zp.y));
@@ -216,9 +218,8 @@ template <int NA, bool F1>
 RF_HD void rf_stft_post_t(int tid, int nt, const rf_c32* V, const rf_gl_tables& tb, int j0, int j1, rf_c32* out0,
                           rf_c32* out1) {
     int jb = j0 + tid;
-    for (; jb + 3 * nt < j1; jb += 4 * nt) rf_stft_post_batch<NA, F1, 4>(jb, nt, V, tb, out0, out1);
-    for (; jb + nt < j1; jb += 2 * nt) rf_stft_post_batch<NA, F1, 2>(jb, nt, V, tb, out0, out1);
-    if (jb < j1) rf_stft_post_batch<NA, F1, 1>(jb, nt, V, tb, out0, out1);
+    for (; jb + 3 * nt < j1; jb += 4 * nt) rf_stft_post_batch<NA, F1, 4, false>(jb, j1, nt, V, tb, out0, out1);
+    if (jb < j1) rf_stft_post_batch<NA, F1, 4, true>(jb, j1, nt, V, tb, out0, out1);
 }
 template <int NA>
 RF_HD void rf_stft_post(int tid, int nt, const rf_c32* V, const rf_gl_tables& tb, int j0, int j1, rf_c32* out0,
@@ -284,8 +285,10 @@ struct rf_istft_in {
 // with C1' = C1 conj(po); alpha, beta are per-bin constants (rf_bin_tabs), so the phase factors cost two complex products.
 // All global loads of a batch of RF_LOAD_UNROLL bins are issued before any is used, so one DRAM latency is paid per
 // batch instead of per bin.  MODE / UP (update mode, momentum term present) are uniform over a launch and compiled out.
-template <int NA, int MODE, bool UP, int U>
-RF_HD void rf_istft_load_batch(int jb, int nt, rf_c32* V, const rf_gl_tables& tb, const rf_istft_in& in) {
+// TAIL: the last batch of a thread, slots past j1 are dropped (their loads are clamped onto the last bin, not predicated:
+// every thread then makes the same number of load -> use round trips, which is what the phase waits on)
+template <int NA, int MODE, bool UP, int U, bool TAIL>
+RF_HD void rf_istft_load_batch(int jb, int j1, int nt, rf_c32* V, const rf_gl_tables& tb, const rf_istft_in& in) {
     // bins jb, jb + nt, ..: one base pointer per array, the slots are constant offsets from it
     const uint32_t* pbt = tb.bt + jb;
     const rf_f4* pab = tb.ab_inv + jb;
@@ -302,17 +305,19 @@ RF_HD void rf_istft_load_batch(int jb, int nt, rf_c32* V, const rf_gl_tables& tb
     rf_c32 a0[U], a1[U], q0[U], q1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        pw[u] = pbt[u * nt];
-        ab[u] = pab[u * nt];
-        s0[u] = rf_ld_stream(pS0 + u * nt);
-        a0[u] = rf_ld_stream(pA0 + u * nt);
-        if (UP) q0[u] = rf_ld_stream(pQ0 + u * nt);
-        s1[u] = rf_ld_stream(pS1 + u * nt);
-        a1[u] = rf_ld_stream(pA1 + u * nt);
-        if (UP) q1[u] = rf_ld_stream(pQ1 + u * nt);
+        const int o = TAIL ? ((jb + u * nt < j1) ? u * nt : 0) : u * nt;
+        pw[u] = pbt[o];
+        ab[u] = pab[o];
+        s0[u] = rf_ld_stream(pS0 + o);
+        a0[u] = rf_ld_stream(pA0 + o);
+        if (UP) q0[u] = rf_ld_stream(pQ0 + o);
+        s1[u] = rf_ld_stream(pS1 + o);
+        a1[u] = rf_ld_stream(pA1 + o);
+        if (UP) q1[u] = rf_ld_stream(pQ1 + o);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+        if (TAIL && u > 0 && jb + u * nt >= j1) continue;
         const uint32_t p = pw[u];
         const rf_c32 c0 = rf_gl_coef<MODE, UP>(s0[u], a0[u], UP ? q0[u] : c_make(0.f, 0.f), mom);
         const rf_c32 c1 = rf_gl_coef<MODE, UP>(s1[u], a1[u], UP ? q1[u] : c_make(0.f, 0.f), mom);
@@ -334,9 +339,8 @@ RF_HD void rf_istft_load_batch(int jb, int nt, rf_c32* V, const rf_gl_tables& tb
 template <int NA, int MODE, bool UP>
 RF_HD void rf_istft_load_t(int tid, int nt, rf_c32* V, const rf_gl_tables& tb, int j0, int j1, const rf_istft_in& in) {
     int jb = j0 + tid;
-    for (; jb + 3 * nt < j1; jb += 4 * nt) rf_istft_load_batch<NA, MODE, UP, 4>(jb, nt, V, tb, in);
-    for (; jb + nt < j1; jb += 2 * nt) rf_istft_load_batch<NA, MODE, UP, 2>(jb, nt, V, tb, in);
-    if (jb < j1) rf_istft_load_batch<NA, MODE, UP, 1>(jb, nt, V, tb, in);
+    for (; jb + 3 * nt < j1; jb += 4 * nt) rf_istft_load_batch<NA, MODE, UP, 4, false>(jb, j1, nt, V, tb, in);
+    if (jb < j1) rf_istft_load_batch<NA, MODE, UP, 4, true>(jb, j1, nt, V, tb, in);
 }
 
 template <int NA>
