@@ -467,7 +467,10 @@ k_stft_edge(rf_gl_tables tb, const float* __restrict__ xd, int L, int T, int hop
 // are RF_XS_HALF_N consecutive odd samples xo[vo0 ..): ONE 1-D TMA bulk copy per pair instead of a load loop, and a CTA takes
 // RF_STFT_HALF_PAIRS consecutive pairs [pr_lo + P i, ..) < pr_hi so that the copy of the next pair flies during the four
 // passes of the current one (two staging buffers, one mbarrier each).
-__global__ void __launch_bounds__(RF_NT, RF_GL_HALF_MINB)
+#ifndef RF_STFT_HALF_MINB
+#define RF_STFT_HALF_MINB RF_GL_HALF_MINB   // 4 fits the shared memory (4 x 54.7 KB) but needs <= 64 registers (A/B builds)
+#endif
+__global__ void __launch_bounds__(RF_NT, RF_STFT_HALF_MINB)
 k_stft_half(rf_gl_tables tb2, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E, int pr_lo, int pr_hi,
             rf_c32* __restrict__ R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -63,10 +63,13 @@ struct rf_gl_tables {
 };
 
 // streaming (evict-first) loads for the spectra, which are read once per launch: the per-bin tables stay in L1
+#ifndef RF_GL_LD_CG
+#define RF_GL_LD_CG 0      // 1: ld.global.cg (L2 only) instead of ld.global.cs (evict-first) — A/B builds
+#endif
 #if defined(__CUDA_ARCH__)
-RF_HD float rf_ld_stream(const float* p) { return __ldcs(p); }
+RF_HD float rf_ld_stream(const float* p) { return RF_GL_LD_CG ? __ldcg(p) : __ldcs(p); }
 RF_HD rf_c32 rf_ld_stream(const rf_c32* p) {
-    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    const float2 v = RF_GL_LD_CG ? __ldcg(reinterpret_cast<const float2*>(p)) : __ldcs(reinterpret_cast<const float2*>(p));
     return c_make(v.x, v.y);
 }
 #else
