@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(320, 1)
 k_flash_attn(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
              const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    rf_pdl_trigger();      // PDL (rf_common.h): dependents may start their prologue
     constexpr int NSLAB = DPAD / 64;
     constexpr int Q_BYTES = NSLAB * TQ * 128;
     constexpr int K_BYTES = NSLAB * TK * 128;
@@ -109,6 +110,7 @@ k_flash_attn(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    rf_pdl_wait();         // prologue done; the producer grid must be complete before Q / K / V are read
     const uint32_t tmem_O = tmem_base + 256;
 
     if (warp == 0 && lane == 0) {
@@ -353,6 +355,7 @@ __global__ void __launch_bounds__(96 + 128 * NG, 1)
 k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    rf_pdl_trigger();      // PDL (rf_common.h): dependents may start their prologue
     constexpr int TKT = 256 / NG;                                 // keys per tile
     constexpr int KSL = TKT / 64;                                 // 64-key slabs per tile (P and V^T)
     constexpr int NSLAB = DPAD / 64;
@@ -420,6 +423,7 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    rf_pdl_wait();         // prologue done; the producer grid must be complete before Q / K / V are read
     const uint32_t tmem_O = tmem_base + 256;
 
     if (warp == 0 && lane == 0) {
@@ -722,6 +726,7 @@ __global__ void __launch_bounds__(160, 1)
 k_attn_short(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
              const __grid_constant__ CUtensorMap mapVt, const AttnParams p, int n_items, int nqb) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    rf_pdl_trigger();      // PDL (rf_common.h): dependents may start their prologue
     constexpr int NSLAB = DPAD / 64;
     constexpr int NVP = NV + 16;
     static_assert(256 + 2 * NVP <= 512, "TMEM budget");
@@ -775,6 +780,7 @@ k_attn_short(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    rf_pdl_wait();         // prologue done; the producer grid must be complete before Q / K / V are read
     const int n_mine = w1 - w0;
 
     if (warp == 0 && lane == 0 && n_mine > 0) {
@@ -999,8 +1005,7 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     static rf_dev_once once;
     const cudaError_t aerr = rf_set_smem_once(once, k_flash_attn<DPAD, NV, NS>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn): ") + cudaGetErrorString(aerr));
-    k_flash_attn<DPAD, NV, NS><<<grid, 320, smem, st>>>(mq, mk, mv, p);
-    RF_CUDA_LAUNCH_CHECK("k_flash_attn");
+    RF_LAUNCH_PDL("k_flash_attn", (k_flash_attn<DPAD, NV, NS>), grid, dim3(320), smem, st, mq, mk, mv, p);
     return RF_OK;
 }
 
@@ -1016,8 +1021,7 @@ int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     static rf_dev_once once;
     const cudaError_t aerr = rf_set_smem_once(once, k_flash_attn1<DPAD, NV, NKS, NVS, NG>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn1): ") + cudaGetErrorString(aerr));
-    k_flash_attn1<DPAD, NV, NKS, NVS, NG><<<grid, 96 + 128 * NG, smem, st>>>(mq, mk, mv, p);
-    RF_CUDA_LAUNCH_CHECK("k_flash_attn1");
+    RF_LAUNCH_PDL("k_flash_attn1", (k_flash_attn1<DPAD, NV, NKS, NVS, NG>), grid, dim3(96 + 128 * NG), smem, st, mq, mk, mv, p);
     return RF_OK;
 }
 
@@ -1041,8 +1045,7 @@ int launch_attn_short(const CUtensorMap& mq, const CUtensorMap& mk, const CUtens
     const int nqb = (p.Nq + TQ - 1) / TQ;
     const int n_items = nqb * p.heads * B;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    k_attn_short<DPAD, NV><<<grid, 160, smem, st>>>(mq, mk, mv, p, n_items, nqb);
-    RF_CUDA_LAUNCH_CHECK("k_attn_short");
+    RF_LAUNCH_PDL("k_attn_short", (k_attn_short<DPAD, NV>), dim3(grid), dim3(160), smem, st, mq, mk, mv, p, n_items, nqb);
     return RF_OK;
 }
 

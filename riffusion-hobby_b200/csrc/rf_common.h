@@ -43,3 +43,46 @@ inline cudaError_t rf_set_smem_once(rf_dev_once& o, F* func, int bytes) {
     if (e == cudaSuccess) o.done.fetch_or(bit, std::memory_order_release);
     return e;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A CFG UNet evaluation is ~440 dependent launches; with the attribute below the
+// next kernel's CTAs are scheduled as soon as every CTA of the current one has passed rf_pdl_trigger(), run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch) and then block in rf_pdl_wait() until the current grid has
+// completed and its writes are visible.  Rules that keep this safe:
+//   * a kernel launched through RF_LAUNCH_PDL executes rf_pdl_wait() in EVERY thread before its first global-memory access
+//     (reads of the producer's output and writes that could overtake the producer's reads alike);
+//   * everything else is launched the ordinary way and therefore still waits for full completion of its predecessor.
+// RF_PDL=0 in the environment launches without the attribute (the device instructions are then no-ops).
+#include <cstdlib>
+inline bool rf_pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RF_PDL");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    return on;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void rf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void rf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+// kernel may be a template-id in parentheses; extra attributes (cluster dimension) go in front of the PDL one
+#define RF_LAUNCH_PDL_ATTRS(name, kernel, grid, block, smem, st, attr_arr, n_attr, ...)                                   \
+    do {                                                                                                             \
+        cudaLaunchConfig_t _cfg = {};                                                                                \
+        _cfg.gridDim = (grid);                                                                                       \
+        _cfg.blockDim = (block);                                                                                     \
+        _cfg.dynamicSmemBytes = (smem);                                                                              \
+        _cfg.stream = (st);                                                                                          \
+        (attr_arr)[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                      \
+        (attr_arr)[n_attr].val.programmaticStreamSerializationAllowed = 1;                                               \
+        _cfg.attrs = (attr_arr);                                                                                        \
+        _cfg.numAttrs = (n_attr) + (rf_pdl_enabled() ? 1 : 0);                                                        \
+        const cudaError_t _le = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                                      \
+        if (_le != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_le)); \
+    } while (0)
+#define RF_LAUNCH_PDL(name, kernel, grid, block, smem, st, ...)                                                       \
+    do {                                                                                                             \
+        cudaLaunchAttribute _attr[1];                                                                                \
+        RF_LAUNCH_PDL_ATTRS(name, kernel, grid, block, smem, st, _attr, 0, __VA_ARGS__);                             \
+    } while (0)

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    rf_pdl_trigger();      // the next kernel may start its prologue; it blocks in its own rf_pdl_wait() until this grid is done
     // BN = 320 (pairs only): two 160-wide MMA instructions per K step share the A operand; the 320 accumulator columns
     // leave no room for a second set, so the epilogue of a tile does not overlap the next tile's MMAs (NBUF = 1) —
     // worth it for long K: 56 B/clk of operands per SM instead of 115 (the 1-SM 128 x 160 tile is L2-feed bound).
@@ -190,6 +191,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     else __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    rf_pdl_wait();         // barriers, TMEM and descriptors are set up: from here on global memory is touched
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -603,24 +605,17 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
         RF_CUDA_TRY(cudaEventCreate(&e1));
         RF_CUDA_TRY(cudaEventRecord(e0, st));
     }
-    if (PAIR) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(GEMM_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        RF_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES>, a0, a1, b, p));
-    } else {
-        k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES><<<grid, GEMM_THREADS, smem, st>>>(a0, a1, b, p);
+    {
+        cudaLaunchAttribute attr[2];
+        if (PAIR) {
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+        }
+        RF_LAUNCH_PDL_ATTRS("k_tc_gemm", (k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES>), grid, dim3(GEMM_THREADS), smem, st, attr,
+                            PAIR ? 1 : 0, a0, a1, b, p);
     }
-    RF_CUDA_LAUNCH_CHECK("k_tc_gemm");
     if (prof) {
         RF_CUDA_TRY(cudaEventRecord(e1, st));
         std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -42,6 +42,8 @@ __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); 
 __global__ void k_gn_partial_v(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, int HW, int C, int G,
                                int slab, int nslabs, float* __restrict__ part /*[B][nslabs][G][2]*/) {
     extern __shared__ float2 shp[];  // [PPI][C/2]
+    rf_pdl_trigger();      // PDL (rf_common.h)
+    rf_pdl_wait();
     const int b = blockIdx.y;
     const int C2 = C >> 1;
     const int c8 = threadIdx.x % (C >> 3), pp = threadIdx.x / (C >> 3), PPI = blockDim.x / (C >> 3);
@@ -110,6 +112,8 @@ __global__ void k_gn_apply_v(const __half* __restrict__ x, const __half* __restr
     // pass 2 folded in: every CTA reduces the slab partials of its image to (mean, rstd) per group — a few KB from L2, in a
     // fixed order (P strided sub-sums per group, then added in index order), instead of a separate launch
     __shared__ float st[64 * 2];              // [G][2] mean, rstd   (G <= 64)
+    rf_pdl_trigger();      // PDL (rf_common.h)
+    rf_pdl_wait();
     __shared__ float sub[64 * 8 * 2];
     const int b = blockIdx.y;
     {
@@ -229,6 +233,8 @@ __global__ void __launch_bounds__(256) k_layernorm_v(const __half* __restrict__ 
                                                      const __half* __restrict__ beta, int rows, float eps,
                                                      __half* __restrict__ y) {
     constexpr int NV = 5, C = 8 * NV * LPR, RPW = 32 / LPR;
+    rf_pdl_trigger();      // PDL (rf_common.h)
+    rf_pdl_wait();
     const int lane = threadIdx.x & 31, sub = lane % LPR;
     const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
     const bool ok = row < rows;
@@ -746,18 +752,16 @@ extern "C" int rf_group_norm_cat_f16(const void* x, const void* x2, int C1, int 
     float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
     const size_t smem = static_cast<size_t>(PPI) * (C / 2) * sizeof(float2);
     dim3 grid(nslabs, B);
-    k_gn_partial_v<<<grid, threads, smem, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(x2), C1, HW, C,
-                                                groups, slab, nslabs, part);
-    RF_CUDA_LAUNCH_CHECK("k_gn_partial_v");
+    RF_LAUNCH_PDL("k_gn_partial_v", k_gn_partial_v, grid, dim3(threads), smem, st, static_cast<const __half*>(x),
+                  static_cast<const __half*>(x2), C1, HW, C, groups, slab, nslabs, part);
     if (groups > 64 || threads < groups) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: at most 64 groups (and not more groups than threads)");
     // tanh form by default: measured on the full-size UNet, both forms leave the kernels AT the fp16-storage floor
     // (1.420e-3 vs 1.418e-3 from the fp32 oracle) and the exp form costs +0.4 ms per evaluation at batch 64
     static const int silu_form = getenv("RF_SILU_EXACT") ? 1 : 2;
-    k_gn_apply_v<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(x2), C1, part, nslabs,
-                                           1.f / (static_cast<float>(HW) * (C / groups)), eps,
-                                           static_cast<const __half*>(gamma), static_cast<const __half*>(beta), HW, C,
-                                           groups, act ? silu_form : 0, slab, static_cast<__half*>(y));
-    RF_CUDA_LAUNCH_CHECK("k_gn_apply_v");
+    RF_LAUNCH_PDL("k_gn_apply_v", k_gn_apply_v, grid, dim3(threads), size_t(0), st, static_cast<const __half*>(x),
+                  static_cast<const __half*>(x2), C1, static_cast<const float*>(part), nslabs,
+                  1.f / (static_cast<float>(HW) * (C / groups)), eps, static_cast<const __half*>(gamma),
+                  static_cast<const __half*>(beta), HW, C, groups, act ? silu_form : 0, slab, static_cast<__half*>(y));
     return RF_OK;
 }
 
@@ -773,10 +777,9 @@ extern "C" int rf_layer_norm_f16(const void* x, int rows, int C, const void* gam
         const __half *xp = static_cast<const __half*>(x), *gp = static_cast<const __half*>(gamma),
                      *bp = static_cast<const __half*>(beta);
         __half* yp = static_cast<__half*>(y);
-        if (C == 320) k_layernorm_v<8><<<blocks, 256, 0, st>>>(xp, gp, bp, rows, eps, yp);
-        else if (C == 640) k_layernorm_v<16><<<blocks, 256, 0, st>>>(xp, gp, bp, rows, eps, yp);
-        else k_layernorm_v<32><<<blocks, 256, 0, st>>>(xp, gp, bp, rows, eps, yp);
-        RF_CUDA_LAUNCH_CHECK("k_layernorm_v");
+        if (C == 320) RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<8>, dim3(blocks), dim3(256), size_t(0), st, xp, gp, bp, rows, eps, yp);
+        else if (C == 640) RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<16>, dim3(blocks), dim3(256), size_t(0), st, xp, gp, bp, rows, eps, yp);
+        else RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<32>, dim3(blocks), dim3(256), size_t(0), st, xp, gp, bp, rows, eps, yp);
         return RF_OK;
     }
     k_layernorm<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
