@@ -43,8 +43,10 @@ struct rf_plan {
         rf_f4* ab_inv = nullptr;
         rf_f4* ab_fwd = nullptr;
         uint16_t* zpos = nullptr;
-    } d10, d5;
-    float* d_zero_row = nullptr;   // [n_live] zeros                     // d5: decimated-loop tables (null when not eligible)
+    } d10, d5;                     // d5: decimated-loop tables (null when not eligible)
+    rf_f4* d5e_wg_inv = nullptr;   // other-parity inverse tables of the decimated grid (rf_plan_host::t5e)
+    rf_f4* d5e_ab_inv = nullptr;
+    float* d_zero_row = nullptr;   // [n_live] zeros
     int32_t* d_bins = nullptr;
     int32_t* d_jofk = nullptr;
     float* d_win2 = nullptr;
@@ -130,7 +132,11 @@ static int rf_plan_upload(rf_plan* p) {
         th[2 * h.n_mels + i] = h.thomas[h.n_mels + i];  // inv_den
     }
     RF_CUDA_TRY(upload(p, &p->d_thomas, th.data(), th.size()));
-    if (h.decimate) RF_CUDA_TRY(upload_tabs(p, &p->d5, h.t5));
+    if (h.decimate) {
+        RF_CUDA_TRY(upload_tabs(p, &p->d5, h.t5));
+        RF_CUDA_TRY(upload(p, &p->d5e_wg_inv, h.t5e.wg_inv.data(), h.t5e.wg_inv.size() / 4));
+        RF_CUDA_TRY(upload(p, &p->d5e_ab_inv, h.t5e.ab_inv.data(), h.t5e.ab_inv.size() / 4));
+    }
     if (h.generic) {
         RF_CUDA_TRY(upload(p, &p->d_window, h.window.data(), h.window.size()));
         RF_CUDA_TRY(upload(p, &p->d_roots2, h.roots2.data(), h.roots2.size() / 2));
@@ -321,34 +327,37 @@ k_istft_chunk(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __rest
                          part + ((static_cast<size_t>(b) * 2 + g) * nchunks + chunk) * PL);
 }
 
-// hybrid decimated loop (rf_gl_dec_geom), two launches with their own footprints:
-//   k_istft_edge: grid (nslots*2, B) — the chunks that overlap the full-rate edge strips, redone at full rate
-//                 (part_e[b][g][slot][PL]; 112 KB of shared memory, 2 CTAs/SM)
-//   k_istft_half: grid (nchunks*2, B) — half-rate partial sums of every chunk (part_h[b][g][chunk][PLh]); 2205-point
-//                 sub-transforms: 57 KB of shared memory and <= 85 registers with the 7-thread radix-49 pass -> 3 CTAs/SM
-// (one merged launch had to give every CTA the full-rate footprint: 2 CTAs/SM for the 91 % of CTAs that are half rate)
-__global__ void __launch_bounds__(RF_NT, 2)
-k_istft_edge(rf_gl_tables tb, const float* __restrict__ S, const rf_c32* __restrict__ cur,
-             const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PL, int c_tail, int nslots,
-             float* __restrict__ part_e) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int g = blockIdx.x & 1, b = blockIdx.y, idx = blockIdx.x >> 1;
-    const int chunk = idx == 0 ? 0 : c_tail + idx - 1;
-    istft_chunk_body<10>(smem_raw, tb, S, cur, prev, mode, momentum, T, G, PL, 2 * tb.off1, b, g, chunk,
-                         part_e + ((static_cast<size_t>(b) * 2 + g) * nslots + idx) * PL);
-}
-
+// hybrid decimated loop (rf_gl_dec_geom): grid ((nchunks + nslots) * 2, B)
+//   blocks [0, nchunks*2): half-rate partial sums of every chunk (part_h[b][g][chunk][PLh]): the waveform samples at even
+//                 padded positions q (odd sample index i).  2205-point sub-transforms: 57 KB of shared memory and <= 85
+//                 registers with the 7-thread radix-49 pass -> 3 CTAs/SM
+//   blocks behind: the edge chunks (slot 0 = chunk 0, slot s = chunk c_tail + s - 1) once more on the OTHER sample parity
+//                 (tables tbo: frame t0 takes the odd live samples, frame t0+1 the even ones) -> part_o[b][g][slot][PLh],
+//                 the samples at odd q.  Together the two parities are the full-rate edge strips: the inverse transform of a
+//                 band-limited spectrum is exact on any sample subset, so nothing aliases here (the forward side is where
+//                 the strips are needed).  Round 2's separate full-rate launch for these chunks (112 KB, 2 CTAs/SM, one
+//                 under-filled wave of long CTAs: 0.2 ms of every iteration) is gone.
 #ifndef RF_GL_HALF_MINB
 #define RF_GL_HALF_MINB 3   // CTAs per SM the half-rate kernels are compiled for (A/B builds: 2)
 #endif
 __global__ void __launch_bounds__(RF_NT, RF_GL_HALF_MINB)
-k_istft_half(rf_gl_tables tb2, const float* __restrict__ S, const rf_c32* __restrict__ cur,
-             const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PLh, int nchunks,
-             float* __restrict__ part_h) {
+k_istft_half(rf_gl_tables tb2, rf_gl_tables tbo, const float* __restrict__ S, const rf_c32* __restrict__ cur,
+             const rf_c32* __restrict__ prev, int mode, float momentum, int T, int G, int PLh, int nchunks, int c_tail,
+             int nslots, float* __restrict__ part_h, float* __restrict__ part_o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = blockIdx.x & 1, b = blockIdx.y, idx = blockIdx.x >> 1;
-    istft_chunk_body<5>(smem_raw, tb2, S, cur, prev, mode, momentum, T, G, PLh, 2 * tb2.off1 - 1, b, g, idx,
-                        part_h + ((static_cast<size_t>(b) * 2 + g) * nchunks + idx) * PLh);
+    const bool other = idx >= nchunks;                       // an edge chunk on the other sample parity
+    const int slot = idx - nchunks;
+    const int chunk = !other ? idx : (slot == 0 ? 0 : c_tail + slot - 1);
+    float* dst = !other ? part_h + ((static_cast<size_t>(b) * 2 + g) * nchunks + idx) * PLh
+                        : part_o + ((static_cast<size_t>(b) * 2 + g) * nslots + slot) * PLh;
+    rf_gl_tables tb = tb2;                                   // the two table sets differ in three fields
+    if (other) {
+        tb.wg_inv = tbo.wg_inv;
+        tb.ab_inv = tbo.ab_inv;
+        tb.off1 = tbo.off1;
+    }
+    istft_chunk_body<5>(smem_raw, tb, S, cur, prev, mode, momentum, T, G, PLh, 441, b, g, chunk, dst);
 }
 
 // ---- overlap-add assembly: x[b][i] = sum(parts) / envelope, kept region only --------------
@@ -369,25 +378,27 @@ __global__ void k_ola_assemble(const float* __restrict__ part, const float* __re
 }
 
 // decimated assembly: xd[b] = [ xo (nxo odd samples 2v+1) | head strip x[0..E) | tail strip x[L-E..L) ]
-__global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float* __restrict__ part_e,
-                                   const float* __restrict__ env, int T, int G, int PL, int PLh, int nchunks,
-                                   int c_tail, int nslots, int H, int W, int L, int nxo, int E,
-                                   float* __restrict__ xd) {
+// strip sample i sits at padded position q = W/2 + i: even q = an ordinary half-rate sample, odd q from the other-parity
+// partial sums of the edge chunks.  The decimated loop only exists for hop 441 / win 4410 / 16-frame chunks
+// (rf_plan_build_host): compile-time constants turn the index divisions into multiplies.
+__global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float* __restrict__ part_o,
+                                   const float* __restrict__ env, int T, int PLh, int nchunks, int c_tail, int nslots,
+                                   int L, int nxo, int E, float* __restrict__ xd) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (v >= nxo + 2 * E) return;
     float* dst = xd + static_cast<size_t>(b) * (nxo + 2 * E);
-    // the decimated loop only exists for hop 441 / win 4410 / 16-frame chunks (rf_plan_build_host): compile-time
-    // constants turn the index divisions below into multiplies
-    (void)G, (void)H, (void)W;
+    const float* ph = part_h + static_cast<size_t>(b) * 2 * nchunks * PLh;
     if (v < nxo) {
-        dst[v] = rf_ola_sample_d2(v, part_h + static_cast<size_t>(b) * 2 * nchunks * PLh, env[2 * v + 1], RF_CHUNK, PLh,
-                                  nchunks, 441, RF_PW);
+        dst[v] = rf_ola_sample_d2(v, ph, env[2 * v + 1], RF_CHUNK, PLh, nchunks, 441, RF_PW);
     } else {
         const int e = v - nxo;
         const int i = e < E ? e : L - 2 * E + e;
-        dst[v] = rf_ola_sample_edge(i, part_e + static_cast<size_t>(b) * 2 * nslots * PL, env[i], T, RF_CHUNK, PL, c_tail,
-                                    nslots, 441, RF_PW);
+        if (i & 1)
+            dst[v] = rf_ola_sample_d2((i - 1) >> 1, ph, env[i], RF_CHUNK, PLh, nchunks, 441, RF_PW);
+        else
+            dst[v] = rf_ola_sample_d2_slots(RF_PW / 2 + i, part_o + static_cast<size_t>(b) * 2 * nslots * PLh, env[i], T,
+                                            RF_CHUNK, PLh, c_tail, nslots, 441, RF_PW);
     }
 }
 
@@ -798,7 +809,7 @@ struct gl_ws {
     rf_c32* R[2];
     float* part;
     float* env;
-    float* part_e;  // decimated loop: full-rate partial sums of the edge chunks [B][2][nslots][PL]
+    float* part_e;  // decimated loop: other-parity half-rate partial sums of the edge chunks [B][2][nslots][PLh]
     float* xd;      // decimated loop: [B][nxo + 2E] odd samples + the two full-rate edge strips
     size_t total;
     int nchunks, PL;
@@ -826,7 +837,7 @@ static gl_ws gl_layout(const rf_plan* p, int B, int T, void* base) {
     if (p->h.decimate && rf_dec_ok(T, RF_CHUNK)) {
         const rf_gl_dec_geom d = rf_dec_geom(T, RF_CHUNK, p->h.H, p->h.W);
         w.part_e = reinterpret_cast<float*>(b + off);
-        off += align256(static_cast<size_t>(B) * 2 * d.nslots * w.PL * 4);
+        off += align256(static_cast<size_t>(B) * 2 * d.nslots * ((w.PL + 1) / 2) * 4);
         w.xd = reinterpret_cast<float*>(b + off);
         off += align256(static_cast<size_t>(B) * (d.nxo + 2 * d.E) * 4);
     }
@@ -852,7 +863,6 @@ static int check_T(const rf_plan* p, int T, const char* who) {
 static int set_smem_attrs() {
     static rf_dev_once once[8];
     cudaError_t err = rf_set_smem_once(once[0], k_istft_chunk, 200 * 1024);
-    if (err == cudaSuccess) err = rf_set_smem_once(once[1], k_istft_edge, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[6], k_istft_half, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[7], k_stft_half, 200 * 1024);
     if (err == cudaSuccess) err = rf_set_smem_once(once[2], k_stft_pair, 200 * 1024);
@@ -923,6 +933,10 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const float m = static_cast<float>(static_cast<double>(momentum_in) / (1.0 + static_cast<double>(momentum_in)));
     const bool dec = h.decimate && p->use_decimation && p->d5.bt != nullptr && w.xd != nullptr;
     const rf_gl_tables tb2 = dec ? make_tables(p, 5) : tb;
+    rf_gl_tables tbo = tb2;        // the other sample parity of the decimated grid (edge chunks): frame t0+1 starts (H-1)/2 later
+    tbo.wg_inv = p->d5e_wg_inv;
+    tbo.ab_inv = p->d5e_ab_inv;
+    tbo.off1 = (h.H - 1) / 2;
     const rf_gl_dec_geom dg = rf_dec_geom(T, RF_CHUNK, h.H, h.W);
     const int PLh = ((RF_CHUNK - 1) * h.H + h.W + 1) / 2;
     const size_t smem_i = 2 * RF_PW * sizeof(rf_c32) + static_cast<size_t>(w.PL) * 4;
@@ -953,11 +967,8 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
         const bool half = dec && !last;   // the final reconstruction is always full rate
         if (prof) RF_CUDA_TRY(prof->mark(0, 0, st));
         if (half) {
-            k_istft_edge<<<dim3(dg.nslots * 2, B), RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL,
-                                                                        dg.c_tail, dg.nslots, w.part_e);
-            RF_CUDA_LAUNCH_CHECK("k_istft_edge");
-            k_istft_half<<<dim3(w.nchunks * 2, B), RF_NT, smem_ih, st>>>(tb2, w.S, cur, prev, mode, m, T, RF_CHUNK, PLh,
-                                                                         w.nchunks, w.part);
+            k_istft_half<<<dim3((w.nchunks + dg.nslots) * 2, B), RF_NT, smem_ih, st>>>(
+                tb2, tbo, w.S, cur, prev, mode, m, T, RF_CHUNK, PLh, w.nchunks, dg.c_tail, dg.nslots, w.part, w.part_e);
             RF_CUDA_LAUNCH_CHECK("k_istft_half");
         } else
             k_istft_chunk<<<grid_i, RF_NT, smem_i, st>>>(tb, w.S, cur, prev, mode, m, T, RF_CHUNK, w.PL, w.nchunks,
@@ -968,8 +979,8 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
             RF_CUDA_TRY(prof->mark(1, 0, st));
         }
         if (half)
-            k_ola_assemble_dec<<<grid_a2, 256, 0, st>>>(w.part, w.part_e, w.env, T, RF_CHUNK, w.PL, PLh, w.nchunks,
-                                                        dg.c_tail, dg.nslots, h.H, h.W, L, dg.nxo, dg.E, w.xd);
+            k_ola_assemble_dec<<<grid_a2, 256, 0, st>>>(w.part, w.part_e, w.env, T, PLh, w.nchunks, dg.c_tail, dg.nslots, L,
+                                                        dg.nxo, dg.E, w.xd);
         else
             k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, w.env, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L, d_wave);
         RF_CUDA_LAUNCH_CHECK("k_ola_assemble");

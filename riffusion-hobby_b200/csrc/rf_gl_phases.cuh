@@ -535,23 +535,22 @@ RF_HD rf_gl_dec_geom rf_dec_geom(int T, int G, int H, int W) {
 }
 RF_HD bool rf_dec_ok(int T, int G) { return T >= 4 * G; }
 
-// full-rate overlap-add sample i inside an edge strip from the edge slots; part_e: [2 groups][nslots][PL]
-RF_HD float rf_ola_sample_edge(int i, const float* part_e, float env, int T, int G, int PL, int c_tail, int nslots,
-                               int H, int W) {
-    const int q = W / 2 + i;
+// Edge-strip sample at padded position q = W/2 + i with q ODD (i even) from the other-parity half-rate partial sums of the
+// edge chunks (the q-even strip samples are ordinary half-rate samples: rf_ola_sample_d2 with v = (i-1)/2).
+// part_o: [2 groups][nslots][PLh], slot 0 = chunk 0, slot s = chunk c_tail + s - 1; position (q - c G H) >> 1 within a chunk.
+RF_HD float rf_ola_sample_d2_slots(int q, const float* part_o, float env, int T, int G, int PLh, int c_tail, int nslots,
+                                   int H, int W) {
     const int t_hi = (T - 1 < q / H) ? T - 1 : q / H;
-    int t_lo = (q - W + H) / H;
+    int t_lo = (q - W + H) / H;  // ceil((q-W+1)/H)
     if (q - W + 1 <= 0) t_lo = 0;
     const int c_lo = t_lo / G, c_hi = t_hi / G;
     float acc = 0.f;
     for (int g = 0; g < 2; ++g)
         for (int c = c_lo; c <= c_hi; ++c) {
-            const int off = q - c * G * H;
-            const int nf = (G < T - c * G) ? G : T - c * G;
+            if (c != 0 && c < c_tail) continue;      // not an edge chunk: its frames do not reach the strips
             const int slot = c == 0 ? 0 : c - c_tail + 1;
-            if (off >= 0 && off < (nf - 1) * H + W)
-                acc += part_e[(static_cast<size_t>(g) * nslots + slot) * PL + off];
+            const int off = (q - c * G * H) >> 1;
+            if (slot < nslots && off >= 0 && off < PLh) acc += part_o[(static_cast<size_t>(g) * nslots + slot) * PLh + off];
         }
     return acc / env;
 }
-

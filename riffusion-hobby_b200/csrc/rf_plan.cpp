@@ -81,8 +81,11 @@ std::vector<float> melscale_fbanks_f32(int n_freqs, float f_min, float f_max, in
 #include "rf_pass_b_perm.inc"
 
 // kernel-side forms of the per-bin / per-sample tables (rf_bin_tabs) for one prime-factor grid
+// swap (NA = 5, inverse tables only): the OTHER sample parity of the decimated grid — frame t0 takes the odd live samples
+// n' = 2u+1 (so it, not frame t0+1, carries the extra modulation exp(2 pi i k/N)) and frame t0+1 the even ones: the
+// half-rate inverse transform then yields the waveform samples the regular half-rate pass skips (rf_plan_host::t5e)
 void build_bin_tabs(const rf_plan_host& p, int NA, const std::vector<uint32_t>& pp, const std::vector<float>* ph_odd,
-                    rf_bin_tabs& t) {
+                    rf_bin_tabs& t, bool swap = false) {
     const int W = NA * 441;
     const int J = p.n_live;
     t.bt.resize(J);
@@ -110,10 +113,17 @@ void build_bin_tabs(const rf_plan_host& p, int NA, const std::vector<uint32_t>& 
         // e = ph * po
         const double ex = phx * pox - phy * poy, ey = phx * poy + phy * pox;
         float* ai = &t.ab_inv[static_cast<size_t>(j) * 4];
-        ai[0] = static_cast<float>(phx);      // alpha = conj(ph)
-        ai[1] = static_cast<float>(-phy);
-        ai[2] = static_cast<float>(ey);       // beta = i conj(e) = (ey, ex)
-        ai[3] = static_cast<float>(ex);
+        if (!swap) {
+            ai[0] = static_cast<float>(phx);      // alpha = conj(ph)
+            ai[1] = static_cast<float>(-phy);
+            ai[2] = static_cast<float>(ey);       // beta = i conj(e) = (ey, ex)
+            ai[3] = static_cast<float>(ex);
+        } else {
+            ai[0] = static_cast<float>(ex);       // alpha = conj(ph) conj(po) = conj(e)
+            ai[1] = static_cast<float>(-ey);
+            ai[2] = static_cast<float>(phy);      // beta = i conj(ph) = (phy, phx)
+            ai[3] = static_cast<float>(phx);
+        }
         float* af = &t.ab_fwd[static_cast<size_t>(j) * 4];
         af[0] = static_cast<float>(0.5 * phx);   // gamma = ph / 2
         af[1] = static_cast<float>(0.5 * phy);
@@ -142,8 +152,8 @@ void build_bin_tabs(const rf_plan_host& p, int NA, const std::vector<uint32_t>& 
         for (int bq = 0; bq < 9; ++bq) {
             const int u = (base + (W / 9) * bq) % W;            // sample index within the (decimated) frame
             const double ang = 2.0 * M_PI * static_cast<double>(u) / (NA == 5 ? p.N / 2 : p.N);
-            const double w0 = NA == 5 ? p.window[2 * u] : p.window[u];
-            const double w1 = NA == 5 ? p.window[2 * u + 1] : p.window[u];
+            const double w0 = NA == 5 ? p.window[2 * u + (swap ? 1 : 0)] : p.window[u];
+            const double w1 = NA == 5 ? p.window[2 * u + (swap ? 0 : 1)] : p.window[u];
             const double fs = NA == 5 ? 2.0 : 1.0;              // half the samples carry the same spectrum at half the level
             const size_t o = (static_cast<size_t>(bq) * n_items + tau) * 4;
             t.wg_fwd[o] = static_cast<float>(fs * w0);
@@ -363,7 +373,10 @@ std::string rf_plan_build_host(const rf_plan_desc& d, const float* window, const
     }
 
     if (!p.generic) build_bin_tabs(p, 10, p.pp, nullptr, p.t10);
-    if (p.decimate) build_bin_tabs(p, 5, p.pp2, &p.ph_odd, p.t5);
+    if (p.decimate) {
+        build_bin_tabs(p, 5, p.pp2, &p.ph_odd, p.t5);
+        build_bin_tabs(p, 5, p.pp2, &p.ph_odd, p.t5e, true);
+    }
 
     // ---- sparse filterbank
     p.melcol_ptr.assign(p.n_mels + 1, 0);

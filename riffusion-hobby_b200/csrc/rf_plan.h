@@ -46,6 +46,8 @@ struct rf_plan_host {
     std::vector<float> wt2_inv;   // same layout,                  w[2u+par]/N * exp(+2 pi i r u/8820)
     std::vector<float> ph_odd;    // [n_live][2]  exp(-2 pi i k/N)
     rf_bin_tabs t10, t5;          // kernel-side forms (t5 empty unless `decimate`)
+    rf_bin_tabs t5e;              // t5 for the other sample parity (inverse tables ab_inv / wg_inv only differ): the hybrid loop's
+                                  // edge chunks run the half-rate inverse transform on both parities instead of a full-rate one
     // mel filterbank in sparse forms over the private bin order
     std::vector<int32_t> melcol_ptr;  // [n_mels+1]  CSR by mel column: entries (j, w)
     std::vector<int32_t> melcol_j;

@@ -27,9 +27,10 @@ void phase(F f) {
     for (int tid = 0; tid < NT; ++tid) f(tid);
 }
 
-rf_gl_tables tables(const rf_plan_host& h, int NA) {
+// other = true (NA = 5 only): the inverse tables of the other sample parity (rf_plan_host::t5e), as gl_loop() builds `tbo`
+rf_gl_tables tables(const rf_plan_host& h, int NA, bool other = false) {
     rf_gl_tables tb;
-    const rf_bin_tabs& t = NA == 10 ? h.t10 : h.t5;
+    const rf_bin_tabs& t = NA == 10 ? h.t10 : (other ? h.t5e : h.t5);
     tb.wg_fwd = reinterpret_cast<const rf_f4*>(t.wg_fwd.data());
     tb.wg_inv = reinterpret_cast<const rf_f4*>(t.wg_inv.data());
     tb.items = t.items.data();
@@ -42,7 +43,7 @@ rf_gl_tables tables(const rf_plan_host& h, int NA) {
     static std::vector<float> zero_row;
     if (static_cast<int>(zero_row.size()) < h.n_live) zero_row.assign(h.n_live, 0.f);
     tb.zero_row = zero_row.data();
-    tb.off1 = NA == 10 ? h.H : (h.H + 1) / 2;
+    tb.off1 = NA == 10 ? h.H : (other ? (h.H - 1) / 2 : (h.H + 1) / 2);
     tb.n_live = h.n_live;
     tb.n_even = h.n_even;
     return tb;
@@ -82,11 +83,11 @@ void emu_stft_clip(const rf_plan_host& h, const float* x, int L, int T, rf_c32* 
 // emulates istft_chunk_body<NA> for one (chunk, group): dst[PL]
 template <int NA>
 void emu_istft_chunk(const rf_plan_host& h, const float* S, const rf_c32* cur, const rf_c32* prev, int mode,
-                     float momentum, int T, int PL, int g, int chunk, float* dst) {
-    const rf_gl_tables tb = tables(h, NA);
+                     float momentum, int T, int PL, int g, int chunk, float* dst, bool other = false) {
+    const rf_gl_tables tb = tables(h, NA, other);
     constexpr int W = rf_geom<NA>::W;
     const int G = RF_CHUNK;
-    const int pair_stride = NA == 10 ? 2 * tb.off1 : 2 * tb.off1 - 1;
+    const int pair_stride = NA == 10 ? 2 * h.H : h.H;
     std::vector<rf_c32> V(2 * W, c_make(NAN, NAN));   // shared memory starts out as garbage on the device
     std::vector<float> ola(PL, 0.f);
     const int f0 = chunk * G;
@@ -144,29 +145,35 @@ void emu_istft_clip(const rf_plan_host& h, const float* S, const rf_c32* cur, co
             x[i] = rf_ola_sample(i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PL, nchunks, h.H,
                                  h.W);
     } else {
-        for (int v = 0; v < (L - 1) / 2; ++v)
+        for (int v = 0; v < L / 2; ++v)      // every odd sample index 2v+1 < L (the device's xo holds (L-1)/2 of them; the
+                                             // last one of an even L only exists in the tail strip)
             x[v] = rf_ola_sample_d2(v, part.data(), rf_envelope(2 * v + 1, win2.data(), T, h.H, h.W), G, PL, nchunks,
                                     h.H, h.W);
     }
 }
 
-// the full-rate edge slots of k_istft_dec + the strip part of k_ola_assemble_dec: xe[2E] = head strip | tail strip
+// the edge strips of the hybrid loop as k_istft_half + k_ola_assemble_dec produce them: xe[2E] = head strip | tail strip.
+// Odd sample indices i are ordinary half-rate samples (xo[(i-1)/2], from emu_istft_clip<5>), even ones come from the edge
+// chunks evaluated on the other sample parity.
 void emu_istft_edges(const rf_plan_host& h, const float* S, const rf_c32* cur, const rf_c32* prev, int mode,
-                     float momentum, int T, float* xe) {
+                     float momentum, int T, const float* xo, float* xe) {
     const int G = RF_CHUNK;
     const rf_gl_dec_geom d = rf_dec_geom(T, G, h.H, h.W);
-    const int PL = (G - 1) * h.H + h.W;
-    std::vector<float> part(static_cast<size_t>(2) * d.nslots * PL, 0.f);
+    const int PLh = ((G - 1) * h.H + h.W + 1) / 2;
+    std::vector<float> part(static_cast<size_t>(2) * d.nslots * PLh, 0.f);
     for (int slot = 0; slot < d.nslots; ++slot)
         for (int g = 0; g < 2; ++g)
-            emu_istft_chunk<10>(h, S, cur, prev, mode, momentum, T, PL, g, slot == 0 ? 0 : d.c_tail + slot - 1,
-                                &part[(static_cast<size_t>(g) * d.nslots + slot) * PL]);
+            emu_istft_chunk<5>(h, S, cur, prev, mode, momentum, T, PLh, g, slot == 0 ? 0 : d.c_tail + slot - 1,
+                               &part[(static_cast<size_t>(g) * d.nslots + slot) * PLh], true);
     const std::vector<float> win2 = window_sq(h);
     const int L = h.H * (T - 1);
     for (int e = 0; e < 2 * d.E; ++e) {
         const int i = e < d.E ? e : L - 2 * d.E + e;
-        xe[e] = rf_ola_sample_edge(i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PL, d.c_tail,
-                                   d.nslots, h.H, h.W);
+        if (i & 1)
+            xe[e] = xo[(i - 1) >> 1];
+        else
+            xe[e] = rf_ola_sample_d2_slots(h.W / 2 + i, part.data(), rf_envelope(i, win2.data(), T, h.H, h.W), T, G, PLh,
+                                           d.c_tail, d.nslots, h.H, h.W);
     }
 }
 }  // namespace
@@ -236,7 +243,12 @@ void emu_istft(void* p, const float* lin, const float* angles, int T, int half, 
             S[static_cast<size_t>(t) * h->n_live + j] = lin[src];
             R1[static_cast<size_t>(t) * h->n_live + j] = c_make(angles[2 * src], angles[2 * src + 1]);
         }
-    if (half) emu_istft_clip<5>(*h, S.data(), R1.data(), nullptr, 0, 0.f, T, wave);
+    if (half) {
+        const int L = h->H * (T - 1);
+        std::vector<float> xo(static_cast<size_t>(L) / 2 + 1);
+        emu_istft_clip<5>(*h, S.data(), R1.data(), nullptr, 0, 0.f, T, xo.data());
+        std::memcpy(wave, xo.data(), static_cast<size_t>((L - 1) / 2) * sizeof(float));
+    }
     else emu_istft_clip<10>(*h, S.data(), R1.data(), nullptr, 0, 0.f, T, wave);
 }
 
@@ -278,7 +290,7 @@ void emu_griffinlim2(void* p, const float* lin, const float* angles, int T, int 
         const bool last = it == n_iter;
         if (dec && !last) {
             emu_istft_clip<5>(*h, S.data(), cur, prev, mode, m, T, xo.data());
-            emu_istft_edges(*h, S.data(), cur, prev, mode, m, T, xe.data());
+            emu_istft_edges(*h, S.data(), cur, prev, mode, m, T, xo.data(), xe.data());
         } else {
             emu_istft_clip<10>(*h, S.data(), cur, prev, mode, m, T, wave);
         }
