@@ -381,25 +381,31 @@ __global__ void k_ola_assemble(const float* __restrict__ part, const float* __re
 // strip sample i sits at padded position q = W/2 + i: even q = an ordinary half-rate sample, odd q from the other-parity
 // partial sums of the edge chunks.  The decimated loop only exists for hop 441 / win 4410 / 16-frame chunks
 // (rf_plan_build_host): compile-time constants turn the index divisions into multiplies.
-__global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float* __restrict__ part_o,
-                                   const float* __restrict__ env, int T, int PLh, int nchunks, int c_tail, int nslots,
-                                   int L, int nxo, int E, float* __restrict__ xd) {
+// (two kernels: the strip samples need frame-accurate chunk bounds and twice the registers; kept out of the streaming one)
+__global__ void k_ola_assemble_dec(const float* __restrict__ part_h, const float* __restrict__ env, int PLh, int nchunks,
+                                   int nxo, int E, float* __restrict__ xd) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (v >= nxo + 2 * E) return;
-    float* dst = xd + static_cast<size_t>(b) * (nxo + 2 * E);
-    const float* ph = part_h + static_cast<size_t>(b) * 2 * nchunks * PLh;
-    if (v < nxo) {
-        dst[v] = rf_ola_sample_d2(v, ph, env[2 * v + 1], RF_CHUNK, PLh, nchunks, 441, RF_PW);
-    } else {
-        const int e = v - nxo;
-        const int i = e < E ? e : L - 2 * E + e;
-        if (i & 1)
-            dst[v] = rf_ola_sample_d2((i - 1) >> 1, ph, env[i], RF_CHUNK, PLh, nchunks, 441, RF_PW);
-        else
-            dst[v] = rf_ola_sample_d2_slots(RF_PW / 2 + i, part_o + static_cast<size_t>(b) * 2 * nslots * PLh, env[i], T,
-                                            RF_CHUNK, PLh, c_tail, nslots, 441, RF_PW);
-    }
+    if (v >= nxo) return;
+    xd[static_cast<size_t>(b) * (nxo + 2 * E) + v] =
+        rf_ola_sample_d2(v, part_h + static_cast<size_t>(b) * 2 * nchunks * PLh, env[2 * v + 1], RF_CHUNK, PLh, nchunks, 441,
+                         RF_PW);
+}
+__global__ void k_ola_assemble_strips(const float* __restrict__ part_h, const float* __restrict__ part_o,
+                                      const float* __restrict__ env, int T, int PLh, int nchunks, int c_tail, int nslots,
+                                      int L, int nxo, int E, float* __restrict__ xd) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (e >= 2 * E) return;
+    const int i = e < E ? e : L - 2 * E + e;
+    float r;
+    if (i & 1)
+        r = rf_ola_sample_d2((i - 1) >> 1, part_h + static_cast<size_t>(b) * 2 * nchunks * PLh, env[i], RF_CHUNK, PLh, nchunks,
+                             441, RF_PW);
+    else
+        r = rf_ola_sample_d2_slots(RF_PW / 2 + i, part_o + static_cast<size_t>(b) * 2 * nslots * PLh, env[i], T, RF_CHUNK, PLh,
+                                   c_tail, nslots, 441, RF_PW);
+    xd[static_cast<size_t>(b) * (nxo + 2 * E) + nxo + e] = r;
 }
 
 // 1-D TMA bulk copy of n floats starting at src (any 4-byte alignment) into shared memory: the copy starts at the enclosing
@@ -948,7 +954,6 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
     const size_t smem_ih = smem_i, smem_fh = smem_f;
 #endif
     const dim3 grid_i(w.nchunks * 2, B), grid_f(((T + 1) / 2) * 2, B), grid_a((L + 255) / 256, B);
-    const dim3 grid_a2((dg.nxo + 2 * dg.E + 255) / 256, B);
     k_envelope<<<(L + 255) / 256, 256, 0, st>>>(p->d_win2, T, h.H, h.W, L, w.env);
     RF_CUDA_LAUNCH_CHECK("k_envelope");
     for (int it = 0; it <= n_iter; ++it) {
@@ -979,8 +984,12 @@ static int gl_loop(rf_plan* p, const gl_ws& w, int B, int T, int n_iter, float m
             RF_CUDA_TRY(prof->mark(1, 0, st));
         }
         if (half)
-            k_ola_assemble_dec<<<grid_a2, 256, 0, st>>>(w.part, w.part_e, w.env, T, PLh, w.nchunks, dg.c_tail, dg.nslots, L,
-                                                        dg.nxo, dg.E, w.xd);
+        {
+            k_ola_assemble_dec<<<dim3((dg.nxo + 255) / 256, B), 256, 0, st>>>(w.part, w.env, PLh, w.nchunks, dg.nxo, dg.E, w.xd);
+            RF_CUDA_LAUNCH_CHECK("k_ola_assemble_dec");
+            k_ola_assemble_strips<<<dim3((2 * dg.E + 255) / 256, B), 256, 0, st>>>(w.part, w.part_e, w.env, T, PLh, w.nchunks,
+                                                                                   dg.c_tail, dg.nslots, L, dg.nxo, dg.E, w.xd);
+        }
         else
             k_ola_assemble<<<grid_a, 256, 0, st>>>(w.part, w.env, T, RF_CHUNK, w.PL, w.nchunks, h.H, h.W, L, d_wave);
         RF_CUDA_LAUNCH_CHECK("k_ola_assemble");
