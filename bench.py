@@ -298,8 +298,9 @@ def main() -> None:
     clips = B * world
     value = clips / (ms_step / 1e3)
     pk = peaks()
-    names = ["k_istft_chunk", "k_ola_assemble", "k_stft_pair"]     # kernel classes: iSTFT (k_istft_edge + k_istft_half in the loop,
-    # k_istft_chunk for the last full-rate pass), overlap-add assembly, STFT (k_stft_edge + k_stft_half)
+    names = ["k_istft_chunk", "k_ola_assemble", "k_stft_pair"]     # kernel classes: iSTFT (k_istft_half in the loop — every chunk
+    # at half rate plus the edge chunks on the other sample parity — and k_istft_chunk for the last full-rate pass), overlap-add
+    # assembly (k_ola_assemble_dec + k_ola_assemble_strips), STFT (k_stft_edge + k_stft_half)
     per_launch_bytes = [B * 12.0 * F_LIVE * T_FRAMES + B * 4.0 * L_WAVE, 0.0, B * 24.0 * F_LIVE * T_FRAMES + B * 4.0 * L_WAVE]
     dom = int(np.argmax(acc))
     dom_ms = acc[dom] / max(launches[dom], 1)
@@ -334,7 +335,10 @@ def main() -> None:
         "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-        "e2e": e2e, "gpu_launches": int((sum(launches) + 2) * args.steps), "roofline": roofline,
+        # kernels per step of the hybrid loop: one iSTFT launch per pass, two assembly launches (one on the last, full-rate
+        # pass), edge + half-rate STFT launches, plus envelope, inverse mel and the angle gather
+        "e2e": e2e, "gpu_launches": int((launches[0] + 2 * launches[1] - 1 + 2 * launches[2] + 3) * args.steps),
+        "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
