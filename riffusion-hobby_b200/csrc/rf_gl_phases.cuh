@@ -11,10 +11,11 @@
 // (position a*441 + b*49 + c).  One CTA handles one "group" (r in {0,2} or r in {1,3}) so
 // that a bin and its Hermitian partner N-k live in the same CTA.
 //
-// Pass order and thread mapping are chosen for conflict-free shared memory:
-//   forward: radix-9 over b fused with gather/window/modulate (lanes run over a: sample stride
-//            441 is odd) -> radix-10 over a (lanes over c) -> radix-49 over c (lane stride 49)
-//   inverse: radix-49 -> radix-10 -> radix-9 fused with demodulate/window/overlap-add.
+// Pass order and thread mapping are chosen for few shared-memory bank conflicts:
+//   forward: radix-9 over b fused with gather/window/modulate (items (a, c) in the plan's annealed slot order,
+//            rf_pass_b_perm.inc) -> radix-10 / radix-5 over a (lanes over consecutive positions) -> radix-49 over c as two
+//            7-thread phases (lane stride 49 = 1 mod 16 eight-byte banks)
+//   inverse: radix-49 -> radix-10 / 5 -> radix-9 fused with demodulate/window/overlap-add.
 #pragma once
 #include <math.h>
 #include <stddef.h>
@@ -517,8 +518,9 @@ RF_HD float rf_ola_sample_d2(int v, const float* part, float env, int G, int PLh
 //     full rate, every other pair reads the odd-sample waveform xo;
 //   * inverse STFT: the frames that overlap the strips are frames <= 15 (chunk 0) and frames >= T-16 (frame t covers
 //     samples [tH - W/2, tH + W/2) and the tail strip starts at (T-1)H - W - H), i.e. chunks >= c_tail = (T-16)/G;
-//     those chunks are ALSO evaluated at full rate into `nslots` extra partial-sum slots (slot 0 = chunk 0, slot s =
-//     chunk c_tail + s - 1).
+//     those chunks are evaluated a second time on the OTHER sample parity of the half-rate grid (the inverse transform
+//     is exact on any sample subset) into `nslots` extra partial-sum slots (slot 0 = chunk 0, slot s = chunk c_tail + s - 1);
+//     the two parities interleaved are the full-rate strips.
 struct rf_gl_dec_geom {
     int E, pr_tail, c_tail, nslots, n_edge_pairs, nxo;
 };

@@ -201,7 +201,7 @@ def test_griffinlim_og_beat_32_iters_vs_torchaudio(conv, ta, golden):
 
 @pytest.mark.parametrize("T_,n_iter,B", [(64, 4, 1), (131, 6, 2), (512, 8, 1)])
 def test_griffinlim_decimated_loop_vs_full_rate(conv, ta, T_, n_iter, B):
-    """The half-rate inner loop (odd samples + full-rate edge strips) is a re-association of the same
+    """The half-rate inner loop (odd samples + full-rate edge strips built from both sample parities) is a re-association of the same
     arithmetic: against the full-rate loop of the same library, the fp64 oracle and torchaudio."""
     from oracle import audio_oracle as ao
     from riffusion.spectrogram_converter import SpectrogramConverter, get_plan

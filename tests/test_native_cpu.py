@@ -204,7 +204,7 @@ def test_emulated_griffinlim_matches_torchaudio(hostemu, full_band, T_, n_iter):
 
 @pytest.mark.parametrize("T_,n_iter", [(64, 3), (75, 4), (97, 8)])
 def test_emulated_decimated_griffinlim(hostemu, T_, n_iter):
-    """The half-rate inner loop (odd samples + two full-rate edge strips) against the full-rate loop,
+    """The half-rate inner loop (odd samples + two full-rate edge strips built from both sample parities) against the full-rate loop,
     the fp64 oracle and torchaudio.  T_=64 is the smallest eligible clip (c_tail = 3: frames >= T-16 reach the tail strip), 75 / 97 have odd frame counts
     and ragged last chunks."""
     import torchaudio
