@@ -1005,7 +1005,7 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     static rf_dev_once once;
     const cudaError_t aerr = rf_set_smem_once(once, k_flash_attn<DPAD, NV, NS>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn): ") + cudaGetErrorString(aerr));
-    RF_LAUNCH_PDL("k_flash_attn", (k_flash_attn<DPAD, NV, NS>), grid, dim3(320), smem, st, mq, mk, mv, p);
+    RF_LAUNCH_PDL("k_flash_attn", (k_flash_attn<DPAD, NV, NS>), grid, dim3(320), smem, st, grid.x * grid.y * grid.z <= 600u, mq, mk, mv, p);
     return RF_OK;
 }
 
@@ -1021,7 +1021,8 @@ int launch_attn1(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
     static rf_dev_once once;
     const cudaError_t aerr = rf_set_smem_once(once, k_flash_attn1<DPAD, NV, NKS, NVS, NG>, int(smem));
     if (aerr != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("cudaFuncSetAttribute(k_flash_attn1): ") + cudaGetErrorString(aerr));
-    RF_LAUNCH_PDL("k_flash_attn1", (k_flash_attn1<DPAD, NV, NKS, NVS, NG>), grid, dim3(96 + 128 * NG), smem, st, mq, mk, mv, p);
+    RF_LAUNCH_PDL("k_flash_attn1", (k_flash_attn1<DPAD, NV, NKS, NVS, NG>), grid, dim3(96 + 128 * NG), smem, st,
+                  grid.x * grid.y * grid.z <= 600u, mq, mk, mv, p);
     return RF_OK;
 }
 
@@ -1045,7 +1046,8 @@ int launch_attn_short(const CUtensorMap& mq, const CUtensorMap& mk, const CUtens
     const int nqb = (p.Nq + TQ - 1) / TQ;
     const int n_items = nqb * p.heads * B;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    RF_LAUNCH_PDL("k_attn_short", (k_attn_short<DPAD, NV>), dim3(grid), dim3(160), smem, st, mq, mk, mv, p, n_items, nqb);
+    RF_LAUNCH_PDL("k_attn_short", (k_attn_short<DPAD, NV>), dim3(grid), dim3(160), smem, st, n_items <= 4 * num_sms, mq, mk, mv, p,
+                  n_items, nqb);
     return RF_OK;
 }
 

@@ -53,24 +53,27 @@ inline cudaError_t rf_set_smem_once(rf_dev_once& o, F* func, int bytes) {
 //   * a kernel launched through RF_LAUNCH_PDL executes rf_pdl_wait() in EVERY thread before its first global-memory access
 //     (reads of the producer's output and writes that could overtake the producer's reads alike);
 //   * everything else is launched the ordinary way and therefore still waits for full completion of its predecessor.
-// Measured on the B200 (scratch/r2_run16.sh, one CFG evaluation as a CUDA graph): 2 images 5.80 -> 5.55 ms (-4 %), 64 images
-// 72.7 -> 73.7 ms (+1 %: at the benchmarked batch the kernels are long, and early-resident dependents only take resources
-// from the tail of the running grid).  OFF by default; RF_PDL=1 in the environment enables it (single-request latency).
-// Without the attribute the device instructions are no-ops.
+// Measured on the B200 (scratch/r2_run16.sh, one CFG evaluation as a CUDA graph, attribute on every launch): 2 images
+// 5.80 -> 5.55 ms (-4 %), 64 images 72.7 -> 73.7 ms (+1 %: at the benchmarked batch the kernels are long, and early-resident
+// dependents only take resources from the tail of the running grid).  Hence the default mode: the attribute goes on launches
+// that cannot fill the GPU anyway (`small`: a couple of waves at most — the single-request regime) and stays off otherwise.
+// RF_PDL in the environment: 0 = never, 1 = small launches (default), 2 = every instrumented launch.  Without the attribute
+// the device instructions are no-ops.
 #include <cstdlib>
-inline bool rf_pdl_enabled() {
-    static const bool on = [] {
+inline int rf_pdl_mode() {
+    static const int mode = [] {
         const char* e = std::getenv("RF_PDL");
-        return e ? std::atoi(e) != 0 : false;
+        return e ? std::atoi(e) : 1;
     }();
-    return on;
+    return mode;
 }
+inline bool rf_pdl_use(bool small) { return rf_pdl_mode() >= 2 || (rf_pdl_mode() == 1 && small); }
 #if defined(__CUDACC__)
 __device__ __forceinline__ void rf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void rf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 // kernel may be a template-id in parentheses; extra attributes (cluster dimension) go in front of the PDL one
-#define RF_LAUNCH_PDL_ATTRS(name, kernel, grid, block, smem, st, attr_arr, n_attr, ...)                                   \
+#define RF_LAUNCH_PDL_ATTRS(name, kernel, grid, block, smem, st, small, attr_arr, n_attr, ...)                                   \
     do {                                                                                                             \
         cudaLaunchConfig_t _cfg = {};                                                                                \
         _cfg.gridDim = (grid);                                                                                       \
@@ -80,12 +83,12 @@ __device__ __forceinline__ void rf_pdl_trigger() { asm volatile("griddepcontrol.
         (attr_arr)[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                      \
         (attr_arr)[n_attr].val.programmaticStreamSerializationAllowed = 1;                                               \
         _cfg.attrs = (attr_arr);                                                                                        \
-        _cfg.numAttrs = (n_attr) + (rf_pdl_enabled() ? 1 : 0);                                                        \
+        _cfg.numAttrs = (n_attr) + (rf_pdl_use(small) ? 1 : 0);                                                        \
         const cudaError_t _le = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                                      \
         if (_le != cudaSuccess) return rf_fail(RF_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_le)); \
     } while (0)
-#define RF_LAUNCH_PDL(name, kernel, grid, block, smem, st, ...)                                                       \
+#define RF_LAUNCH_PDL(name, kernel, grid, block, smem, st, small, ...)                                                       \
     do {                                                                                                             \
         cudaLaunchAttribute _attr[1];                                                                                \
-        RF_LAUNCH_PDL_ATTRS(name, kernel, grid, block, smem, st, _attr, 0, __VA_ARGS__);                             \
+        RF_LAUNCH_PDL_ATTRS(name, kernel, grid, block, smem, st, small, _attr, 0, __VA_ARGS__);                             \
     } while (0)

@@ -613,8 +613,8 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
         }
-        RF_LAUNCH_PDL_ATTRS("k_tc_gemm", (k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES>), grid, dim3(GEMM_THREADS), smem, st, attr,
-                            PAIR ? 1 : 0, a0, a1, b, p);
+        RF_LAUNCH_PDL_ATTRS("k_tc_gemm", (k_tc_gemm<BN, STAGES, PAIR, SLABS, BRES>), grid, dim3(GEMM_THREADS), smem, st,
+                            n_tiles <= 2 * num_sms, attr, PAIR ? 1 : 0, a0, a1, b, p);
     }
     if (prof) {
         RF_CUDA_TRY(cudaEventRecord(e1, st));

@@ -752,13 +752,13 @@ extern "C" int rf_group_norm_cat_f16(const void* x, const void* x2, int C1, int 
     float* part = d_scratch + static_cast<size_t>(B) * groups * 2;     // [B][nslabs][G][2]
     const size_t smem = static_cast<size_t>(PPI) * (C / 2) * sizeof(float2);
     dim3 grid(nslabs, B);
-    RF_LAUNCH_PDL("k_gn_partial_v", k_gn_partial_v, grid, dim3(threads), smem, st, static_cast<const __half*>(x),
+    RF_LAUNCH_PDL("k_gn_partial_v", k_gn_partial_v, grid, dim3(threads), smem, st, grid.x * grid.y <= 600u, static_cast<const __half*>(x),
                   static_cast<const __half*>(x2), C1, HW, C, groups, slab, nslabs, part);
     if (groups > 64 || threads < groups) return rf_fail(RF_ERR_UNSUPPORTED, "rf_group_norm_f16: at most 64 groups (and not more groups than threads)");
     // tanh form by default: measured on the full-size UNet, both forms leave the kernels AT the fp16-storage floor
     // (1.420e-3 vs 1.418e-3 from the fp32 oracle) and the exp form costs +0.4 ms per evaluation at batch 64
     static const int silu_form = getenv("RF_SILU_EXACT") ? 1 : 2;
-    RF_LAUNCH_PDL("k_gn_apply_v", k_gn_apply_v, grid, dim3(threads), size_t(0), st, static_cast<const __half*>(x),
+    RF_LAUNCH_PDL("k_gn_apply_v", k_gn_apply_v, grid, dim3(threads), size_t(0), st, grid.x * grid.y <= 600u, static_cast<const __half*>(x),
                   static_cast<const __half*>(x2), C1, static_cast<const float*>(part), nslabs,
                   1.f / (static_cast<float>(HW) * (C / groups)), eps, static_cast<const __half*>(gamma),
                   static_cast<const __half*>(beta), HW, C, groups, act ? silu_form : 0, slab, static_cast<__half*>(y));
@@ -777,9 +777,9 @@ extern "C" int rf_layer_norm_f16(const void* x, int rows, int C, const void* gam
         const __half *xp = static_cast<const __half*>(x), *gp = static_cast<const __half*>(gamma),
                      *bp = static_cast<const __half*>(beta);
         __half* yp = static_cast<__half*>(y);
-        if (C == 320) RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<8>, dim3(blocks), dim3(256), size_t(0), st, xp, gp, bp, rows, eps, yp);
-        else if (C == 640) RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<16>, dim3(blocks), dim3(256), size_t(0), st, xp, gp, bp, rows, eps, yp);
-        else RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<32>, dim3(blocks), dim3(256), size_t(0), st, xp, gp, bp, rows, eps, yp);
+        if (C == 320) RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<8>, dim3(blocks), dim3(256), size_t(0), st, blocks <= 600, xp, gp, bp, rows, eps, yp);
+        else if (C == 640) RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<16>, dim3(blocks), dim3(256), size_t(0), st, blocks <= 600, xp, gp, bp, rows, eps, yp);
+        else RF_LAUNCH_PDL("k_layernorm_v", k_layernorm_v<32>, dim3(blocks), dim3(256), size_t(0), st, blocks <= 600, xp, gp, bp, rows, eps, yp);
         return RF_OK;
     }
     k_layernorm<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -1,9 +1,10 @@
 #!/bin/bash
-# PDL A/B: evaluation time at batch 32 and 1 with and without the launch attribute, then the tensor-core / UNet parity tests
+# PDL A/B: evaluation time at batch 32 and 1 with RF_PDL = 1 (small launches only, the default), 0 (never), 2 (every
+# instrumented launch), then the tensor-core / UNet parity tests
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 for b in 32 1; do
-  for pdl in 1 0; do
+  for pdl in 1 0 2; do
     echo "== B=$b RF_PDL=$pdl"; RF_PDL=$pdl timeout -k 10 300 python scratch/prof_eval.py $b 2>&1 | tail -1
   done
 done 2>&1 | tee gpurun_out/pdl_ab.txt
