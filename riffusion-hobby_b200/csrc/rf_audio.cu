@@ -468,7 +468,7 @@ k_stft_pair(rf_gl_tables tb, const float* __restrict__ x, int L, int T, int hop,
 
 // hybrid decimated loop, two launches: k_stft_edge, grid (n_edge_pairs*2, B): the edge pairs (3 head pairs, then the
 // pairs from pr_tail on) at full rate from the strips of xd; k_stft_half, grid ((npairs - n_edge_pairs)*2, B): the rest
-// from the odd samples xo at half rate (45 KB of shared memory, <= 85 registers: 3 CTAs/SM)
+// from the odd samples xo at half rate (55 KB of shared memory with the two TMA staging buffers, <= 85 registers: 3 CTAs/SM)
 __global__ void __launch_bounds__(RF_NT, 2)
 k_stft_edge(rf_gl_tables tb, const float* __restrict__ xd, int L, int T, int hop, int nxo, int E, int pr_tail,
             rf_c32* __restrict__ R) {
