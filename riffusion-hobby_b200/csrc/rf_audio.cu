@@ -205,6 +205,8 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
     else if (s == "bt") { src = h.t10.bt.data(); n = h.t10.bt.size() * 4; }
     else if (s == "ab_inv") { src = h.t10.ab_inv.data(); n = h.t10.ab_inv.size() * 4; }
     else if (s == "ab_fwd") { src = h.t10.ab_fwd.data(); n = h.t10.ab_fwd.size() * 4; }
+    else if (s == "items") { src = h.t10.items.data(); n = h.t10.items.size() * 4; }
+    else if (s == "items2") { src = h.t5.items.data(); n = h.t5.items.size() * 4; }
     else if (s == "bt2") { src = h.t5.bt.data(); n = h.t5.bt.size() * 4; }
     else if (s == "ab2_inv") { src = h.t5.ab_inv.data(); n = h.t5.ab_inv.size() * 4; }
     else if (s == "ab2_fwd") { src = h.t5.ab_fwd.data(); n = h.t5.ab_fwd.size() * 4; }

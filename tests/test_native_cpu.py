@@ -260,3 +260,36 @@ def test_decimation_eligibility(hostemu):
     p = hostemu.emu_plan_create(ctypes.byref(desc), win.ctypes.data, fb.ctypes.data)
     assert p and hostemu.emu_plan_decimate(p) == 0
     hostemu.emu_plan_destroy(p)
+
+
+def test_radix9_slot_order_is_a_permutation_with_fewer_bank_conflicts(native_lib):
+    """csrc/rf_pass_b_perm.inc (scratch/gen_pass_b_perm.py): the slot -> item order of the radix-9 pass covers every (a, c)
+    item once, its sample index is n'(a, 0, c), and by the exact shared-memory bank model (32 banks x 4 B; 8-byte accesses in
+    half-warp phases) a pass costs fewer wavefronts than with lanes running over a, the round-1 order."""
+    from riffusion.spectrogram_converter import get_plan
+    from riffusion.spectrogram_params import SpectrogramParams
+
+    plan = get_plan(SpectrogramParams(), full_band=False)
+
+    def cost(NA, items_ac):
+        Wn, SB, SC, off1 = NA * 441, NA * 49, NA * 9, (441 if NA == 10 else 221)
+        tot = 0
+        for w0 in range(0, len(items_ac), 32):
+            grp = items_ac[w0:w0 + 32]
+            for b in range(9):
+                n0 = [((441 * a + SC * c) % Wn + SB * b) % Wn for a, c in grp]
+                for sh in (0, off1):
+                    tot += np.bincount([(n + sh) % 32 for n in n0], minlength=32).max()
+                v = [(a * 441 + c + 49 * b) % 16 for a, c in grp]
+                tot += np.bincount(v[:16], minlength=16).max() + (np.bincount(v[16:], minlength=16).max() if len(v) > 16 else 0)
+        return int(tot)
+
+    for NA, name in ((10, "items"), (5, "items2")):
+        it = plan.table(name, np.uint32, (49 * NA,))
+        vpos, base = it & 4095, it >> 12
+        a, c = vpos // 441, vpos % 441
+        assert c.max() < 49 and sorted((a * 49 + c).tolist()) == list(range(49 * NA))
+        assert np.array_equal(base, (441 * a + (NA * 9) * c) % (NA * 441))
+        shipped = cost(NA, list(zip(a.tolist(), c.tolist())))
+        lanes_over_a = cost(NA, [(t % NA, t // NA) for t in range(49 * NA)])
+        assert shipped < 0.9 * lanes_over_a, (NA, shipped, lanes_over_a)
