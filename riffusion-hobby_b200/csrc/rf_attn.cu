@@ -40,7 +40,6 @@ struct AttnParams {
     long out_pitch;       // C
     int causal;           // 1: key j is visible to query i only if j <= i (CLIP text encoder); short-key kernel only
     int poly_exp;         // 1: half of the exponentials of the single-pass kernel on the FMA pipe (experiment, RF_ATTN_POLY=1)
-    int defer_max;        // 1: single-pass kernel starts the exponentials before the tile maximum is known (RF_ATTN_DEFER_MAX)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -346,9 +345,6 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 //     exponentials, so the next Q K^T overlaps the softmax arithmetic.
 // TMEM: S0 | S1 | O_A (NV+16 columns) | O_B (NV+16 columns).
 constexpr float RESCALE_LOG2 = 4.f;
-#ifndef RF_ATTN_DEFER_MAX_DEFAULT
-#define RF_ATTN_DEFER_MAX_DEFAULT 0
-#endif
 
 // NG softmax groups (2 or 4) take the key tiles round-robin; a tile is TKT = 256/NG keys, so the NG score buffers always
 // fill TMEM columns [0, 256) and O_g sits at 256 + g*(NV+16).  NG = 4 (head dim <= 48) puts four independent warps on
@@ -568,90 +564,6 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 for (int i = 0; i < TKT; ++i)
                     if (i >= kmax) v[i] = 0xff800000u;   // -inf
             }
-            // exponentials of the tile against the reference maximum mcv = m_ref * c -> fp16 P in shared memory; returns the
-            // largest argument seen (four chains: the maximum rides along on the ALU pipe, the MUFU pipe is the one that counts)
-            auto do_exps = [&](float mcv) -> float {
-                float am[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-                for (int c0 = 0; c0 < TKT; c0 += 8) {
-                    uint32_t pk[4];
-                    if (p.poly_exp && (c0 & 8)) {
-                        // every second group of 8 keys: 2^a on the FMA / ALU pipes instead of MUFU (the exponentials of a key
-                        // tile are the whole MUFU budget of that tile): n = round(a) by the magic-number add, 2^(a - n) by a
-                        // degree-3 polynomial on [-0.5, 0.5] (7.5e-5 relative, below the 4.9e-4 fp16 rounding of P), exponent
-                        // bits of n added to the result.  a <= RESCALE_LOG2; a < -24 is clamped (2^-24 = fp16's smallest).
-#pragma unroll
-                        for (int i = 0; i < 8; i += 2) {
-                            float e[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const float a = fmaxf(fmaf(__uint_as_float(v[c0 + i + u]), c, -mcv), -24.f);
-                                am[(i >> 1) & 3] = fmaxf(am[(i >> 1) & 3], a);
-                                const float t = a + 12582912.f;
-                                const float f = a - (t - 12582912.f);
-                                const float q = fmaf(fmaf(fmaf(0.05517144f, f, 0.24261071f), f, 0.69326097f), f, 0.99992812f);
-                                e[u] = __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
-                            }
-                            const __half2 h = __floats2half2_rn(e[0], e[1]);
-                            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                    } else
-#pragma unroll
-                    for (int i = 0; i < 8; i += 2) {
-                        // the argument (<= RESCALE_LOG2) is formed in fp32 and rounded once to fp16; P is fp16 anyway
-                        const float a0 = fmaf(__uint_as_float(v[c0 + i]), c, -mcv);
-                        const float a1 = fmaf(__uint_as_float(v[c0 + i + 1]), c, -mcv);
-                        am[(i >> 1) & 3] = fmaxf(am[(i >> 1) & 3], fmaxf(a0, a1));
-#ifdef RF_ATTN_EXP_F16X2
-                        const __half2 arg = __floats2half2_rn(a0, a1);
-                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i >> 1]) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
-#else
-                        float e0, e1;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-                        const __half2 h = __floats2half2_rn(e0, e1);
-                        pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-#endif
-                    }
-                    const int slab = c0 >> 6, chunk = (c0 & 63) >> 3;
-                    *reinterpret_cast<uint4*>(myP + slab * TQ * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) =
-                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-                return fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3]));
-            };
-            // rescale O_g by fac (raising the reference maximum); warp-collective
-            auto rescale_O = [&](float fac) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < NVP; c0 += 16) {
-                    uint32_t o[16];
-                    tmem_ld16(t_Og + c0, o);
-                    tc::tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * fac);
-                    tmem_st16(t_Og + c0, o);
-                }
-                tmem_wait_st();
-            };
-            if (p.defer_max && n_mine > 0) {
-                // The row maximum is NOT found first: the exponentials start against the current reference right after the
-                // scores arrive (the maximum used to be a dependent ~100-cycle phase in front of every tile's MUFU work) and
-                // the largest argument falls out of the same loop.  Only if it exceeds 2^RESCALE_LOG2 — a handful of tiles
-                // per row — is the reference raised, O_g rescaled and the tile redone.
-                tc::mbar_wait(&p_empty[g], pe_phase);            // previous P V of this group done: P buffer free, O_g quiet
-                pe_phase ^= 1;
-                tc::fence_after_sync();
-                const float amax = do_exps(m_ref * c);
-                const bool grow = amax > RESCALE_LOG2;
-                if (__any_sync(0xffffffffu, grow)) {
-                    float fac = 1.f;
-                    if (grow) {
-                        fac = exp2f(-amax);
-                        m_ref += amax / c;
-                    }
-                    rescale_O(fac);
-                    do_exps(m_ref * c);
-                }
-            } else {
             float mx[8];                          // eight independent chains: the maximum is latency, not issue, bound
 #pragma unroll
             for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(v[i]);
@@ -671,9 +583,62 @@ k_flash_attn1(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 tc::mbar_wait(&p_empty[g], pe_phase);            // previous P V of this group done: P buffer free, O_g quiet
                 pe_phase ^= 1;
                 tc::fence_after_sync();
-                if (__any_sync(0xffffffffu, grow)) rescale_O(fac);
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < NVP; c0 += 16) {
+                        uint32_t o[16];
+                        tmem_ld16(t_Og + c0, o);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * fac);
+                        tmem_st16(t_Og + c0, o);
+                    }
+                    tmem_wait_st();
+                }
             }
-            do_exps(m_ref * c);
+            const float mc = m_ref * c;
+#pragma unroll
+            for (int c0 = 0; c0 < TKT; c0 += 8) {
+                uint32_t pk[4];
+                if (p.poly_exp && (c0 & 8)) {
+                    // every second group of 8 keys: 2^a on the FMA / ALU pipes instead of MUFU (the exponentials of a key
+                    // tile are the whole MUFU budget of that tile): n = round(a) by the magic-number add, 2^(a - n) by a
+                    // degree-3 polynomial on [-0.5, 0.5] (7.5e-5 relative, below the 4.9e-4 fp16 rounding of P), exponent
+                    // bits of n added to the result.  a <= RESCALE_LOG2; a < -24 is clamped (2^-24 = fp16's smallest).
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        float e[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float a = fmaxf(fmaf(__uint_as_float(v[c0 + i + u]), c, -mc), -24.f);
+                            const float t = a + 12582912.f;
+                            const float f = a - (t - 12582912.f);
+                            const float q = fmaf(fmaf(fmaf(0.05517144f, f, 0.24261071f), f, 0.69326097f), f, 0.99992812f);
+                            e[u] = __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+                        }
+                        const __half2 h = __floats2half2_rn(e[0], e[1]);
+                        pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                } else
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    // the argument (<= RESCALE_LOG2) is formed in fp32 and rounded once to fp16; P is fp16 anyway
+                    const float a0 = fmaf(__uint_as_float(v[c0 + i]), c, -mc);
+                    const float a1 = fmaf(__uint_as_float(v[c0 + i + 1]), c, -mc);
+#ifdef RF_ATTN_EXP_F16X2
+                    const __half2 arg = __floats2half2_rn(a0, a1);
+                    asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i >> 1]) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+#else
+                    float e0, e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+                    const __half2 h = __floats2half2_rn(e0, e1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+#endif
+                }
+                const int slab = c0 >> 6, chunk = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4*>(myP + slab * TQ * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
             fence_async_smem();                  // P stores -> async proxy
             tc::fence_before_sync();             // orders the tcgen05.st of a rescale before the P V issued after p_full
@@ -1147,8 +1112,6 @@ extern "C" int rf_attention_masked_f16(const void* q, const void* k, const void*
         // the FMA pipe loses.  Kept as an experiment switch (RF_ATTN_POLY=1), off by default.
         const char* e = getenv("RF_ATTN_POLY");
         p.poly_exp = (e && e[0] == '1') ? 1 : 0;
-        const char* dm = getenv("RF_ATTN_DEFER_MAX");
-        p.defer_max = dm ? (dm[0] == '1' ? 1 : 0) : RF_ATTN_DEFER_MAX_DEFAULT;
     }
     dim3 grid((Nq + TQ - 1) / TQ, heads, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
