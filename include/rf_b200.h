@@ -91,7 +91,9 @@ int rf_plan_set_decimation(rf_plan* plan, int enable);
  * "wt2_fwd"/"wt2_inv" float[2][4][win/2][2], "ph_odd" float[n_live][2]; the kernel-side forms derived from them:
  * "bt" uint32[n_live] (V offset | partner offset << 14 | self-paired << 31), "ab_inv"/"ab_fwd" float[n_live][4]
  * (per-bin phase constants of the inverse / forward pair packing), "bt2"/"ab2_inv"/"ab2_fwd" for the decimated loop,
- * "items"/"items2" uint32[49 * 10 | 49 * 5] (radix-9 pass: V position a*441 + c | first sample index << 12 of slot tau).
+ * "items"/"items2" uint32[49 * 10 | 49 * 5] (radix-9 pass: V position a*441 + c | first sample index << 12 of slot tau),
+ * "wg2_inv" float[9][245][4] (per sample of the decimated grid: window of frame t0, of frame t0+1, cos, sin) and the
+ * other-parity tables of the hybrid loop's edge chunks "wg2o_inv" (the two windows swapped), "ab2o_inv" float[n_live][4].
  * Returns RF_ERR_INVALID if
  * `bytes` does not match the table size. */
 int rf_plan_table(const rf_plan* plan, const char* name, void* dst, size_t bytes);

@@ -211,6 +211,9 @@ extern "C" int rf_plan_table(const rf_plan* p, const char* name, void* dst, size
     else if (s == "ab2_inv") { src = h.t5.ab_inv.data(); n = h.t5.ab_inv.size() * 4; }
     else if (s == "ab2_fwd") { src = h.t5.ab_fwd.data(); n = h.t5.ab_fwd.size() * 4; }
     else if (s == "ph_odd") { src = h.ph_odd.data(); n = h.ph_odd.size() * 4; }
+    else if (s == "ab2o_inv") { src = h.t5e.ab_inv.data(); n = h.t5e.ab_inv.size() * 4; }
+    else if (s == "wg2_inv") { src = h.t5.wg_inv.data(); n = h.t5.wg_inv.size() * 4; }
+    else if (s == "wg2o_inv") { src = h.t5e.wg_inv.data(); n = h.t5e.wg_inv.size() * 4; }
     else if (s == "pinv") {
         // dense min-norm operator P = fb (fb^T fb)^{-1}, built column by column with the
         // same Thomas factors the kernel uses (fp64), for tests

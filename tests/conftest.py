@@ -57,6 +57,7 @@ def hostemu():
     lib.emu_griffinlim.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_float, ctypes.c_void_p]
     lib.emu_plan_decimate.argtypes = [ctypes.c_void_p]
+    lib.emu_istft_other_parity.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     lib.emu_griffinlim2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
     return lib

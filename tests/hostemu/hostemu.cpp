@@ -232,6 +232,33 @@ void emu_stft_d2(void* p, const float* x, int L, float* spec) {
 }
 
 // debug/validation: one inverse STFT (mode 0: spec = S * cur) at full (NA=10 -> wave[L]) or half rate (-> wave[(L-1)/2])
+// debug/validation: one inverse STFT (mode 0) of EVERY chunk on the other sample parity of the half-rate grid (tables t5e):
+// even[v] = x[2v], v < (L + 1) / 2 — the samples the regular half-rate pass skips
+void emu_istft_other_parity(void* p, const float* lin, const float* angles, int T, float* even) {
+    auto* h = static_cast<rf_plan_host*>(p);
+    const size_t n = static_cast<size_t>(T) * h->n_live;
+    std::vector<float> S(n);
+    std::vector<rf_c32> R1(n);
+    for (int t = 0; t < T; ++t)
+        for (int j = 0; j < h->n_live; ++j) {
+            const size_t src = static_cast<size_t>(h->bins[j]) * T + t;
+            S[static_cast<size_t>(t) * h->n_live + j] = lin[src];
+            R1[static_cast<size_t>(t) * h->n_live + j] = c_make(angles[2 * src], angles[2 * src + 1]);
+        }
+    const int G = RF_CHUNK, nchunks = (T + G - 1) / G;
+    const int PLh = ((G - 1) * h->H + h->W + 1) / 2;
+    std::vector<float> part(static_cast<size_t>(2) * nchunks * PLh, 0.f);
+    for (int c = 0; c < nchunks; ++c)
+        for (int g = 0; g < 2; ++g)
+            emu_istft_chunk<5>(*h, S.data(), R1.data(), nullptr, 0, 0.f, T, PLh, g, c,
+                               &part[(static_cast<size_t>(g) * nchunks + c) * PLh], true);
+    const std::vector<float> win2 = window_sq(*h);
+    const int L = h->H * (T - 1);
+    for (int i = 0; i < L; i += 2)      // slot s = chunk s: c_tail = 1 makes rf_ola_sample_d2_slots' slot map the identity
+        even[i >> 1] = rf_ola_sample_d2_slots(h->W / 2 + i, part.data(), rf_envelope(i, win2.data(), T, h->H, h->W), T, G, PLh,
+                                              1, nchunks, h->H, h->W);
+}
+
 void emu_istft(void* p, const float* lin, const float* angles, int T, int half, float* wave) {
     auto* h = static_cast<rf_plan_host*>(p);
     const size_t n = static_cast<size_t>(T) * h->n_live;

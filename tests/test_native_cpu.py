@@ -293,3 +293,37 @@ def test_radix9_slot_order_is_a_permutation_with_fewer_bank_conflicts(native_lib
         shipped = cost(NA, list(zip(a.tolist(), c.tolist())))
         lanes_over_a = cost(NA, [(t % NA, t // NA) for t in range(49 * NA)])
         assert shipped < 0.9 * lanes_over_a, (NA, shipped, lanes_over_a)
+
+
+def test_other_parity_tables_and_inverse_transform(native_lib, hostemu):
+    """The hybrid Griffin-Lim loop fills its full-rate edge strips from two half-rate inverse transforms, one per sample
+    parity.  (1) The other-parity tables: windows swapped, alpha = conj(ph po), beta = i conj(ph).
+    (2) The emulated half-rate inverse transform on the other parity, run over EVERY chunk, reproduces the even samples of
+    torch.istft — the inverse transform of a band-limited spectrum is exact on any sample subset."""
+    from riffusion.spectrogram_converter import get_plan
+    from riffusion.spectrogram_params import SpectrogramParams
+
+    plan = get_plan(SpectrogramParams(), full_band=False)
+    n_live = plan.info.n_live
+    bins = plan.table("bins", np.int32, (n_live,))
+    ph, po = np.exp(-2j * np.pi * 3 * bins / 8), np.exp(-2j * np.pi * bins / N)
+    ab = plan.table("ab2o_inv", np.float32, (n_live, 4)).astype(np.float64)
+    assert np.abs(ab[:, 0] + 1j * ab[:, 1] - np.conj(ph * po)).max() < 1e-7
+    assert np.abs(ab[:, 2] + 1j * ab[:, 3] - 1j * np.conj(ph)).max() < 1e-7
+    w2, w2o = plan.table("wg2_inv", np.float32, (9, 245, 4)), plan.table("wg2o_inv", np.float32, (9, 245, 4))
+    assert np.array_equal(w2[..., 0], w2o[..., 1]) and np.array_equal(w2[..., 1], w2o[..., 0])
+    assert np.array_equal(w2[..., 2:], w2o[..., 2:])
+
+    p, fb = _emu_plan(hostemu, False)
+    for T_ in (40, 51):                                   # even and odd frame counts, ragged last chunk
+        torch.manual_seed(T_)
+        live = torch.from_numpy((fb != 0).any(axis=1))[:, None]
+        mag = torch.rand(F, T_) * 10 * live
+        ang = torch.exp(2j * np.pi * torch.rand(F, T_)).to(torch.complex64)
+        L = H * (T_ - 1)
+        ref = torch.istft((mag * ang).to(torch.complex64), N, H, W, torch.hann_window(W), length=L).numpy()
+        even = np.zeros((L + 1) // 2, np.float32)
+        hostemu.emu_istft_other_parity(p, mag.numpy().ctypes.data, torch.view_as_real(ang).contiguous().numpy().ctypes.data,
+                                       T_, even.ctypes.data)
+        assert np.abs(even - ref[0::2]).max() < 2e-6 * np.abs(ref).max()
+    hostemu.emu_plan_destroy(p)
