@@ -665,13 +665,24 @@ k_inverse_mel(const float* __restrict__ mel, int T, int n_mels, int n_live, int 
     }
     __syncthreads();
     if (out_mode == 0) {
-        for (int tl = 0; tl < 32 && t0 + tl < T; ++tl) {
-            float* row = out + (static_cast<size_t>(b) * T + t0 + tl) * n_live;
-            for (int j = tid; j < n_live; j += blockDim.x) {
-                float acc = 0.f;
-                for (int e = binrow_ptr[j]; e < binrow_ptr[j + 1]; ++e)
-                    acc += binrow_w[e] * ys[binrow_m[e] * 33 + tl];
-                row[j] = fmaxf(acc, 0.f);
+        // bin outer, time inner: a live bin touches at most two filters (tridiagonal Gram), so its (filter, weight) pairs
+        // are fetched once and reused for the 32 time columns; for each column consecutive threads write consecutive bins
+        const int nt = min(32, T - t0);
+        float* base = out + (static_cast<size_t>(b) * T + t0) * n_live;
+        for (int j = tid; j < n_live; j += blockDim.x) {
+            const int e0 = binrow_ptr[j], e1 = binrow_ptr[j + 1];
+            if (e1 - e0 <= 2) {
+                const float w0 = e1 > e0 ? binrow_w[e0] : 0.f, w1 = e1 > e0 + 1 ? binrow_w[e0 + 1] : 0.f;
+                const float* y0 = ys + (e1 > e0 ? binrow_m[e0] : 0) * 33;
+                const float* y1 = ys + (e1 > e0 + 1 ? binrow_m[e0 + 1] : 0) * 33;
+                for (int tl = 0; tl < nt; ++tl)
+                    base[static_cast<size_t>(tl) * n_live + j] = fmaxf(fmaf(w1, y1[tl], w0 * y0[tl]), 0.f);
+            } else {
+                for (int tl = 0; tl < nt; ++tl) {
+                    float acc = 0.f;
+                    for (int e = e0; e < e1; ++e) acc += binrow_w[e] * ys[binrow_m[e] * 33 + tl];
+                    base[static_cast<size_t>(tl) * n_live + j] = fmaxf(acc, 0.f);
+                }
             }
         }
     } else {
